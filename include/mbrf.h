@@ -1,0 +1,174 @@
+/*
+ * mbrf.h — C ABI of libmbrf.so, the B200 (sm_100a) engine behind the MATLAB/MEX
+ * signatures of shanghong/Multiband-RF-pulse-Design's data-parallel hot paths.
+ *
+ * Plain C: pointers, sizes and scalars only — no torch, no C++ types.  Every entry
+ * point names the reference interface it replaces (file:line under /root/reference).
+ * All functions return MBRF_OK (0) or a negative MBRF_E* code; the message of the
+ * last failure on the calling thread is available from mbrf_last_error().
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns
+ * MBRF_ENODEVICE.
+ *
+ * Pointer conventions
+ *   *_host entry points (no suffix)  : host memory, pageable or pinned; the call is
+ *                                      synchronous and performs its own H2D / D2H.
+ *   *_device entry points            : device memory of the current device; work is
+ *                                      enqueued on `stream` (a cudaStream_t passed as
+ *                                      void*, NULL = legacy default stream) and NOT
+ *                                      synchronised.
+ * Arrays are column-major doubles; complex data is split into real / imaginary
+ * planes exactly as the pre-R2018a MEX API hands them over (mxGetPr / mxGetPi).
+ */
+#ifndef MBRF_H
+#define MBRF_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBRF_OK          0
+#define MBRF_EINVAL     -1   /* bad argument (sizes, NULL where data is required, bad mode) */
+#define MBRF_ENODEVICE  -2   /* no usable CUDA device: the engine has no CPU path */
+#define MBRF_ECUDA      -3   /* CUDA runtime error, text in mbrf_last_error() */
+#define MBRF_ENOMEM     -4
+
+#define MBRF_GAMMA_C13  6726.1   /* blochC.c:6 */
+#define MBRF_GAMMA_H1   26754.0  /* blochH.c:6 */
+#define MBRF_TWOPI      6.283185 /* blochC.c:7 — the reference's truncated 2*pi, kept for parity */
+
+/* ---- library / device ---------------------------------------------------- */
+const char *mbrf_version(void);
+const char *mbrf_last_error(void);
+int  mbrf_device_count(void);             /* >= 0, never fails */
+int  mbrf_set_device(int device);         /* device used by this host thread's later calls */
+int  mbrf_device_sm_count(int *sm_count); /* multiprocessors of the current device */
+/* counts kernel launches made by this library on the calling process (for bench `gpu_launches`) */
+unsigned long long mbrf_launch_count(void);
+
+/* Diagnostic: FP64 FMA throughput of the current device (TFLOP/s, FMA = 2 flops), measured with a
+ * DFMA-only kernel.  The Bloch / SLR kernels are bound by this pipe; bench.py reports against it. */
+int  mbrf_measure_fp64_peak(double *tflops, double *kernel_ms);
+
+/* ---- Bloch simulation ---------------------------------------------------- */
+
+/*
+ * Replaces  int blochsimfz(...)  — blochC.c:422-511 / blochH.c:422-511.
+ * Same argument order and meaning, plus the trailing gyromagnetic ratio that
+ * distinguishes blochC (MBRF_GAMMA_C13) from blochH (MBRF_GAMMA_H1).
+ *
+ *   b1real,b1imag,xgrad,ygrad,zgrad,tsteps : ntime samples each (G, G/cm, s);
+ *        b1imag / ygrad / zgrad may be NULL meaning all-zero.
+ *   dfreq  : nfreq off-resonances (Hz);  dxpos,dypos,dzpos : npos positions (cm),
+ *        dypos / dzpos may be NULL meaning all-zero.
+ *   mode   : bit0 steady state, bit1 record every sample (blochC.c:772-781).
+ *   mx,my,mz : IN/OUT, ntout*npos*nfreq doubles, ntout = (mode&2) ? ntime : 1.
+ *        On entry element [ntout*(p + npos*f)] holds the initial magnetisation of
+ *        spin (p,f) (blochC.c:838-865); on return element [t + ntout*(p + npos*f)]
+ *        holds the result (blochC.c:497-499).
+ * Spins are independent; they are spread over one thread each on the current device.
+ */
+int mbrf_blochsimfz(const double *b1real, const double *b1imag,
+                    const double *xgrad, const double *ygrad, const double *zgrad,
+                    const double *tsteps, int ntime, double t1, double t2,
+                    const double *dfreq, int nfreq,
+                    const double *dxpos, const double *dypos, const double *dzpos, int npos,
+                    double *mx, double *my, double *mz, int mode, double gamma);
+
+/*
+ * Replaces the argument handling of  mexFunction  — blochC.c:514-927 — i.e. the MATLAB call
+ *   [mx,my,mz] = blochC(b1, gr, tp, t1, t2, df, dp, mode, mx0, my0, mz0)
+ * so that the MEX gateway (matlab/bloch_mex.c) only unpacks mxArrays.
+ *
+ *   b1r,b1i : ntime samples, b1i NULL for a real pulse            (blochC.c:571-587)
+ *   gr      : ngr = numel(gr) doubles, column-major ntime x {1,2,3}; missing axes are
+ *             zero; ngr not in {1,2,3}*ntime only warns in the reference (:595-638)
+ *   tp, ntp : ntp == 1 constant step; ntp == ntime: end times if strictly increasing
+ *             from 0, else intervals (:660-681); any other ntp -> MBRF_EINVAL
+ *             (the reference prints a warning and then reads out of bounds)
+ *   df, nf  : off-resonances                                       (:691-692)
+ *   dp      : column-major npos_m x npos_n; npos_n == 3 / 2 -> xyz / xy columns,
+ *             anything else -> npos_m*npos_n one-dimensional x positions (:701-758)
+ *   mode    : 0..3                                                 (:772-781)
+ *   mx0,my0,mz0,n_m0 : optional initial magnetisation, used only if all three are
+ *             non-NULL and n_m0 == npos*nf, else (0,0,1)           (:820-865)
+ *   mx,my,mz: OUT, ntout*npos*nf doubles each, layout [t + ntout*(p + npos*f)]
+ *   out_dims: OUT, the MATLAB shape of the outputs; returns ndim (2 or 3) in
+ *             out_dims[3]                                          (:880-904)
+ */
+int mbrf_bloch(const double *b1r, const double *b1i, int ntime,
+               const double *gr, int ngr,
+               const double *tp, int ntp, double t1, double t2,
+               const double *df, int nf,
+               const double *dp, int npos_m, int npos_n, int mode,
+               const double *mx0, const double *my0, const double *mz0, int n_m0,
+               double *mx, double *my, double *mz, int out_dims[4], double gamma);
+
+/*
+ * Device-resident form of mbrf_blochsimfz for callers that keep data in HBM
+ * (bench `value`, multi-GPU shards).  All pointers are device pointers.
+ *   spin0, nspins : this call simulates flattened spins s in [spin0, spin0+nspins),
+ *                   s = p + npos*f (blochC.c:468-473), which is how shards are cut.
+ *   m0x,m0y,m0z   : initial magnetisation indexed by LOCAL spin (s - spin0) with stride
+ *                   m0_stride doubles, or all NULL for (0,0,1).
+ *   mx,my,mz      : outputs indexed [t + ntout*(s - spin0)].
+ *   workspace     : device scratch of mbrf_bloch_workspace_bytes(ntime) bytes.
+ */
+unsigned long long mbrf_bloch_workspace_bytes(int ntime);
+int mbrf_bloch_device(const double *b1real, const double *b1imag,
+                      const double *xgrad, const double *ygrad, const double *zgrad,
+                      const double *tsteps, int ntime, double t1, double t2,
+                      const double *dfreq, int nfreq,
+                      const double *dxpos, const double *dypos, const double *dzpos, int npos,
+                      long long spin0, long long nspins,
+                      const double *m0x, const double *m0y, const double *m0z, int m0_stride,
+                      double *mx, double *my, double *mz, int mode, double gamma,
+                      void *workspace, void *stream);
+
+/*
+ * Sweep extension (no reference twin: the reference runs it as one blochC call per
+ * scale, sim_rf_scale.m:82-89).  Spin s = i_f + nfreq*i_s sees b1 * b1scale[i_s] and
+ * off-resonance dfreq[i_f], at position (0,0,0)-free gradient-less conditions unless
+ * gradients/positions are given (position index 0 is used for every spin).
+ */
+int mbrf_bloch_scale_sweep_device(const double *b1real, const double *b1imag,
+                                  const double *tsteps, int ntime, double t1, double t2,
+                                  const double *dfreq, int nfreq,
+                                  const double *b1scale, int nscale,
+                                  long long spin0, long long nspins,
+                                  double *mx, double *my, double *mz, double gamma,
+                                  void *workspace, void *stream);
+
+/* tuning knobs of the Bloch kernel (0 = automatic): resident CTAs per SM, spins per thread (1|2) */
+int mbrf_bloch_set_tuning(int ctas_per_sm, int spins_per_thread);
+
+/* ---- forward SLR (Cayley-Klein) ------------------------------------------ */
+
+#define MBRF_SLR_ABRX 0   /* rf_tools/mex5/abrx.c convention                         */
+#define MBRF_SLR_ABRM 1   /* rf_tools/abrm.m convention: (a_abrx(-x), conj b_abrx(-x)), NaN at phi==0 */
+#define MBRF_SLR_ABR  2   /* rf_tools/abr.m:34: abrx followed by b = -conj(b)         */
+
+/*
+ * Replaces  mexFunction + abrot  — rf_tools/mex5/abrx.c:35-115 — and, through
+ * `convention`, rf_tools/abrm.m:46-60 and rf_tools/abr.m:19-37.
+ *   rfr,rfi : ns samples (radians); rfi NULL for a real pulse     (abrx.c:51,92)
+ *   gx,gy   : ns samples; gy NULL = no y gradient                  (abrx.c:49-50,89)
+ *   x, nx   : positions; y, ny: second axis, y NULL => ny = 1, y = 0 (abrx.c:53-57,68)
+ *   outputs : nx*ny doubles each, index ix + iy*nx                 (abrx.c:73-76)
+ */
+int mbrf_abr(const double *rfr, const double *rfi, const double *gx, const double *gy, int ns,
+             const double *x, int nx, const double *y, int ny, int convention,
+             double *alpha_r, double *alpha_i, double *beta_r, double *beta_i);
+
+/* device-resident form; positions [pos0, pos0+npos) of the flattened ix + iy*nx index */
+int mbrf_abr_device(const double *rfr, const double *rfi, const double *gx, const double *gy, int ns,
+                    const double *x, int nx, const double *y, int ny, int convention,
+                    long long pos0, long long npos,
+                    double *alpha_r, double *alpha_i, double *beta_r, double *beta_i,
+                    void *workspace, void *stream);
+unsigned long long mbrf_abr_workspace_bytes(int ns);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBRF_H */

@@ -1,0 +1,18 @@
+"""mbrf-b200: B200 (sm_100a) engine behind the MATLAB/MEX signatures of the
+multiband RF pulse design toolbox's data-parallel paths.
+
+Host-side mirror of the reference interface (same names, argument meaning and error
+behaviour) over the C ABI in ``include/mbrf.h`` / ``libmbrf.so``:
+
+    blochC, blochH, bloch            <- bloch_simulation/blochC.c, blochH.c (mexFunction)
+    abrx, abrm, abr                  <- rf_tools/mex5/abrx.c, rf_tools/abrm.m, rf_tools/abr.m
+
+There is no CPU fallback: importing works anywhere, computing needs the built library
+and a CUDA device.
+"""
+from ._lib import lib, MbrfError, library_path  # noqa: F401
+from .bloch import bloch, blochC, blochH, blochsimfz, GAMMA_C13, GAMMA_H1  # noqa: F401
+from .slr import abr, abrm, abrx  # noqa: F401
+
+__all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "lib", "MbrfError",
+           "library_path", "GAMMA_C13", "GAMMA_H1"]

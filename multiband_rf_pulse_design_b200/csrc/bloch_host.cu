@@ -1,0 +1,261 @@
+// Host-pointer entry points of the Bloch path: mbrf_blochsimfz (the reference's inner C
+// ABI, blochC.c:422-426) and mbrf_bloch (the argument handling of its mexFunction,
+// blochC.c:514-927).  They stage inputs through one pinned buffer, run the device path
+// of bloch.cu and bring the result back; there is no CPU computation of the physics.
+#include "common.h"
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace mbrf {
+namespace bloch {
+
+struct HostCtx {
+    DeviceScratch dev;
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaStream_t stream = nullptr;
+    int stream_device = -1;
+    ~HostCtx()
+    {
+        if (pinned) cudaFreeHost(pinned);
+        // streams die with the context
+    }
+    int reserve_pinned(size_t need)
+    {
+        if (pinned && pinned_bytes >= need) return MBRF_OK;
+        if (pinned) { cudaFreeHost(pinned); pinned = nullptr; pinned_bytes = 0; }
+        size_t want = need + need / 4 + 4096;
+        MBRF_CUDA(cudaMallocHost(&pinned, want));
+        pinned_bytes = want;
+        return MBRF_OK;
+    }
+    int get_stream(cudaStream_t *out)
+    {
+        int dev = 0;
+        MBRF_CUDA(cudaGetDevice(&dev));
+        if (!stream || stream_device != dev) {
+            MBRF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            stream_device = dev;
+        }
+        *out = stream;
+        return MBRF_OK;
+    }
+};
+static thread_local HostCtx t_ctx;
+
+static bool all_zero(const double *v, long long n)
+{
+    if (!v) return true;
+    for (long long i = 0; i < n; ++i)
+        if (v[i] != 0.0) return false;  // NaN counts as non-zero, as it must
+    return true;
+}
+
+// If `p` is page-locked host memory the GPU can address, return its device alias, else NULL.
+static double *device_alias_if_pinned(double *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) return (double *)at.devicePointer;
+    return nullptr;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// m0*: host, element i at [i*m0_stride], or all NULL for (0,0,1).  Outputs: host, [t + ntout*s].
+static int run_host(const double *b1r, const double *b1i, const double *gx, const double *gy, const double *gz,
+                    const double *dt, int ntime, double t1, double t2, const double *df, int nf,
+                    const double *dx, const double *dy, const double *dz, int npos, const double *m0x,
+                    const double *m0y, const double *m0z, long long m0_stride, double *mx, double *my,
+                    double *mz, int mode, double gamma)
+{
+    if (int rc = require_device()) return rc;
+    if (mode < 0 || mode > 3) { set_error("bloch: mode must be 0..3, got %d", mode); return MBRF_EINVAL; }
+    if (ntime <= 0 || nf < 0 || npos < 0) { set_error("bloch: bad sizes ntime=%d nf=%d npos=%d", ntime, nf, npos); return MBRF_EINVAL; }
+    const long long nspins = (long long)nf * npos;
+    if (nspins == 0) return MBRF_OK;
+    if (!b1r || !dt || !df || !dx || !mx || !my || !mz) { set_error("bloch: NULL required pointer"); return MBRF_EINVAL; }
+    const long long ntout = (mode & 2) ? ntime : 1;
+
+    // gradient axes that cannot contribute are dropped so the kernel skips their FMAs
+    const bool x_live = !all_zero(gx, ntime) && !all_zero(dx, npos);
+    const bool y_live = !all_zero(gy, ntime) && !all_zero(dy, npos);
+    const bool z_live = !all_zero(gz, ntime) && !all_zero(dz, npos);
+    const bool any_yz = y_live || z_live;
+    const bool use_x = x_live || any_yz;
+
+    HostCtx &cx = t_ctx;
+    cudaStream_t st;
+    if (int rc = cx.get_stream(&st)) return rc;
+
+    // ---- pack small inputs into one pinned block -> one H2D --------------------------------
+    const size_t nt = (size_t)ntime;
+    size_t off = 0;
+    auto take = [&](size_t n_doubles) { size_t o = off; off += align_up(n_doubles * sizeof(double), 64); return o; };
+    const size_t o_b1r = take(nt), o_b1i = b1i ? take(nt) : 0, o_dt = take(nt);
+    const size_t o_gx = (use_x && gx) ? take(nt) : 0, o_gy = (y_live) ? take(nt) : 0, o_gz = (z_live) ? take(nt) : 0;
+    const size_t o_df = take((size_t)nf);
+    const size_t o_dx = take((size_t)npos), o_dy = (any_yz && dy) ? take((size_t)npos) : 0,
+                 o_dz = (any_yz && dz) ? take((size_t)npos) : 0;
+    const size_t in_bytes = off;
+
+    // outputs are produced in chunks of spins so that mode 2/3 (ntout = ntime) cannot exhaust HBM
+    const size_t out_budget = (size_t)3 << 30;  // bytes of device output per chunk
+    long long chunk = nspins;
+    if ((size_t)nspins * (size_t)ntout * 24 > out_budget) {
+        chunk = (long long)(out_budget / ((size_t)ntout * 24));
+        if (chunk < 1) chunk = 1;
+    }
+    const bool have_m0 = m0x && m0y && m0z;
+    const size_t m0_bytes = have_m0 ? align_up((size_t)chunk * 8, 64) * 3 : 0;
+    if (int rc = cx.reserve_pinned(in_bytes + m0_bytes)) return rc;
+
+    double *zero_copy[3] = {nullptr, nullptr, nullptr};
+    if (ntout == 1 && chunk == nspins) {
+        // page-locked result arrays: let the kernel store straight into them over PCIe
+        zero_copy[0] = device_alias_if_pinned(mx);
+        zero_copy[1] = device_alias_if_pinned(my);
+        zero_copy[2] = device_alias_if_pinned(mz);
+        if (!(zero_copy[0] && zero_copy[1] && zero_copy[2])) zero_copy[0] = zero_copy[1] = zero_copy[2] = nullptr;
+    }
+    const size_t out_bytes = zero_copy[0] ? 0 : align_up((size_t)chunk * (size_t)ntout * 8, 256) * 3;
+    const size_t ws_bytes = align_up(mbrf_bloch_workspace_bytes(ntime), 256);
+    if (int rc = cx.dev.reserve(align_up(in_bytes, 256) + align_up(m0_bytes, 256) + ws_bytes + out_bytes)) return rc;
+
+    char *hp = (char *)cx.pinned;
+    char *dp = (char *)cx.dev.ptr;
+    memcpy(hp + o_b1r, b1r, nt * 8);
+    if (b1i) memcpy(hp + o_b1i, b1i, nt * 8);
+    memcpy(hp + o_dt, dt, nt * 8);
+    if (use_x && gx) memcpy(hp + o_gx, gx, nt * 8);
+    if (y_live) memcpy(hp + o_gy, gy, nt * 8);
+    if (z_live) memcpy(hp + o_gz, gz, nt * 8);
+    memcpy(hp + o_df, df, (size_t)nf * 8);
+    memcpy(hp + o_dx, dx, (size_t)npos * 8);
+    if (any_yz && dy) memcpy(hp + o_dy, dy, (size_t)npos * 8);
+    if (any_yz && dz) memcpy(hp + o_dz, dz, (size_t)npos * 8);
+    MBRF_CUDA(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+
+    auto dptr = [&](size_t o) { return (const double *)(dp + o); };
+    char *d_m0 = dp + align_up(in_bytes, 256);
+    char *d_ws = d_m0 + align_up(m0_bytes, 256);
+    char *d_out = d_ws + ws_bytes;
+    const size_t comp_out = out_bytes / 3, comp_m0 = m0_bytes / 3;
+
+    for (long long s0 = 0; s0 < nspins; s0 += chunk) {
+        const long long n = (nspins - s0 < chunk) ? nspins - s0 : chunk;
+        const double *dm0[3] = {nullptr, nullptr, nullptr};
+        if (have_m0) {
+            double *h = (double *)(hp + in_bytes);
+            const size_t cs = comp_m0 / 8;
+            // the previous chunk's H2D of this staging area has completed (stream synced below)
+            for (long long i = 0; i < n; ++i) {
+                h[i] = m0x[(s0 + i) * m0_stride];
+                h[cs + i] = m0y[(s0 + i) * m0_stride];
+                h[2 * cs + i] = m0z[(s0 + i) * m0_stride];
+            }
+            MBRF_CUDA(cudaMemcpyAsync(d_m0, h, m0_bytes, cudaMemcpyHostToDevice, st));
+            for (int c = 0; c < 3; ++c) dm0[c] = (const double *)(d_m0 + c * comp_m0);
+        }
+        double *dout[3];
+        for (int c = 0; c < 3; ++c) dout[c] = zero_copy[0] ? zero_copy[c] : (double *)(d_out + c * comp_out);
+        int rc = mbrf_bloch_device(dptr(o_b1r), b1i ? dptr(o_b1i) : nullptr, (use_x && gx) ? dptr(o_gx) : nullptr,
+                                   y_live ? dptr(o_gy) : nullptr, z_live ? dptr(o_gz) : nullptr, dptr(o_dt), ntime,
+                                   t1, t2, dptr(o_df), nf, dptr(o_dx), (any_yz && dy) ? dptr(o_dy) : nullptr,
+                                   (any_yz && dz) ? dptr(o_dz) : nullptr, npos, s0, n, dm0[0], dm0[1], dm0[2], 1,
+                                   dout[0], dout[1], dout[2], mode, gamma, d_ws, st);
+        if (rc) return rc;
+        if (!zero_copy[0]) {
+            double *hout[3] = {mx, my, mz};
+            for (int c = 0; c < 3; ++c)
+                MBRF_CUDA(cudaMemcpyAsync(hout[c] + (size_t)s0 * ntout, dout[c], (size_t)n * ntout * 8,
+                                          cudaMemcpyDeviceToHost, st));
+        }
+        MBRF_CUDA(cudaStreamSynchronize(st));
+    }
+    return MBRF_OK;
+}
+
+}  // namespace bloch
+}  // namespace mbrf
+
+using namespace mbrf;
+using namespace mbrf::bloch;
+
+extern "C" {
+
+int mbrf_blochsimfz(const double *b1real, const double *b1imag, const double *xgrad, const double *ygrad,
+                    const double *zgrad, const double *tsteps, int ntime, double t1, double t2,
+                    const double *dfreq, int nfreq, const double *dxpos, const double *dypos,
+                    const double *dzpos, int npos, double *mx, double *my, double *mz, int mode, double gamma)
+{
+    const long long ntout = (mode & 2) ? ntime : 1;
+    // mx/my/mz carry the initial magnetisation at stride ntout (blochC.c:838-865) and receive the result
+    return run_host(b1real, b1imag, xgrad, ygrad, zgrad, tsteps, ntime, t1, t2, dfreq, nfreq, dxpos, dypos, dzpos,
+                    npos, mx, my, mz, ntout, mx, my, mz, mode, gamma);
+}
+
+int mbrf_bloch(const double *b1r, const double *b1i, int ntime, const double *gr, int ngr, const double *tp,
+               int ntp, double t1, double t2, const double *df, int nf, const double *dp, int npos_m, int npos_n,
+               int mode, const double *mx0, const double *my0, const double *mz0, int n_m0, double *mx,
+               double *my, double *mz, int out_dims[4], double gamma)
+{
+    if (ntime <= 0 || !b1r) { set_error("bloch: b1 is empty"); return MBRF_EINVAL; }
+    if (ngr < 0 || (ngr > 0 && !gr) || !tp || !df || nf < 0 || npos_m < 0 || npos_n < 0 ||
+        ((long long)npos_m * npos_n > 0 && !dp) || !out_dims) {
+        set_error("bloch: NULL / negative argument");
+        return MBRF_EINVAL;
+    }
+    // ---- gradients (blochC.c:595-638): first ntime values are x; y and z only if present ----
+    if (ngr < ntime) {
+        // the reference reads ntime x-gradient samples regardless; fewer is an out-of-bounds read there
+        set_error("bloch: gradient has %d samples, b1 has %d", ngr, ntime);
+        return MBRF_EINVAL;
+    }
+    const double *gx = gr;
+    const double *gy = (ngr < 2 * ntime) ? nullptr : gr + ntime;
+    const double *gz = (ngr < 3 * ntime) ? nullptr : gr + 2 * (size_t)ntime;
+    if (ngr != ntime && ngr != 2 * ntime && ngr != 3 * ntime)
+        printf("Gradient length differs from B1 length\n");  // blochC.c:637-638, same text
+    // ---- time (blochC.c:660-681) ----
+    std::vector<double> dt((size_t)ntime);
+    if (ntp == 1) {
+        for (int i = 0; i < ntime; ++i) dt[i] = tp[0];
+    } else if (ntp != ntime) {
+        // reference: prints "Time-point length differs from B1 length" and then indexes tp[0..ntime)
+        set_error("bloch: time vector has %d entries, b1 has %d", ntp, ntime);
+        return MBRF_EINVAL;
+    } else {
+        bool allpos = true;  // times2intervals, blochC.c:249-276
+        double last = 0.0;
+        for (int i = 0; i < ntime; ++i) {
+            dt[i] = tp[i] - last;
+            last = tp[i];
+            if (dt[i] <= 0) allpos = false;
+        }
+        if (!allpos) memcpy(dt.data(), tp, sizeof(double) * (size_t)ntime);  // they were intervals
+    }
+    // ---- positions (blochC.c:701-758) ----
+    int npos;
+    const double *dx = dp, *dy = nullptr, *dz = nullptr;
+    if (npos_n == 3) { npos = npos_m; dy = dx + npos; dz = dy + npos; }
+    else if (npos_n == 2) { npos = npos_m; dy = dx + npos; }
+    else npos = npos_m * npos_n;
+    const long long nfnpos = (long long)nf * npos;
+    const long long ntout = (mode & 2) ? ntime : 1;
+    // ---- output shape (blochC.c:880-904) ----
+    if (ntout > 1 && nf > 1 && npos > 1) { out_dims[0] = (int)ntout; out_dims[1] = npos; out_dims[2] = nf; out_dims[3] = 3; }
+    else if (ntout > 1) { out_dims[0] = (int)ntout; out_dims[1] = npos * nf; out_dims[2] = 1; out_dims[3] = 2; }
+    else { out_dims[0] = npos; out_dims[1] = nf; out_dims[2] = 1; out_dims[3] = 2; }
+    // ---- initial magnetisation (blochC.c:820-865): used only when all three have npos*nf elements ----
+    const bool have_m0 = mx0 && my0 && mz0 && (long long)n_m0 == nfnpos;
+    if (nfnpos == 0) return MBRF_OK;
+    if (!mx || !my || !mz) { set_error("bloch: NULL output"); return MBRF_EINVAL; }
+    return run_host(b1r, b1i, gx, gy, gz, dt.data(), ntime, t1, t2, df, nf, dx, dy, dz, npos,
+                    have_m0 ? mx0 : nullptr, have_m0 ? my0 : nullptr, have_m0 ? mz0 : nullptr, 1, mx, my, mz,
+                    mode, gamma);
+}
+
+}  // extern "C"
