@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py — Bloch hot path on B200 (BASELINE.json metric "Bloch spin-steps/sec").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (`config.workload`): BASELINE configs[1] — a 512-sample excitation pulse simulated
+over 10^6 spins per GPU (1000 off-resonances x 1000 positions with a 0.05 G/cm x-gradient,
+T1 = T2 = 1000 s, mode 0, 13C gamma), i.e. 5.12e8 spin-steps per step per GPU.  At N GPUs the
+job is 1000*N off-resonances x 1000 positions, sharded by contiguous spin range
+(s = p + npos*f, blochC.c:468-473) with one NCCL gather of mx/my/mz to rank 0 per step.
+
+One JSON line is printed by rank 0:
+  value        device-resident throughput (inputs already in HBM, mbrf_bloch_device + gather),
+               timed with CUDA events on the launching stream, max over ranks
+  e2e          the same metric through the reference-facing call  blochC(b1,gr,tp,t1,t2,df,dp,mode)
+               (C ABI mbrf_bloch) with pinned HOST buffers; H2D of the inputs and the result
+               landing in host memory are inside the timed region
+  roofline     FP64-pipe roofline of the dominant kernel (76 algorithmic flops per
+               spin-step; the path is FP64-bound, 56 B of HBM traffic per spin) against the FP64
+               FMA peak measured in this run by a DFMA-only kernel; `hbm` shows why it is not HBM-bound
+  cpu_baseline the reference's own C (oracle/_ref/libblochC.so: blochC.c compiled unmodified)
+               on this box's host cores over a bounded sample of the same workload
+
+`--impl reference` times that CPU implementation alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Bloch spin-steps/sec"
+UNIT = "spin-steps/s"
+NTIME = 512
+NF_PER_GPU = 1000
+NPOS = 1000
+FLOPS_PER_SPIN_STEP = 76        # blochC.c:330-361 as written, sqrt/div/sin/cos at 1 each
+FP64_INST_PER_SPIN_STEP = 39    # what our kernel issues on the FP64 pipe (cuobjdump -sass, 1 gradient axis, tier SMALL)
+BYTES_PER_SPIN = 56             # df (8) + M0/positions amortised (24) + M out (24): SURVEY.md 8(d)
+WORKLOAD = ("bloch cfg2: 512-sample dzrf 'ex' pulse x 1e6 spins per GPU "
+            "(1000 df x 1000 dp, Gx=0.05 G/cm, T1=T2=1e3 s, mode 0, blochC gamma)")
+
+
+# ----------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------
+def make_pulse():
+    """512-sample b1 in Gauss: the committed fixture made with the reference's own dzrf recipe
+    (tests/golden/make_golden.py); an inline Hamming-sinc stand-in if the fixture is absent."""
+    p = os.path.join(ROOT, "tests", "golden", "pulses.npz")
+    if os.path.exists(p):
+        return np.load(p)["b1_cfg2_gauss"].astype(np.complex128), "tests/golden/pulses.npz:b1_cfg2_gauss"
+    n, m = NTIME, 2
+    x = np.arange(-n / 2, n / 2) / (n / 2)
+    snc = np.sin(m * 2 * np.pi * x + 1e-5) / (m * 2 * np.pi * x + 1e-5)
+    rf = snc * (0.54 + 0.46 * np.cos(np.pi * x))
+    rf = rf / rf.sum() * (np.pi / 2)
+    return (rf / (2 * np.pi * 1.0705 * (8.0 / n))).astype(np.complex128), "inline msinc stand-in"
+
+
+def make_workload(world):
+    b1, src = make_pulse()
+    nt = b1.size
+    return dict(b1=b1, gx=np.full(nt, 0.05), dt=8e-3 / nt, t1=1e3, t2=1e3,
+                df=np.linspace(-5000.0, 5000.0, NF_PER_GPU * world), dx=np.linspace(-5.0, 5.0, NPOS), src=src)
+
+
+# ----------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [l.split(",") for (t, l) in self.lines if t0 <= t <= t1 + 0.03] or [l.split(",") for _, l in self.lines]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nme, v in zip(names, r[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the reference's own C on host cores
+# ----------------------------------------------------------------------------
+def cpu_reference_run(wl, nf_per_thread, threads):
+    """Time the reference blochsimfz over threads x nf_per_thread offsets x NPOS positions.
+    Returns (spin_steps_per_s, seconds, kind)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import ref
+    ref.build()
+    use_ref = ref.have_ref()
+    nt = wl["b1"].size
+    df_all = wl["df"]
+
+    def work(i):
+        df = np.ascontiguousarray(df_all[(i * nf_per_thread) % max(1, df_all.size - nf_per_thread):][:nf_per_thread])
+        if use_ref:
+            lib = ref._lib(os.path.join(ref.REF_DIR, "libblochC.so"))
+            fn = lib.blochsimfz
+            fn.argtypes = ref._BLOCHSIMFZ_ARGS
+        else:
+            lib = ref._lib(os.path.join(ref.HERE, "liboracle.so"))
+            fn = lib.oracle_blochsimfz
+            fn.argtypes = ref._BLOCHSIMFZ_ARGS + [C.c_double]
+        fn.restype = C.c_int
+        b1r, b1i, gx, gy, gz, dt, n, dfp, dx, dy, dz, ntout, out = ref._prep_sim(
+            wl["b1"], wl["gx"], None, None, wl["dt"], df, wl["dx"], None, None, 0, None)
+        a = [ref._ptr(b1r), ref._ptr(b1i), ref._ptr(gx), ref._ptr(gy), ref._ptr(gz), ref._ptr(dt), n, wl["t1"],
+             wl["t2"], ref._ptr(dfp), dfp.size, ref._ptr(dx), ref._ptr(dy), ref._ptr(dz), dx.size,
+             ref._ptr(out[0]), ref._ptr(out[1]), ref._ptr(out[2]), 0]
+        if not use_ref:
+            a.append(ref.GAMMA_C13)
+        fn(*a)                       # ctypes releases the GIL: threads run the C loop in parallel
+        return float(out[2][0])
+
+    with ref._quiet_stdout():        # the reference prints "%d%% Complete." above 40 000 spins (blochC.c:502)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, range(threads)))
+        sec = time.perf_counter() - t0
+    steps = threads * nf_per_thread * NPOS * nt
+    return steps / sec, sec, ("reference" if use_ref else "port")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    wl = make_workload(1)
+    nf_pt = 20                      # 20 offsets x 1000 positions x 512 samples ~ 0.65 s per thread per step
+    for _ in range(args.warmup):
+        cpu_reference_run(wl, nf_pt, threads)
+    tot_steps, tot_sec, kind = 0.0, 0.0, "reference"
+    for _ in range(args.steps):
+        v, sec, kind = cpu_reference_run(wl, nf_pt, threads)
+        tot_steps += v * sec
+        tot_sec += sec
+    value = tot_steps / tot_sec
+    sample = f"{threads} threads x {nf_pt} df x {NPOS} dp x {NTIME} samples per step (bounded sample of the workload)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_sec / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pulse": wl["src"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import multiband_rf_pulse_design_b200 as m
+    from multiband_rf_pulse_design_b200._lib import check
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmbrf has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = m.lib()
+    check(lib.mbrf_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = make_workload(world)
+    nt = wl["b1"].size
+    nf, npos = wl["df"].size, wl["dx"].size
+    nlocal = NF_PER_GPU * npos
+    spin0 = rank * nlocal
+    steps_per_gpu = nlocal * nt
+
+    def T(a):
+        return torch.tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev)
+
+    b1r, b1i, gx = T(wl["b1"].real), T(wl["b1"].imag), T(wl["gx"])
+    dts, df, dx = T(np.full(nt, wl["dt"])), T(wl["df"]), T(wl["dx"])
+    out = torch.empty((3, nlocal), dtype=torch.float64, device=dev)
+    gathered = [torch.empty((3, nlocal), dtype=torch.float64, device=dev) for _ in range(world)] \
+        if (world > 1 and rank == 0) else None
+    ws = torch.empty(int(lib.mbrf_bloch_workspace_bytes(nt)), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        check(lib.mbrf_bloch_device(b1r.data_ptr(), b1i.data_ptr(), gx.data_ptr(), None, None, dts.data_ptr(), nt,
+                                    wl["t1"], wl["t2"], df.data_ptr(), nf, dx.data_ptr(), None, None, npos,
+                                    spin0, nlocal, None, None, None, 1,
+                                    out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), 0, m.GAMMA_C13,
+                                    ws.data_ptr(), stream.cuda_stream))
+        if world > 1:
+            dist.gather(out, gathered, dst=0)        # the one collective of the path: final gather over NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.1)
+    barrier()
+    launches0 = lib.mbrf_launch_count()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                # evict L2 between timed iterations (outside the event pair)
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = lib.mbrf_launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_dev = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    ms_dev = max_over_ranks(ms_dev)
+    value = world * steps_per_gpu / (ms_dev * 1e-3)
+
+    # dominant kernel alone (prep + spin kernel, no gather) for the roofline, same stream, L2 flushed
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        kev[k][0].record(stream)
+        check(lib.mbrf_bloch_device(b1r.data_ptr(), b1i.data_ptr(), gx.data_ptr(), None, None, dts.data_ptr(), nt,
+                                    wl["t1"], wl["t2"], df.data_ptr(), nf, dx.data_ptr(), None, None, npos,
+                                    spin0, nlocal, None, None, None, 1,
+                                    out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), 0, m.GAMMA_C13,
+                                    ws.data_ptr(), stream.cuda_stream))
+        kev[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+
+    # ---- end-to-end leg: the reference-facing call on pinned host buffers --------------------
+    h_out = [torch.empty(nlocal, dtype=torch.float64).pin_memory() for _ in range(3)]
+    h_out_np = tuple(t.numpy() for t in h_out)
+    h_b1 = wl["b1"].reshape(-1, 1)
+    h_gr = wl["gx"].reshape(-1, 1)
+    h_df = np.ascontiguousarray(wl["df"][rank * NF_PER_GPU:(rank + 1) * NF_PER_GPU]).reshape(-1, 1)
+    h_dp = wl["dx"].reshape(-1, 1)
+    h2d = 8 * (2 * nt + nt + nt + h_df.size + h_dp.size)   # b1 re/im, gradient, time steps, df, dp
+    d2h = 3 * 8 * nlocal
+
+    def step_e2e():
+        m.blochC(h_b1, h_gr, wl["dt"], wl["t1"], wl["t2"], h_df, h_dp, 0, out=h_out_np)
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()                                   # synchronous: returns with the result in host memory
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+    ms_e2e = max_over_ranks(ms_e2e)
+    barrier()
+    e2e_value = world * steps_per_gpu / (ms_e2e * 1e-3)
+    # the e2e result must be the same numbers as the device-resident leg
+    chk = float(np.abs(h_out_np[2][:4096] - out[2][:4096].cpu().numpy()).max())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline ---------------------------------------------------------------------------
+    tf, kms = C.c_double(), C.c_double()
+    check(lib.mbrf_measure_fp64_peak(C.byref(tf), C.byref(kms)))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved_tf = FLOPS_PER_SPIN_STEP * steps_per_gpu / (ms_kernel * 1e-3) / 1e12
+    pipe_tf = 2 * FP64_INST_PER_SPIN_STEP * steps_per_gpu / (ms_kernel * 1e-3) / 1e12
+    hbm_gbs = BYTES_PER_SPIN * nlocal / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "bloch_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            traffic = None
+    roofline = {
+        "bound": "fp64", "kernel": "mbrf::bloch::bloch_kernel<0,1,2,false>",
+        "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value,
+        "traffic": traffic,
+        "peak_source": "FP64 FMA peak measured in this run by mbrf_measure_fp64_peak (DFMA-only kernel); "
+                       "MEASURED_PEAKS.json has no FP64 figure",
+        "flops_per_spin_step": FLOPS_PER_SPIN_STEP, "kernel_ms": ms_kernel,
+        "fp64_pipe": {"inst_per_spin_step": FP64_INST_PER_SPIN_STEP, "issued_tflops_equiv": pipe_tf,
+                      "frac": pipe_tf / tf.value},
+        "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                "note": "56 algorithmic bytes per spin per call: the path is FP64-bound, not HBM-bound"},
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        nf_pt = 30
+        v, sec, kind = cpu_reference_run(wl, nf_pt, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "seconds": sec,
+               "sample": f"{threads} threads x {nf_pt} df x {NPOS} dp x {nt} samples of the same workload "
+                         f"(blochC.c compiled -O2, one blochsimfz call per thread)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pulse": wl["src"], "spins_per_gpu": nlocal, "ntime": nt,
+                   "sharding": f"contiguous spin ranges over {world} GPU(s), one NCCL gather to rank 0 per step"
+                   if world > 1 else "single GPU", "l2": "flushed between timed iterations (256 MiB memset)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e, "call": "blochC(b1,gr,tp,t1,t2,df,dp,0) -> mbrf_bloch (C ABI), pinned host buffers",
+                "check_vs_device_leg": chk},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 200 and args.warmup == 10:
+            args.steps, args.warmup = 10, 3
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -25,7 +25,7 @@
 // instructions, all on the FP64 pipe, no SFU, no divide.  The kernel is FP64-pipe bound;
 // HBM traffic is 56 B per spin per call (df/dp in, M out).
 #include "common.h"
-#include "rot_poly.h"
+#include "rot_coeffs.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -41,8 +41,8 @@ constexpr int NBUF = 2;    // tiles in flight
 constexpr int BLOCK = 128; // threads per CTA
 constexpr int WS_HEADER = 8;  // doubles of bounds in front of the table
 
-enum { E_RX = 0, E_RY, E_C, E_DTN, E_E1, E_E2, E_REC, E_GXD, E_GYD, E_GZD };
-enum { B_C = 0, B_DTN, B_GXD, B_GYD, B_GZD };
+enum { E_RX = 0, E_RY, E_C, E_REC, E_E1, E_E2, E_DTN, E_GXD, E_GYD, E_GZD };  // 16-byte pairs: (rx,ry)(c,rec)(e1,e2)(dtn,gxd)(gyd,gzd)
+enum { B_C = 0, B_DTN, B_GXD, B_GYD, B_GZD, B_NONUNIFORM };
 
 // ---------------------------------------------------------------------------
 // prep: waveform -> table + bounds
@@ -81,51 +81,17 @@ __global__ void bloch_prep_kernel(const double *__restrict__ b1r, const double *
     atomic_max_nonneg(ws + B_GXD, e[E_GXD]);
     atomic_max_nonneg(ws + B_GYD, e[E_GYD]);
     atomic_max_nonneg(ws + B_GZD, e[E_GZD]);
+    // Constant time step and constant gradients (every call site of the reference: scalar tp, G = 0
+    // or a constant slice-select gradient) make rz a per-spin constant; flag anything else.
+    const double d0 = dt[0];
+    const bool same = e[E_DTN] == -MBRF_TWOPI * d0 && e[E_GXD] == (gx ? -gx[0] * d0 : 0.0) &&
+                      e[E_GYD] == (gy ? -gy[0] * d0 : 0.0) && e[E_GZD] == (gz ? -gz[0] * d0 : 0.0);
+    if (!same) ws[B_NONUNIFORM] = 1.0;
 }
 
 // ---------------------------------------------------------------------------
 // rotation coefficients  w = cos(phi/2),  s2 = 2 sin(phi/2)/phi  from u = phi^2
 // ---------------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ double horner(const double (&c)[N], double u)
-{
-    double acc = c[N - 1];
-#pragma unroll
-    for (int i = N - 2; i >= 0; --i) acc = fma(acc, u, c[i]);
-    return acc;
-}
-
-enum { TIER_SMALL = 0, TIER_MED = 1, TIER_BIG = 2, TIER_ANY = 3 };
-
-template <int TIER>
-__device__ __forceinline__ void rot_coeffs(double u, double &w, double &s2)
-{
-    if (TIER == TIER_SMALL) {
-        constexpr double cc[] = ROT_C_SMALL;
-        constexpr double cs[] = ROT_S_SMALL;
-        w = horner(cc, u);
-        s2 = horner(cs, u);
-    } else if (TIER == TIER_MED) {
-        constexpr double cc[] = ROT_C_MED;
-        constexpr double cs[] = ROT_S_MED;
-        w = horner(cc, u);
-        s2 = horner(cs, u);
-    } else {
-        constexpr double cc[] = ROT_C_BIG;
-        constexpr double cs[] = ROT_S_BIG;
-        if (TIER == TIER_BIG || u <= ROT_U_BIG) {
-            w = horner(cc, u);
-            s2 = horner(cs, u);
-        } else {  // more than a full turn in one sample (or NaN): the reference's own formula
-            const double phi = sqrt(u);
-            double s, c;
-            sincos(0.5 * phi, &s, &c);
-            w = c;
-            s2 = 2.0 * s / phi;
-        }
-    }
-}
-
 // M <- R(q) M  with q = (w, v/2), v = (vx,vy,vz) = n*s2.
 __device__ __forceinline__ void rotate(double w, double vx, double vy, double vz, double &mx, double &my,
                                        double &mz)
@@ -158,33 +124,35 @@ struct Params {
 struct Spin {
     double px, py, pz, fz;  // gamma*position, off-resonance
     double sc, sc2;         // b1 scale (sweep)
+    double rz0, rz2;        // rz and rz^2 when they do not depend on the sample (CRZ)
     double mx, my, mz;
     double A[9], b[3];      // steady-state propagators (modes 1, 3); column-major like the reference
 };
 
-template <int NG, int TIER, bool SWEEP, bool STEADY>
+template <int NG, int TIER, bool SWEEP, bool STEADY, bool CRZ>
 __device__ __forceinline__ void spin_step(const double *__restrict__ e, Spin &s)
 {
     const double2 rxy = *reinterpret_cast<const double2 *>(e + E_RX);
-    const double2 cd = *reinterpret_cast<const double2 *>(e + E_C);
+    const double2 cr = *reinterpret_cast<const double2 *>(e + E_C);    // c, rec
     const double2 e12 = *reinterpret_cast<const double2 *>(e + E_E1);
-    double rz = cd.y * s.fz;
-    double rec;
-    if (NG >= 1) {
-        const double2 rg = *reinterpret_cast<const double2 *>(e + E_REC);
-        rec = rg.x;
-        rz = fma(rg.y, s.px, rz);
+    const double rec = cr.y;
+    double rz, u, w, s2;
+    if (CRZ) {
+        rz = s.rz0;
+        if (SWEEP) u = fma(cr.x, s.sc2, s.rz2);
+        else u = s.rz2 + cr.x;
     } else {
-        rec = e[E_REC];
+        const double2 dg = *reinterpret_cast<const double2 *>(e + E_DTN);  // dtn, gxd
+        rz = dg.x * s.fz;
+        if (NG >= 1) rz = fma(dg.y, s.px, rz);
+        if (NG >= 2) {
+            const double2 gyz = *reinterpret_cast<const double2 *>(e + E_GYD);
+            rz = fma(gyz.x, s.py, rz);
+            rz = fma(gyz.y, s.pz, rz);
+        }
+        if (SWEEP) u = fma(rz, rz, cr.x * s.sc2);
+        else u = fma(rz, rz, cr.x);
     }
-    if (NG >= 2) {
-        const double2 gyz = *reinterpret_cast<const double2 *>(e + E_GYD);
-        rz = fma(gyz.x, s.py, rz);
-        rz = fma(gyz.y, s.pz, rz);
-    }
-    double u, w, s2;
-    if (SWEEP) u = fma(rz, rz, cd.x * s.sc2);
-    else u = fma(rz, rz, cd.x);
     rot_coeffs<TIER>(u, w, s2);
     const double sxy = SWEEP ? s2 * s.sc : s2;
     const double vx = rxy.x * sxy, vy = rxy.y * sxy, vz = rz * s2;
@@ -237,7 +205,7 @@ __device__ void steady_state(Spin &s)
 }
 
 // One tile of n samples for this thread's SPT spins.  RECORD: write every sample (mode bit 1).
-template <int NG, int SPT, int TIER, bool SWEEP, bool STEADY, bool RECORD>
+template <int NG, int SPT, int TIER, bool SWEEP, bool STEADY, bool RECORD, bool CRZ>
 __device__ __forceinline__ void run_tile(const double *__restrict__ tile, int n, Spin (&sp)[SPT],
                                          const bool (&active)[SPT], double *const (&ox)[SPT],
                                          double *const (&oy)[SPT], double *const (&oz)[SPT], int t0)
@@ -246,7 +214,7 @@ __device__ __forceinline__ void run_tile(const double *__restrict__ tile, int n,
     for (int i = 0; i < n; ++i) {
         const double *e = tile + i * SD;
 #pragma unroll
-        for (int j = 0; j < SPT; ++j) spin_step<NG, TIER, SWEEP, STEADY>(e, sp[j]);
+        for (int j = 0; j < SPT; ++j) spin_step<NG, TIER, SWEEP, STEADY, CRZ>(e, sp[j]);
         if (RECORD) {
 #pragma unroll
             for (int j = 0; j < SPT; ++j)
@@ -301,13 +269,16 @@ __global__ void __launch_bounds__(BLOCK) bloch_kernel(const Params p)
 
     // bounds for tier selection: u <= cmax + (|fz| dtn + |px| gxd + |py| gyd + |pz| gzd)^2
     const double bc = p.ws[B_C], bdtn = p.ws[B_DTN], bgx = p.ws[B_GXD], bgy = p.ws[B_GYD], bgz = p.ws[B_GZD];
+    // sample-independent rz: entry 0 of the table holds the (constant) dtn, gxd, gyd, gzd
+    const bool crz = (MODE == 0 || MODE == 2) && p.ws[B_NONUNIFORM] == 0.0;
+    const double dtn0 = tab[E_DTN], gxd0 = tab[E_GXD], gyd0 = tab[E_GYD], gzd0 = tab[E_GZD];
 
     unsigned k = 0;
     for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
         Spin sp[SPT];
         bool active[SPT];
         double *ox[SPT], *oy[SPT], *oz[SPT];
-        int tier = TIER_SMALL;
+        int tier = TIER_TINY;
 #pragma unroll
         for (int j = 0; j < SPT; ++j) {
             const long long ls = g * group_spins + (long long)j * BLOCK + tid;  // local spin
@@ -347,8 +318,10 @@ __global__ void __launch_bounds__(BLOCK) bloch_kernel(const Params p)
             oz[j] = p.mz + o * ntout;
             const double rzb = fabs(q.fz) * bdtn + fabs(q.px) * bgx + fabs(q.py) * bgy + fabs(q.pz) * bgz;
             const double ub = fma(rzb, rzb, bc * q.sc2);
-            const int tj = ub <= ROT_U_SMALL ? TIER_SMALL : ub <= ROT_U_MED ? TIER_MED : ub <= ROT_U_BIG ? TIER_BIG : TIER_ANY;
-            tier = max(tier, active[j] ? tj : TIER_SMALL);
+            const int tj = rot_tier(ub);
+            tier = max(tier, active[j] ? tj : TIER_TINY);
+            q.rz0 = fma(gzd0, q.pz, fma(gyd0, q.py, fma(gxd0, q.px, dtn0 * q.fz)));
+            q.rz2 = q.rz0 * q.rz0;
         }
         tier = __reduce_max_sync(0xffffffffu, tier);  // one code path per warp
 
@@ -367,18 +340,25 @@ __global__ void __launch_bounds__(BLOCK) bloch_kernel(const Params p)
                 const int n = min(TT, p.ntime - ti * TT);
                 const double *tile = tiles[k % NBUF];
                 mbar_wait(&full[k % NBUF], (k / NBUF) & 1u);
-#define MBRF_RUN(TIER_)                                                                                  \
-    if (steady) run_tile<NG, SPT, TIER_, SWEEP, true, false>(tile, n, sp, active, ox, oy, oz, ti * TT);   \
-    else run_tile<NG, SPT, TIER_, SWEEP, false, (MODE & 2) != 0>(tile, n, sp, active, ox, oy, oz, ti * TT);
+#define MBRF_RUN(TIER_, CRZ_)                                                                                   \
+    if (steady) run_tile<NG, SPT, TIER_, SWEEP, true, false, false>(tile, n, sp, active, ox, oy, oz, ti * TT);     \
+    else run_tile<NG, SPT, TIER_, SWEEP, false, (MODE & 2) != 0, CRZ_>(tile, n, sp, active, ox, oy, oz, ti * TT);
                 if (MODE == 1 || MODE == 3) {
                     // steady-state modes are rare (no caller in the reference): one general path
-                    MBRF_RUN(TIER_ANY)
+                    MBRF_RUN(TIER_ANY, false)
+                } else if (crz && tier <= TIER_MED) {
+                    switch (tier) {
+                    case TIER_TINY: MBRF_RUN(TIER_TINY, true) break;
+                    case TIER_SMALL: MBRF_RUN(TIER_SMALL, true) break;
+                    default: MBRF_RUN(TIER_MED, true) break;
+                    }
                 } else {
                     switch (tier) {
-                    case TIER_SMALL: MBRF_RUN(TIER_SMALL) break;
-                    case TIER_MED: MBRF_RUN(TIER_MED) break;
-                    case TIER_BIG: MBRF_RUN(TIER_BIG) break;
-                    default: MBRF_RUN(TIER_ANY) break;
+                    case TIER_TINY: MBRF_RUN(TIER_TINY, false) break;
+                    case TIER_SMALL: MBRF_RUN(TIER_SMALL, false) break;
+                    case TIER_MED: MBRF_RUN(TIER_MED, false) break;
+                    case TIER_BIG: MBRF_RUN(TIER_BIG, false) break;
+                    default: MBRF_RUN(TIER_ANY, false) break;
                     }
                 }
 #undef MBRF_RUN
@@ -417,24 +397,15 @@ static int launch_balanced(K kernel, const Params &p, int spt, cudaStream_t stre
     int occ = 0;
     MBRF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BLOCK, 0));
     if (occ < 1) occ = 1;
-    const int sms = sm_count();
-    int bps = occ;
-    if (g_tune_ctas_per_sm > 0) bps = g_tune_ctas_per_sm < occ ? g_tune_ctas_per_sm : occ;
-    else {
-        // The kernel is FP64-pipe bound, so a wave costs ~bps units of time.  Among residencies that
-        // still hide latency (>= occ/2), take the one with the least tail: min ceil(G/(sms*bps))*bps.
-        long long best = -1;
-        for (int c = occ; c >= (occ + 1) / 2 && c >= 1; --c) {
-            const long long per_wave = (long long)sms * c;
-            const long long cost = ((ngroups + per_wave - 1) / per_wave) * c;
-            if (best < 0 || cost < best) {
-                best = cost;
-                bps = c;
-            }
-        }
+    // Default: one group of BLOCK*SPT spins per CTA and let the hardware block scheduler balance the
+    // SMs (a finished CTA is replaced at once; the tail is at most one group).  A positive tuning value
+    // selects the persistent form instead: sms*ctas_per_sm CTAs striding over the groups.
+    long long grid = ngroups;
+    if (g_tune_ctas_per_sm > 0) {
+        const int bps = g_tune_ctas_per_sm < occ ? g_tune_ctas_per_sm : occ;
+        grid = (long long)sm_count() * bps;
+        if (grid > ngroups) grid = ngroups;
     }
-    long long grid = (long long)sms * bps;
-    if (grid > ngroups) grid = ngroups;
     kernel<<<(unsigned)grid, BLOCK, 0, stream>>>(p);
     MBRF_LAUNCH_CHECK();
     return MBRF_OK;
@@ -449,15 +420,14 @@ static int dispatch_ng_spt(const Params &p, int ng, int spt, cudaStream_t stream
     } else if constexpr (MODE == 1 || MODE == 3) {
         MBRF_CASE(2, 1);
     } else {
-        if (spt == 1) {
-            if (ng == 0) MBRF_CASE(0, 1);
-            if (ng == 1) MBRF_CASE(1, 1);
-            MBRF_CASE(2, 1);
-        } else {
+        if (MODE == 0 && spt == 2) {
             if (ng == 0) MBRF_CASE(0, 2);
             if (ng == 1) MBRF_CASE(1, 2);
             MBRF_CASE(2, 2);
         }
+        if (ng == 0) MBRF_CASE(0, 1);
+        if (ng == 1) MBRF_CASE(1, 1);
+        MBRF_CASE(2, 1);
     }
 #undef MBRF_CASE
 }
@@ -532,7 +502,7 @@ int mbrf_bloch_device(const double *b1real, const double *b1imag, const double *
     p.m0x = m0x; p.m0y = m0y; p.m0z = m0z; p.m0_stride = m0_stride > 0 ? m0_stride : 1;
     p.mx = mx; p.my = my; p.mz = mz; p.gamma = gamma; p.b1scale = nullptr;
     const int ng = (ygrad || zgrad) ? 2 : (xgrad ? 1 : 0);
-    int spt = g_tune_spt ? g_tune_spt : 2;
+    int spt = g_tune_spt ? g_tune_spt : 1;
     switch (mode) {
     case 0: return dispatch_ng_spt<0, false>(p, ng, spt, st);
     case 1: return dispatch_ng_spt<1, false>(p, ng, 1, st);

@@ -12,7 +12,7 @@
 // u = 0 value of the same polynomials.  Update (abrx.c:103-111):
 //        a <- al*a - be*conj(b)        b <- al*b + be*conj(a)
 #include "common.h"
-#include "rot_poly.h"
+#include "rot_coeffs.cuh"
 #include <cstring>
 
 namespace mbrf {
@@ -25,7 +25,6 @@ constexpr int BLOCK = 128;
 constexpr int WS_HEADER = 8;
 enum { E_RFR = 0, E_RFI, E_C, E_GX, E_GY };
 enum { B_C = 0, B_GX, B_GY };
-enum { TIER_SMALL = 0, TIER_MED = 1, TIER_BIG = 2, TIER_ANY = 3 };
 
 __global__ void slr_prep_kernel(const double *__restrict__ rfr, const double *__restrict__ rfi,
                                 const double *__restrict__ gx, const double *__restrict__ gy, int ns,
@@ -48,45 +47,6 @@ __global__ void slr_prep_kernel(const double *__restrict__ rfr, const double *__
     amax(ws + B_C, e[E_C]);
     amax(ws + B_GX, e[E_GX]);
     amax(ws + B_GY, e[E_GY]);
-}
-
-template <int N>
-__device__ __forceinline__ double horner(const double (&c)[N], double u)
-{
-    double acc = c[N - 1];
-#pragma unroll
-    for (int i = N - 2; i >= 0; --i) acc = fma(acc, u, c[i]);
-    return acc;
-}
-
-// w = cos(phi/2), s2 = 2 sin(phi/2)/phi
-template <int TIER>
-__device__ __forceinline__ void rot_coeffs(double u, double &w, double &s2)
-{
-    if (TIER == TIER_SMALL) {
-        constexpr double cc[] = ROT_C_SMALL;
-        constexpr double cs[] = ROT_S_SMALL;
-        w = horner(cc, u);
-        s2 = horner(cs, u);
-    } else if (TIER == TIER_MED) {
-        constexpr double cc[] = ROT_C_MED;
-        constexpr double cs[] = ROT_S_MED;
-        w = horner(cc, u);
-        s2 = horner(cs, u);
-    } else {
-        constexpr double cc[] = ROT_C_BIG;
-        constexpr double cs[] = ROT_S_BIG;
-        if (TIER == TIER_BIG || u <= ROT_U_BIG) {
-            w = horner(cc, u);
-            s2 = horner(cs, u);
-        } else {
-            const double phi = sqrt(u);
-            double s, c;
-            sincos(0.5 * phi, &s, &c);
-            w = c;
-            s2 = 2.0 * s / phi;
-        }
-    }
 }
 
 struct Params {
@@ -178,7 +138,7 @@ __global__ void __launch_bounds__(BLOCK) slr_kernel(const Params p)
         State st[SPT];
         bool active[SPT];
         long long lp[SPT];
-        int tier = TIER_SMALL;
+        int tier = TIER_TINY;
 #pragma unroll
         for (int j = 0; j < SPT; ++j) {
             lp[j] = g * group_pos + (long long)j * BLOCK + tid;
@@ -191,8 +151,8 @@ __global__ void __launch_bounds__(BLOCK) slr_kernel(const Params p)
             st[j].degenerate = false;
             const double cgb = fabs(st[j].x) * bgx + fabs(st[j].y) * bgy;
             const double ub = fma(cgb, cgb, bc);
-            const int tj = ub <= ROT_U_SMALL ? TIER_SMALL : ub <= ROT_U_MED ? TIER_MED : ub <= ROT_U_BIG ? TIER_BIG : TIER_ANY;
-            tier = max(tier, active[j] ? tj : TIER_SMALL);
+            const int tj = rot_tier(ub);
+            tier = max(tier, active[j] ? tj : TIER_TINY);
         }
         tier = __reduce_max_sync(0xffffffffu, tier);
         for (int ti = 0; ti < ntiles; ++ti, ++k) {
@@ -200,6 +160,7 @@ __global__ void __launch_bounds__(BLOCK) slr_kernel(const Params p)
             const double *tile = tiles[k % NBUF];
             mbar_wait(&full[k % NBUF], (k / NBUF) & 1u);
             switch (tier) {
+            case TIER_TINY: run_tile<HAVE_Y, SPT, TIER_TINY, TRACK_ZERO>(tile, n, st); break;
             case TIER_SMALL: run_tile<HAVE_Y, SPT, TIER_SMALL, TRACK_ZERO>(tile, n, st); break;
             case TIER_MED: run_tile<HAVE_Y, SPT, TIER_MED, TRACK_ZERO>(tile, n, st); break;
             case TIER_BIG: run_tile<HAVE_Y, SPT, TIER_BIG, TRACK_ZERO>(tile, n, st); break;

@@ -145,9 +145,12 @@ def test_full_size_properties(mbrf):
     eff = df[j] + dp[i, 0] * hz_per_cm
     one = mbrf.blochC(b1.reshape(-1, 1), np.zeros((nt, 1)), dt, 1e3, 1e3, np.array([eff]), 0.0, 0)
     assert abs(one[0][0, 0] - mx[i, j]) < 1e-9 and abs(one[2][0, 0] - mz[i, j]) < 1e-9
-    # symmetric real pulse: Mz even in the effective offset, on resonance a pi/2 excitation
-    centre = mbrf.blochC(b1.reshape(-1, 1), np.zeros((nt, 1)), dt, 1e3, 1e3, np.array([0.0, 300.0, -300.0]), 0.0, 0)
-    assert abs(centre[2][0, 0]) < 1e-3 and abs(centre[2][0, 1] - centre[2][0, 2]) < 1e-9
+    # symmetric real pulse: Mz even in the effective offset; on resonance the flip angle is
+    # sum(b1)*gamma*dt (all rotations about one axis), ~pi/2 for this 'ex' pulse
+    centre = mbrf.blochC(b1.reshape(-1, 1), np.zeros((nt, 1)), dt, 1e30, 1e30, np.array([0.0, 300.0, -300.0]), 0.0, 0)
+    flip = b1.real.sum() * 6726.1 * dt
+    assert abs(flip - np.pi / 2) < 0.01
+    assert abs(centre[2][0, 0] - np.cos(flip)) < 1e-12 and abs(centre[2][0, 1] - centre[2][0, 2]) < 1e-9
 
 
 def test_full_size_sample_vs_oracle(mbrf, oracle):
