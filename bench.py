@@ -47,7 +47,8 @@ NTIME = 512
 NF_PER_GPU = 1000
 NPOS = 1000
 FLOPS_PER_SPIN_STEP = 76        # blochC.c:330-361 as written, sqrt/div/sin/cos at 1 each
-FP64_INST_PER_SPIN_STEP = 39    # what our kernel issues on the FP64 pipe (cuobjdump -sass, 1 gradient axis, tier SMALL)
+FP64_INST_PER_SPIN_STEP = 35    # what our kernel issues on the FP64 pipe for this workload (cuobjdump -sass:
+                                # constant dt and gradient -> constant-rz loop, |phi| <= 1 rad -> tier TINY)
 BYTES_PER_SPIN = 56             # df (8) + M0/positions amortised (24) + M out (24): SURVEY.md 8(d)
 WORKLOAD = ("bloch cfg2: 512-sample dzrf 'ex' pulse x 1e6 spins per GPU "
             "(1000 df x 1000 dp, Gx=0.05 G/cm, T1=T2=1e3 s, mode 0, blochC gamma)")
@@ -231,20 +232,18 @@ def run_ours(args):
     b1r, b1i, gx = T(wl["b1"].real), T(wl["b1"].imag), T(wl["gx"])
     dts, df, dx = T(np.full(nt, wl["dt"])), T(wl["df"]), T(wl["dx"])
     out = torch.empty((3, nlocal), dtype=torch.float64, device=dev)
-    gathered = [torch.empty((3, nlocal), dtype=torch.float64, device=dev) for _ in range(world)] \
-        if (world > 1 and rank == 0) else None
     ws = torch.empty(int(lib.mbrf_bloch_workspace_bytes(nt)), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream()
 
+    from multiband_rf_pulse_design_b200.shard import bloch_sharded
+    dev_args = dict(b1r=b1r.data_ptr(), b1i=b1i.data_ptr(), gx=gx.data_ptr(), gy=None, gz=None, dt=dts.data_ptr(),
+                    ntime=nt, t1=wl["t1"], t2=wl["t2"], df=df.data_ptr(), nf=nf, dx=dx.data_ptr(), dy=None, dz=None,
+                    npos=npos)
+
     def step_device():
-        check(lib.mbrf_bloch_device(b1r.data_ptr(), b1i.data_ptr(), gx.data_ptr(), None, None, dts.data_ptr(), nt,
-                                    wl["t1"], wl["t2"], df.data_ptr(), nf, dx.data_ptr(), None, None, npos,
-                                    spin0, nlocal, None, None, None, 1,
-                                    out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), 0, m.GAMMA_C13,
-                                    ws.data_ptr(), stream.cuda_stream))
-        if world > 1:
-            dist.gather(out, gathered, dst=0)        # the one collective of the path: final gather over NVLink
+        # this rank's contiguous spin range, then the one collective of the path: the final gather (NCCL/NVLink)
+        return bloch_sharded(lib, dev_args, nf * npos, out, ws.data_ptr(), stream.cuda_stream, 0, m.GAMMA_C13)
 
     def barrier():
         if world > 1:
@@ -349,7 +348,7 @@ def run_ours(args):
         except (OSError, ValueError):
             traffic = None
     roofline = {
-        "bound": "fp64", "kernel": "mbrf::bloch::bloch_kernel<0,1,2,false>",
+        "bound": "fp64", "kernel": "mbrf::bloch::bloch_kernel<0,1,1,false>",
         "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value,
         "traffic": traffic,
         "peak_source": "FP64 FMA peak measured in this run by mbrf_measure_fp64_peak (DFMA-only kernel); "

@@ -210,7 +210,7 @@ __device__ __forceinline__ void run_tile(const double *__restrict__ tile, int n,
                                          const bool (&active)[SPT], double *const (&ox)[SPT],
                                          double *const (&oy)[SPT], double *const (&oz)[SPT], int t0)
 {
-#pragma unroll 2
+#pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const double *e = tile + i * SD;
 #pragma unroll

@@ -53,7 +53,7 @@ static inline int mxIsEmpty(const mxArray *a) { return a->m * a->n == 0; }
 static inline mxArray *mxCreateDoubleMatrix(size_t m, size_t n, mxComplexity c)
 {
     mxArray *a = (mxArray *)calloc(1, sizeof(mxArray));
-    size_t cnt = m * n ? m * n : 1;
+    size_t cnt = (m * n) > 0 ? m * n : 1;
     a->m = m; a->n = n; a->ndim = 2;
     a->dims[0] = (int)m; a->dims[1] = (int)n; a->dims[2] = 1;
     a->pr = (double *)calloc(cnt, sizeof(double));

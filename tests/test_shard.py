@@ -1,0 +1,67 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes exercise the spin-range partition and the
+final gather (the only collective of the path)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_shard_bounds_cover_exactly():
+    from multiband_rf_pulse_design_b200.shard import shard_bounds
+    for n in (0, 1, 7, 1000, 10 ** 6, 10 ** 6 + 3):
+        for w in (1, 2, 3, 4, 8):
+            b = shard_bounds(n, w)
+            assert len(b) == w and b[0][0] == 0
+            assert sum(c for _, c in b) == n
+            assert all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(c for _, c in b) - min(c for _, c in b) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(5, 0)
+
+
+def _worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multiband_rf_pulse_design_b200.shard import gather_planes, shard_bounds
+    bounds = shard_bounds(n, world)
+    s0, cnt = bounds[rank]
+    width = max(c for _, c in bounds)
+    local = torch.full((3, width), float("nan"), dtype=torch.float64)
+    s = torch.arange(s0, s0 + cnt, dtype=torch.float64)
+    # stand-in for the kernel's output: a known function of the GLOBAL spin index per plane
+    local[0, :cnt], local[1, :cnt], local[2, :cnt] = s, -2 * s, s * s
+    full = gather_planes(local, [c for _, c in bounds], dst=0)
+    if rank == 0:
+        ref = torch.arange(n, dtype=torch.float64)
+        ok = (full.shape == (3, n) and torch.equal(full[0], ref) and torch.equal(full[1], -2 * ref)
+              and torch.equal(full[2], ref * ref))
+        q.put(bool(ok))
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1001, 4096])
+def test_gather_world2_gloo(n):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
