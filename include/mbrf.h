@@ -168,6 +168,48 @@ int mbrf_abr_device(const double *rfr, const double *rfi, const double *gx, cons
                     void *workspace, void *stream);
 unsigned long long mbrf_abr_workspace_bytes(int ns);
 
+/* ---- convex FIR design step: batched restarted PDHG --------------------------- */
+
+/*
+ * Replaces the SOLVE inside  fir_ap_cvx.m:160-169 (CVX -> SeDuMi/SDPT3),  ss/fir_linprog.m:246-252
+ * (MATLAB linprog) and the probes of fir_ap.m:51-173 / ss/fir_min_order_linprog.m:98-211: B problems
+ *
+ *      minimise c^T z   s.t.   lo <= K z <= hi,   bl <= z <= bu,   ||(z_pi, z_pj)|| <= rho
+ *
+ * that share one frequency-sampled Fourier matrix K (M x N), generated ON THE DEVICE from
+ *      K[i][j] = col_amp[j] * {1, cos, sin}[col_type[j]] (w_row[i] * col_kappa[j]),  col_type 3 = zero,
+ *      K[i][tcol] = tcoef[i]   (tcol < 0: no such column)
+ * which covers A = [1, 2cos(w k), 2sin(w k)] (fir_ap_cvx.m:100), [Acos Asin] (fir_linprog.m:195-217)
+ * and the ripple_stop column of fir_ap_cvx.m:165.  HOST pointers; per-design arrays are [dim x B]
+ * row-major (design index fastest).  obj_upper[b] (optional): an upper bound on the objective of any
+ * feasible point; a dual bound above it certifies infeasibility (status 2).
+ *   z_out [N x B]: solutions in the caller's units;  info_out [B x 8]: status (1 solved, 2 infeasible,
+ *   3 iteration limit), iterations, objective, dual objective, max row violation, natural residual,
+ *   rigorous lower bound on the optimum, primal weight;  colscale_out [N] optional.
+ * The status maps onto the reference's strings: 1 -> 'Solved', 2/3 -> 'Failed' (fir_ap_cvx.m:176-182).
+ */
+int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M,
+                        const int *col_type, const double *col_kappa, const double *col_amp, int N, int tcol,
+                        const int *pair_i, const int *pair_j, int npairs,
+                        const double *c, const double *lo, const double *hi,
+                        const double *bl, const double *bu, const double *rho, int B,
+                        const double *obj_upper, int max_iter, int check_every,
+                        double eps_pr, double eps_dr, double eps_gap,
+                        double *z_out, double *info_out, double *colscale_out);
+
+/* Device-resident core of the above on a padded batch (Mp, Np, Bp multiples of 64; arrays [dim x Bp]);
+ * K row-major [Mp x ldk] with columns already scaled, KT its transpose [Np x Mp]. */
+int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
+unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
+int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk,
+                           const double *c, const double *lo, const double *hi,
+                           const double *bl, const double *bu,
+                           const int *pair_i, const int *pair_j, int npairs, const double *rho,
+                           int Bp, int B, const double *obj_upper,
+                           int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
+                           double *z_out, double *y_out, double *info_out,
+                           void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

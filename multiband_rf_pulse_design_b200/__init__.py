@@ -6,6 +6,7 @@ behaviour) over the C ABI in ``include/mbrf.h`` / ``libmbrf.so``:
 
     blochC, blochH, bloch            <- bloch_simulation/blochC.c, blochH.c (mexFunction)
     abrx, abrm, abr                  <- rf_tools/mex5/abrx.c, rf_tools/abrm.m, rf_tools/abr.m
+    fir_ap_cvx, fir_ap               <- fir_ap_cvx.m, fir_ap.m (solve = batched restarted PDHG on the GPU)
 
 There is no CPU fallback: importing works anywhere, computing needs the built library
 and a CUDA device.
@@ -13,6 +14,9 @@ and a CUDA device.
 from ._lib import lib, MbrfError, library_path  # noqa: F401
 from .bloch import bloch, blochC, blochH, blochsimfz, GAMMA_C13, GAMMA_H1  # noqa: F401
 from .slr import abr, abrm, abrx  # noqa: F401
+from .fir import (fir_ap, fir_ap_cvx, fir_ap_cvx_batch, fir_linprog, fir_min_order,  # noqa: F401
+                  fir_min_order_linprog, fmp2)
 
-__all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "lib", "MbrfError",
+__all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "fir_ap", "fir_ap_cvx",
+           "fir_ap_cvx_batch", "fir_linprog", "fir_min_order", "fir_min_order_linprog", "fmp2", "lib", "MbrfError",
            "library_path", "GAMMA_C13", "GAMMA_H1"]

@@ -55,6 +55,12 @@ SIGNATURES = {
     "mbrf_abr_device": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _ll, _ll,
                              _vp, _vp, _vp, _vp, _vp, _vp]),
     "mbrf_abr_workspace_bytes": (C.c_ulonglong, [_i]),
+    "mbrf_pdhg_padded_sizes": (_i, [_i, _i, _i, c_int_p, c_int_p, c_int_p]),
+    "mbrf_pdhg_workspace_bytes": (C.c_ulonglong, [_i, _i, _i]),
+    "mbrf_pdhg_solve_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp,
+                                    _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
+    "mbrf_fir_pdhg_solve": (_i, [_dp, _dp, _i, c_int_p, _dp, _dp, _i, _i, c_int_p, c_int_p, _i,
+                                 _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _i, _i, _d, _d, _d, _dp, _dp, _dp]),
 }
 
 

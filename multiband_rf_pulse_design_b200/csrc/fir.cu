@@ -1,0 +1,238 @@
+// Host-pointer front end of the FIR design solver: builds the frequency-sampled Fourier matrix on the
+// device from a column/row description (so the 30 MB matrix never crosses PCIe), scales its columns,
+// uploads the per-design vectors, runs the batched PDHG of pdhg.cu and returns the solutions.
+//
+// The matrices of the reference all have entries amp_j * {1, cos, sin}(w_i * kappa_j):
+//   fir_ap_cvx.m:100      A = [1, 2cos(w k), 2sin(w k)],  k = 1..n-1
+//   ss/fir_linprog.m:195-217  Acos = [1, 2cos(w k)] or 2cos(w (k+1/2)),  Asin likewise
+//   fir_qp_cvx.m:96-109   [cos(w k), sin(w k); -sin(w k), cos(w k)],  k = 0..n-1
+// plus one optional extra column with explicit per-row coefficients (ripple_stop of fir_ap_cvx.m:165).
+#include "common.h"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+extern "C" {
+int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
+unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
+int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, const double *c, const double *lo,
+                           const double *hi, const double *bl, const double *bu, const int *pair_i,
+                           const int *pair_j, int npairs, const double *rho, int Bp, int B,
+                           const double *obj_upper, int max_iter, int check_every, double eps_pr,
+                           double eps_dr, double eps_gap, double *z_out, double *y_out, double *info_out,
+                           void *workspace, void *stream);
+}
+
+namespace mbrf {
+namespace fir {
+
+// K[i][j] = amp_j * trig_j(w_i * kappa_j)   (type 0: 1, 1: cos, 2: sin, 3: 0);  K[i][tcol] = tcoef[i]
+__global__ void build_matrix_kernel(const double *__restrict__ w, const double *__restrict__ tcoef, int M,
+                                    const int *__restrict__ type, const double *__restrict__ kappa,
+                                    const double *__restrict__ amp, int N, int tcol, double *__restrict__ K,
+                                    int Mp, int ldk)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)Mp * ldk) return;
+    const int i = (int)(idx / ldk), j = (int)(idx % ldk);
+    double v = 0.0;
+    if (i < M && j < N) {
+        if (j == tcol) v = tcoef ? tcoef[i] : 0.0;
+        else {
+            const int t = type[j];
+            if (t == 0) v = amp[j];
+            else if (t == 1) v = amp[j] * cos(w[i] * kappa[j]);
+            else if (t == 2) v = amp[j] * sin(w[i] * kappa[j]);
+        }
+    }
+    K[idx] = v;
+}
+
+// cs2[j] = sum_i K[i][j]^2 : one block per 32 columns, threads stride the rows
+__global__ void col_norm2_kernel(const double *__restrict__ K, int Mp, int ldk, double *__restrict__ cs2)
+{
+    __shared__ double sh[8][33];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.y; i < Mp; i += 8) { const double v = K[(size_t)i * ldk + j]; s = fma(v, v, s); }
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        for (int r = 1; r < 8; ++r) s += sh[r][threadIdx.x];
+        cs2[j] = s;
+    }
+}
+
+// scale the columns of K in place and write the transposed copy KT [ldk x Mp] (32 x 32 smem transpose)
+__global__ void scale_transpose_kernel(double *__restrict__ K, double *__restrict__ KT, int Mp, int ldk,
+                                       const double *__restrict__ inv_cs)
+{
+    __shared__ double t[32][33];
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const size_t o = (size_t)(i0 + r) * ldk + j0 + threadIdx.x;
+        const double v = K[o] * inv_cs[j0 + threadIdx.x];
+        K[o] = v;
+        t[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) KT[(size_t)(j0 + r) * Mp + i0 + threadIdx.x] = t[threadIdx.x][r];
+}
+
+struct Ctx {
+    DeviceScratch dev;
+    cudaStream_t stream = nullptr;
+    int stream_device = -1;
+};
+static thread_local Ctx t_ctx;
+
+}  // namespace fir
+}  // namespace mbrf
+
+using namespace mbrf;
+using namespace mbrf::fir;
+
+extern "C" {
+
+/*
+ * Solve B convex FIR design problems that share one frequency-sampled matrix.  HOST pointers.
+ *   minimise c^T z  s.t.  lo <= K z <= hi,  bl <= z <= bu,  ||(z_pi, z_pj)|| <= rho
+ * per-design arrays are [dim x B] row-major (design index fastest).  The solver scales the columns of K
+ * to unit norm internally (pair members share a scale) and returns z in the caller's units.
+ * info: [B x 8] = status (1 solved, 2 infeasible, 3 iteration limit), iterations, objective, dual objective,
+ *       max row violation, natural residual, rigorous lower bound on the optimum, primal weight.
+ */
+int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const int *col_type,
+                        const double *col_kappa, const double *col_amp, int N, int tcol, const int *pair_i,
+                        const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
+                        const double *bl, const double *bu, const double *rho, int B, const double *obj_upper,
+                        int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
+                        double *z_out, double *info_out, double *colscale_out)
+{
+    if (int rc = require_device()) return rc;
+    if (M <= 0 || N <= 0 || B <= 0 || !w_row || !col_type || !col_kappa || !col_amp || !c || !lo || !hi || !bl ||
+        !bu || !z_out || !info_out || npairs < 0 || (npairs && (!pair_i || !pair_j || !rho)) || tcol >= N) {
+        set_error("fir_pdhg_solve: bad arguments");
+        return MBRF_EINVAL;
+    }
+    int Mp, Np, Bp;
+    mbrf_pdhg_padded_sizes(M, N, B, &Mp, &Np, &Bp);
+    const int ldk = Np;
+    Ctx &cx = t_ctx;
+    int dev = 0;
+    MBRF_CUDA(cudaGetDevice(&dev));
+    if (!cx.stream || cx.stream_device != dev) {
+        MBRF_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+        cx.stream_device = dev;
+    }
+    cudaStream_t st = cx.stream;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
+    const size_t bK = al((size_t)Mp * ldk * 8), bw = al((size_t)Mp * 8), bcol = al((size_t)Np * 8),
+                 bz = al(zn * 8), by = al(yn * 8), bpair = al((size_t)(npairs > 0 ? npairs : 1) * 4),
+                 brho = al((size_t)(npairs > 0 ? npairs : 1) * Bp * 8), binfo = al((size_t)Bp * 8 * 8),
+                 bws = al(mbrf_pdhg_workspace_bytes(Mp, Np, Bp));
+    const size_t total = 2 * bK + 2 * bw + 4 * bcol + 4 * bz /*c,bl,bu,zout*/ + 2 * by /*lo,hi*/ + 2 * bpair + brho +
+                         binfo + al((size_t)Bp * 8) + bws;
+    if (int rc = cx.dev.reserve(total)) return rc;
+    char *d = (char *)cx.dev.ptr;
+    auto take = [&](size_t b) { char *p = d; d += b; return p; };
+    double *dK = (double *)take(bK), *dKT = (double *)take(bK), *dw = (double *)take(bw), *dt = (double *)take(bw);
+    int *dtype = (int *)take(bcol);
+    double *dkap = (double *)take(bcol), *damp = (double *)take(bcol), *dcs = (double *)take(bcol);
+    double *dc = (double *)take(bz), *dbl = (double *)take(bz), *dbu = (double *)take(bz), *dz = (double *)take(bz);
+    double *dlo = (double *)take(by), *dhi = (double *)take(by);
+    int *dpi = (int *)take(bpair), *dpj = (int *)take(bpair);
+    double *drho = (double *)take(brho), *dinfo = (double *)take(binfo), *dupper = (double *)take(al((size_t)Bp * 8));
+    void *dws = take(bws);
+
+    // ---- matrix: build, column norms, scale ----
+    MBRF_CUDA(cudaMemcpyAsync(dw, w_row, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    if (tcoef) MBRF_CUDA(cudaMemcpyAsync(dt, tcoef, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    MBRF_CUDA(cudaMemcpyAsync(dtype, col_type, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    MBRF_CUDA(cudaMemcpyAsync(dkap, col_kappa, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    MBRF_CUDA(cudaMemcpyAsync(damp, col_amp, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    const long long nK = (long long)Mp * ldk;
+    build_matrix_kernel<<<(unsigned)((nK + 255) / 256), 256, 0, st>>>(dw, tcoef ? dt : nullptr, M, dtype, dkap, damp, N,
+                                                                     tcol, dK, Mp, ldk);
+    MBRF_LAUNCH_CHECK();
+    col_norm2_kernel<<<ldk / 32, dim3(32, 8), 0, st>>>(dK, Mp, ldk, dcs);
+    MBRF_LAUNCH_CHECK();
+    std::vector<double> cs((size_t)Np), inv((size_t)Np);
+    MBRF_CUDA(cudaMemcpyAsync(cs.data(), dcs, (size_t)Np * 8, cudaMemcpyDeviceToHost, st));
+    MBRF_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < Np; ++j) cs[j] = cs[j] > 0.0 ? sqrt(cs[j]) : 1.0;
+    for (int q = 0; q < npairs; ++q) {  // a disk must stay a disk: both members share one scale
+        const int i = pair_i[q], j = pair_j[q];
+        if (i < 0 || i >= N || j < 0 || j >= N) { set_error("fir_pdhg_solve: pair %d out of range", q); return MBRF_EINVAL; }
+        const double pm = sqrt(0.5 * (cs[i] * cs[i] + cs[j] * cs[j]));
+        cs[i] = cs[j] = pm;
+    }
+    for (int j = 0; j < Np; ++j) inv[j] = 1.0 / cs[j];
+    MBRF_CUDA(cudaMemcpyAsync(dcs, inv.data(), (size_t)Np * 8, cudaMemcpyHostToDevice, st));
+    scale_transpose_kernel<<<dim3(ldk / 32, Mp / 32), dim3(32, 8), 0, st>>>(dK, dKT, Mp, ldk, dcs);
+    MBRF_LAUNCH_CHECK();
+    if (colscale_out) memcpy(colscale_out, cs.data(), (size_t)N * 8);
+
+    // ---- per-design vectors: pad to [dim_p x Bp], apply the column scaling on the way ----
+    const double INF = INFINITY;
+    std::vector<double> h;
+    auto upload_cols = [&](const double *src, double *dst, int mode) -> int {   // N-side arrays
+        // mode 0: c / cs ; 1: bound * cs (padding: 0 / [0,0])
+        h.assign(zn, 0.0);
+        for (int j = 0; j < N; ++j)
+            for (int b = 0; b < B; ++b) {
+                const double v = src[(size_t)j * B + b];
+                h[(size_t)j * Bp + b] = mode == 0 ? v / cs[j] : v * cs[j];
+            }
+        MBRF_CUDA(cudaMemcpyAsync(dst, h.data(), zn * 8, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+        return MBRF_OK;
+    };
+    if (int rc = upload_cols(c, dc, 0)) return rc;
+    if (int rc = upload_cols(bl, dbl, 1)) return rc;
+    if (int rc = upload_cols(bu, dbu, 1)) return rc;
+    auto upload_rows = [&](const double *src, double *dst, double pad) -> int {
+        h.assign(yn, pad);
+        for (int i = 0; i < M; ++i)
+            for (int b = 0; b < B; ++b) h[(size_t)i * Bp + b] = src[(size_t)i * B + b];
+        MBRF_CUDA(cudaMemcpyAsync(dst, h.data(), yn * 8, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+        return MBRF_OK;
+    };
+    if (int rc = upload_rows(lo, dlo, -INF)) return rc;
+    if (int rc = upload_rows(hi, dhi, INF)) return rc;
+    if (npairs) {
+        MBRF_CUDA(cudaMemcpyAsync(dpi, pair_i, (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaMemcpyAsync(dpj, pair_j, (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
+        h.assign((size_t)npairs * Bp, 0.0);
+        for (int q = 0; q < npairs; ++q)
+            for (int b = 0; b < B; ++b) h[(size_t)q * Bp + b] = rho[(size_t)q * B + b] * cs[pair_i[q]];
+        MBRF_CUDA(cudaMemcpyAsync(drho, h.data(), (size_t)npairs * Bp * 8, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+    }
+    if (obj_upper) {
+        h.assign((size_t)Bp, INF);
+        for (int b = 0; b < B; ++b) h[b] = obj_upper[b];
+        MBRF_CUDA(cudaMemcpyAsync(dupper, h.data(), (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+    }
+
+    int rc = mbrf_pdhg_solve_device(dK, dKT, Mp, Np, ldk, dc, dlo, dhi, dbl, dbu, npairs ? dpi : nullptr,
+                                    npairs ? dpj : nullptr, npairs, npairs ? drho : nullptr, Bp, B,
+                                    obj_upper ? dupper : nullptr, max_iter, check_every, eps_pr, eps_dr, eps_gap, dz,
+                                    nullptr, dinfo, dws, st);
+    if (rc) return rc;
+    h.assign(zn, 0.0);
+    std::vector<double> info((size_t)Bp * 8);
+    MBRF_CUDA(cudaMemcpyAsync(h.data(), dz, zn * 8, cudaMemcpyDeviceToHost, st));
+    MBRF_CUDA(cudaMemcpyAsync(info.data(), dinfo, (size_t)Bp * 64, cudaMemcpyDeviceToHost, st));
+    MBRF_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < N; ++j)
+        for (int b = 0; b < B; ++b) z_out[(size_t)j * B + b] = h[(size_t)j * Bp + b] / cs[j];
+    memcpy(info_out, info.data(), (size_t)B * 64);
+    return MBRF_OK;
+}
+
+}  // extern "C"

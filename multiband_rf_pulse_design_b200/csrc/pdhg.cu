@@ -1,0 +1,671 @@
+// Batched restarted PDHG for the convex FIR design step (fir_ap_cvx.m:160-169, ss/fir_linprog.m:246,
+// and — through polygonal/disk rows — fir_qp_cvx.m) on B200.
+//
+// Canonical form, one dense frequency-sampled Fourier matrix K shared by a batch of B designs:
+//
+//        minimise  c^T z    subject to   lo <= K z <= hi ,   z in X
+//        X = product of boxes  bl_j <= z_j <= bu_j  and 2-D disks  ||(z_i, z_j)|| <= rho
+//
+// Every per-design vector is stored [dim x Bp] with the design index fastest, so that
+//   * the two products of an iteration, K * Zbar and K^T * Y, are dense fp64 GEMMs
+//     [Mp x Np] x [Np x Bp] and [Np x Mp] x [Mp x Bp] (kernels dgemm_nn / dgemm_tn below), and
+//   * all vector kernels (prox, projections, reductions) are coalesced over designs.
+// A single design is the same code with Bp = 16 (the matrix then streams from L2: HBM/L2-bound).
+//
+// Iteration (Chambolle-Pock with PDLP-style restarts and primal weight, per design b):
+//     g    = c + K^T y
+//     z+   = P_X(z - tau_b g)            zbar = 2 z+ - z
+//     v    = y + sigma_b K zbar          y+   = v - sigma_b clip(v / sigma_b, lo, hi)
+//     tau_b = eta / omega_b, sigma_b = eta * omega_b, eta = 0.9 / ||K||_2
+// Every `check_every` iterations both the running average and the current iterate are scored by
+//     err = max(row violation, natural residual ||z - P_X(z - g)||_inf, |c^T z - (-h*(y) + g^T z)|)
+// and the better one becomes the restart candidate (sufficient / necessary decay or 0.36 rule).
+//
+// Precision: fp64 throughout.  The tolerance of the path (constraint violation <= 1e-6 on |H|^2 values
+// of order 1, objective 1e-4 relative on values of order 1e-2) is reached only in the last ~70 % of
+// the iterations, where fp32-accumulate tensor-core products (tcgen05 has no fp64 kind) no longer
+// contract; see DESIGN.md section 6 for the measured numbers and the split-precision plan.
+#include "common.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace mbrf {
+namespace pdhg {
+
+// ---------------------------------------------------------------------------
+// fp64 SIMT GEMM:  C[R x Bp] = AT^T * X  with AT stored [kdim x R] row-major (ld = ldat), X [kdim x Bp].
+//   K * Zbar  : AT = K^T (kept as a second copy, [Np x Mp]),  kdim = Np, R = Mp
+//   K^T * Y   : AT = K   ([Mp x Np]),                          kdim = Mp, R = Np, split over kdim (blockIdx.z)
+// Tile 64 x 64 per CTA of 64 threads (2 warps); each thread owns an 8 x 8 micro-tile: per k it issues
+// 8 LDS.128 for 64 DFMA, so the FP64 pipe (2 issue cycles per DFMA) is the only busy unit.  Operand tiles
+// arrive with 16-byte cp.async (LDGSTS) into a 2-stage shared-memory ring: no staging registers.
+// Many small CTAs (976 for a 7872 x 512 output) keep the tail of the last wave short on 148 SMs.
+// ---------------------------------------------------------------------------
+constexpr int BM = 64, BN = 64, BK = 16, GEMM_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 128 threads, each an 8 (rows) x 4 (columns) micro-tile: rows q*16 + ty*2 + {0,1} (q = 0..3, ty = 0..7),
+// columns q*32 + tx*2 + {0,1} (q = 0..1, tx = 0..15).  The 8 threads of an LDS.128 phase read 128 contiguous
+// bytes: no bank conflicts.  ~110 registers -> 4 CTAs = 16 warps per SM, which the FP64 pipe needs: one warp
+// alone cannot issue a DFMA every 2 cycles (measured: 71 % pipe-busy at 2 warps per scheduler, ncu).
+__global__ void __launch_bounds__(GEMM_THREADS, 4)
+dgemm_kernel(const double *__restrict__ AT, int ldat,         // [kdim x R] row-major
+             const double *__restrict__ X, int Bp,            // [kdim x Bp]
+             double *__restrict__ C,                          // [R x Bp], one slab per blockIdx.z
+             int kdim_total, int kchunk, long long slab)
+{
+    __shared__ __align__(16) double As[2][BK][BM];
+    __shared__ __align__(16) double Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * kchunk;
+    const int k_end = min(kdim_total, k_begin + kchunk);
+    const int ty = tid / 16, tx = tid % 16;
+
+    // each cp.async moves 2 doubles; a 16 x 64 tile is 512 such pieces = 4 per thread, for A and for B
+    auto load_slice = [&](int buf, int k0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int piece = e * GEMM_THREADS + tid;        // kk = piece / 32, c = (piece % 32) * 2
+            const int kk = piece >> 5, c = (piece & 31) * 2;
+            cp_async16(&As[buf][kk][c], AT + (size_t)(k0 + kk) * ldat + row0 + c);
+            cp_async16(&Bs[buf][kk][c], X + (size_t)(k0 + kk) * Bp + col0 + c);
+        }
+        cp_async_commit();
+    };
+
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    int buf = 0;
+    if (k_begin < k_end) load_slice(0, k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        const bool more = k0 + BK < k_end;
+        if (more) {
+            load_slice(buf ^ 1, k0 + BK);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 av = *reinterpret_cast<const double2 *>(&As[buf][kk][q * 16 + ty * 2]);
+                a[2 * q] = av.x; a[2 * q + 1] = av.y;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const double2 bv = *reinterpret_cast<const double2 *>(&Bs[buf][kk][q * 32 + tx * 2]);
+                b[2 * q] = bv.x; b[2 * q + 1] = bv.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();   // everyone is done with `buf` before the next iteration's cp.async overwrites it
+        buf ^= 1;
+    }
+    double *Cz = C + (size_t)blockIdx.z * slab;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = row0 + (i >> 1) * 16 + ty * 2 + (i & 1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<double2 *>(Cz + (size_t)r * Bp + col0 + q * 32 + tx * 2) =
+                make_double2(acc[i][2 * q], acc[i][2 * q + 1]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// solver state
+// ---------------------------------------------------------------------------
+struct Ctl {           // per-design control block (device), doubles for simplicity
+    double tau, sigma, omega;
+    double last_err, prev_err;
+    double since, cnt;          // iterations since last restart / samples in the running sums
+    double status;              // 0 running, 1 solved, 2 infeasible (certificate), 3 iteration limit
+    double iters;               // iteration at which status was decided
+    double obj, dual, pr, dr, rigorous;
+    double restart, use_avg;    // decisions of the last check
+};
+
+struct Problem {
+    int Mp, Np, Bp, B, npairs, P;       // padded sizes, live designs, pairs, split-K slabs
+    int ldk;
+    const double *K, *KT;                       // K [Mp x ldk] and its transpose [Np x Mp]
+    const double *c, *lo, *hi, *bl, *bu, *rho;  // [dim x Bp]
+    const int *pair_i, *pair_j;                 // [npairs]
+    const int *pair_of;                         // [Np]: pair index of a coordinate or -1
+    const double *obj_upper;                    // [Bp] or null
+    double *z, *zbar, *zs, *z0, *zbest;         // [Np x Bp]
+    double *y, *ys, *y0, *ybest;                // [Mp x Bp]
+    double *S;                                  // [Mp x Bp]   K*zbar, K*z, K*zs
+    double *G;                                  // [P x Np x Bp] split-K slabs of K^T y
+    double *G2;                                 // [Np x Bp] reduced K^T (.) for metrics
+    double *acc;                                // [2 cand][NACC][Bp] reduction targets
+    Ctl *ctl;
+    int *active;                                // number of designs still running
+    double eta, eps_pr, eps_dr, eps_gap;
+    int check_every;
+};
+
+enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, NACC };
+
+__device__ __forceinline__ void atomic_max_pos(double *addr, double v)
+{
+    if (!(v > 0.0)) return;
+    atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// z+ = P_X(z - tau (c + sum_p G_p)), zbar = 2 z+ - z, zs += z+.   One thread per (coordinate, design);
+// the thread of pair member i handles both members (j is skipped).
+__global__ void z_update_kernel(Problem p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = (int)(idx % p.Bp);
+    const int j = (int)(idx / p.Bp);
+    if (j >= p.Np) return;
+    const int pr = p.pair_of[j];
+    if (pr >= 0 && p.pair_j[pr] == j) return;  // second member: done by the first
+    const double tau = p.ctl[b].tau;
+    const size_t stride = (size_t)p.Np * p.Bp;
+    auto grad = [&](int jj) {
+        double g = p.c[(size_t)jj * p.Bp + b];
+        for (int s = 0; s < p.P; ++s) g += p.G[s * stride + (size_t)jj * p.Bp + b];
+        return g;
+    };
+    const size_t o = (size_t)j * p.Bp + b;
+    if (pr < 0) {
+        const double zo = p.z[o];
+        double zn = zo - tau * grad(j);
+        zn = fmin(fmax(zn, p.bl[o]), p.bu[o]);
+        p.z[o] = zn;
+        p.zbar[o] = 2.0 * zn - zo;
+        p.zs[o] += zn;
+    } else {
+        const int j2 = p.pair_j[pr];
+        const size_t o2 = (size_t)j2 * p.Bp + b;
+        const double z1 = p.z[o], z2 = p.z[o2];
+        double a = z1 - tau * grad(j), c2 = z2 - tau * grad(j2);
+        const double r = hypot(a, c2), rho = p.rho[(size_t)pr * p.Bp + b];
+        if (r > rho) {
+            const double s = rho / r;
+            a *= s;
+            c2 *= s;
+        }
+        p.z[o] = a; p.z[o2] = c2;
+        p.zbar[o] = 2.0 * a - z1; p.zbar[o2] = 2.0 * c2 - z2;
+        p.zs[o] += a; p.zs[o2] += c2;
+    }
+}
+
+// v = y + sigma S;  y+ = v - sigma clip(v/sigma, lo, hi);  ys += y+
+__global__ void y_update_kernel(Problem p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.Mp * p.Bp) return;
+    const int b = (int)(idx % p.Bp);
+    const double sig = p.ctl[b].sigma;
+    const double v = p.y[idx] + sig * p.S[idx];
+    const double w = v / sig, lo = p.lo[idx], hi = p.hi[idx];
+    // exact zero inside the interval: v - sig*(v/sig) would leave rounding dust that h*(y) multiplies by +-inf
+    const double yn = w > hi ? v - sig * hi : (w < lo ? v - sig * lo : 0.0);
+    p.y[idx] = yn;
+    p.ys[idx] += yn;
+}
+
+// reduce split-K slabs: G2 = sum_p G_p
+__global__ void reduce_slabs_kernel(Problem p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)p.Np * p.Bp;
+    if (idx >= n) return;
+    double g = 0.0;
+    for (int s = 0; s < p.P; ++s) g += p.G[(size_t)s * n + idx];
+    p.G2[idx] = g;
+}
+
+// Row-side metrics of a candidate (cand 0: running average = sums/cnt, cand 1: current iterate):
+//   pr = max violation of K z, hs = h*(y), dy2 = ||y - y0||^2.   S holds K*(zs or z).
+__global__ void row_metrics_kernel(Problem p, int cand)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per design, rows strided over blockIdx.y
+    if (b >= p.Bp) return;
+    const double inv = cand == 0 ? 1.0 / fmax(p.ctl[b].cnt, 1.0) : 1.0;
+    const double *yv = cand == 0 ? p.ys : p.y;
+    double pr = 0.0, hs = 0.0, dy2 = 0.0;
+    for (int i = blockIdx.y; i < p.Mp; i += gridDim.y) {
+        const size_t o = (size_t)i * p.Bp + b;
+        const double kz = p.S[o] * inv, y = yv[o] * inv, lo = p.lo[o], hi = p.hi[o];
+        pr = fmax(pr, fmax(kz - hi, lo - kz));
+        if (y > 0.0) hs += hi * y;
+        else if (y < 0.0) hs += lo * y;
+        const double d = y - p.y0[o];
+        dy2 = fma(d, d, dy2);
+    }
+    double *acc = p.acc + (size_t)cand * NACC * p.Bp;
+    atomic_max_pos(acc + A_PR * p.Bp + b, pr);
+    atomicAdd(acc + A_HS * p.Bp + b, hs);
+    atomicAdd(acc + A_DY2 * p.Bp + b, dy2);
+}
+
+// Column-side metrics: pobj = c^T z, gz = g^T z, dr = ||z - P_X(z - g)||_inf, dz2 = ||z - z0||^2,
+// rigx = min_{x in X} g^T x (for the rigorous dual bound).  G2 holds K^T (ys or y).
+__global__ void col_metrics_kernel(Problem p, int cand)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.Bp) return;
+    const double inv = cand == 0 ? 1.0 / fmax(p.ctl[b].cnt, 1.0) : 1.0;
+    const double *zv = cand == 0 ? p.zs : p.z;
+    double pobj = 0.0, gz = 0.0, dr = 0.0, dz2 = 0.0, rigx = 0.0;
+    for (int j = blockIdx.y; j < p.Np; j += gridDim.y) {
+        const int pr = p.pair_of[j];
+        if (pr >= 0 && p.pair_j[pr] == j) continue;
+        const size_t o = (size_t)j * p.Bp + b;
+        const double z = zv[o] * inv, c = p.c[o], g = c + p.G2[o] * inv;
+        if (pr < 0) {
+            const double bl = p.bl[o], bu = p.bu[o];
+            const double t = fmin(fmax(z - g, bl), bu);
+            dr = fmax(dr, fabs(z - t));
+            pobj = fma(c, z, pobj);
+            gz = fma(g, z, gz);
+            const double d = z - p.z0[o];
+            dz2 = fma(d, d, dz2);
+            rigx += g > 0.0 ? g * bl : (g < 0.0 ? g * bu : 0.0);
+        } else {
+            const size_t o2 = (size_t)p.pair_j[pr] * p.Bp + b;
+            const double z2 = zv[o2] * inv, c2 = p.c[o2], g2 = c2 + p.G2[o2] * inv;
+            double a = z - g, e = z2 - g2;
+            const double r = hypot(a, e), rho = p.rho[(size_t)pr * p.Bp + b];
+            if (r > rho) { const double s = rho / r; a *= s; e *= s; }
+            dr = fmax(dr, fmax(fabs(z - a), fabs(z2 - e)));
+            pobj = fma(c, z, fma(c2, z2, pobj));
+            gz = fma(g, z, fma(g2, z2, gz));
+            const double d1 = z - p.z0[o], d2 = z2 - p.z0[o2];
+            dz2 = fma(d1, d1, fma(d2, d2, dz2));
+            rigx -= rho * hypot(g, g2);
+        }
+    }
+    double *acc = p.acc + (size_t)cand * NACC * p.Bp;
+    atomic_max_pos(acc + A_DR * p.Bp + b, dr);
+    atomicAdd(acc + A_POBJ * p.Bp + b, pobj);
+    atomicAdd(acc + A_GZ * p.Bp + b, gz);
+    atomicAdd(acc + A_DZ2 * p.Bp + b, dz2);
+    atomicAdd(acc + A_RIGX * p.Bp + b, rigx);
+}
+
+// Advance the per-design counters by one block of iterations (before the metrics use cnt).
+__global__ void advance_kernel(Problem p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.Bp) return;
+    p.ctl[b].since += p.check_every;
+    p.ctl[b].cnt += p.check_every;
+}
+
+// One thread per design: score both candidates, decide convergence / infeasibility / restart.
+__global__ void control_kernel(Problem p, int iter_now, int max_iter)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.Bp) return;
+    Ctl &c = p.ctl[b];
+    c.restart = 0.0;
+    if (b >= p.B) { c.status = 1.0; return; }     // padding designs
+    double err[2], pr[2], dr[2], po[2], du[2], rig[2], dz[2], dy[2];
+    for (int k = 0; k < 2; ++k) {
+        const double *a = p.acc + (size_t)k * NACC * p.Bp;
+        pr[k] = a[A_PR * p.Bp + b];
+        dr[k] = a[A_DR * p.Bp + b];
+        po[k] = a[A_POBJ * p.Bp + b];
+        du[k] = -a[A_HS * p.Bp + b] + a[A_GZ * p.Bp + b];
+        rig[k] = -a[A_HS * p.Bp + b] + a[A_RIGX * p.Bp + b];
+        dz[k] = sqrt(a[A_DZ2 * p.Bp + b]);
+        dy[k] = sqrt(a[A_DY2 * p.Bp + b]);
+        err[k] = fmax(fmax(pr[k], dr[k]), fabs(po[k] - du[k]));
+        if (!(err[k] == err[k])) err[k] = DBL_MAX;   // NaN never wins
+    }
+    const int k = err[0] < err[1] ? 0 : 1;
+    c.use_avg = k == 0 ? 1.0 : 0.0;
+    if (c.status == 0.0) {
+        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = fmax(rig[0], rig[1]);
+        const bool solved = pr[k] <= p.eps_pr && dr[k] <= p.eps_dr &&
+                            fabs(po[k] - du[k]) <= p.eps_gap * fmax(fabs(po[k]), 1e-12);
+        const bool infeasible = !solved && p.obj_upper && c.rigorous > p.obj_upper[b];
+        if (solved) { c.status = 1.0; c.iters = iter_now; }
+        else if (infeasible) { c.status = 2.0; c.iters = iter_now; }
+        else if (iter_now >= max_iter) { c.status = 3.0; c.iters = iter_now; }
+        if (c.status != 0.0) atomicSub(p.active, 1);
+        c.restart = 1.0;   // also snapshot the candidate into zbest / ybest (see apply kernel)
+    }
+    if (c.status != 0.0 && c.restart == 0.0) return;
+    // restart rules (PDLP): sufficient decay, necessary decay + no progress, or long since last restart
+    const double e = err[k];
+    const bool doit = e <= 0.2 * c.last_err || (e <= 0.8 * c.last_err && e > c.prev_err) ||
+                      c.since >= 0.36 * (double)iter_now;
+    c.prev_err = e;
+    if (doit && c.status == 0.0) {
+        if (dz[k] > 1e-12 && dy[k] > 1e-12) c.omega = exp(0.5 * log(dy[k] / dz[k]) + 0.5 * log(c.omega));
+        c.tau = p.eta / c.omega;
+        c.sigma = p.eta * c.omega;
+        c.last_err = e;
+        c.since = 0.0;
+        c.restart = 2.0;   // 2: real restart (iterate, anchor and sums are reset)
+    }
+}
+
+// restart == 1: snapshot candidate into best.  restart == 2: additionally z,y <- candidate, anchors, sums = 0.
+__global__ void apply_kernel(Problem p, int side)   // side 0: z arrays, 1: y arrays
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)(side == 0 ? p.Np : p.Mp) * p.Bp;
+    if (idx >= n) return;
+    const int b = (int)(idx % p.Bp);
+    const Ctl &c = p.ctl[b];
+    if (c.restart == 0.0) return;
+    double *cur = side == 0 ? p.z : p.y, *sum = side == 0 ? p.zs : p.ys;
+    double *anchor = side == 0 ? p.z0 : p.y0, *best = side == 0 ? p.zbest : p.ybest;
+    // cnt was already advanced in the control kernel; on a real restart it is reset by reset_cnt_kernel
+    const double cand = c.use_avg != 0.0 ? sum[idx] / fmax(c.cnt, 1.0) : cur[idx];
+    best[idx] = cand;
+    if (c.restart == 2.0) {
+        cur[idx] = cand;
+        anchor[idx] = cand;
+        sum[idx] = 0.0;
+    }
+}
+
+__global__ void reset_cnt_kernel(Problem p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.Bp) return;
+    if (p.ctl[b].restart == 2.0) p.ctl[b].cnt = 0.0;
+}
+
+// power iteration helpers for ||K||_2
+__global__ void scale_first_col_kernel(double *v, int n, int Bp, const double *nrm2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    v[(size_t)j * Bp] = v[(size_t)j * Bp] / sqrt(nrm2[0]);
+}
+__global__ void norm2_first_col_kernel(const double *v, int n, int Bp, double *out)
+{
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) { const double x = v[(size_t)j * Bp]; s = fma(x, x, s); }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+static inline int up(int v, int a) { return (v + a - 1) / a * a; }
+
+static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st)   // C[Mp x Bp] = K X
+{
+    dim3 grid(p.Bp / BN, p.Mp / BM, 1);
+    dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
+    MBRF_LAUNCH_CHECK();
+    return MBRF_OK;
+}
+static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st)   // G[P][Np x Bp] = K^T Y
+{
+    const int kchunk = up((p.Mp + p.P - 1) / p.P, BK);
+    dim3 grid(p.Bp / BN, p.Np / BM, p.P);
+    dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.K, p.ldk, Y, p.Bp, G, p.Mp, kchunk, (long long)p.Np * p.Bp);
+    MBRF_LAUNCH_CHECK();
+    return MBRF_OK;
+}
+
+}  // namespace pdhg
+}  // namespace mbrf
+
+using namespace mbrf;
+using namespace mbrf::pdhg;
+
+extern "C" {
+
+// sizes of the padded problem and of the workspace (bytes) for given live sizes
+int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp)
+{
+    if (M <= 0 || N <= 0 || B <= 0 || !Mp || !Np || !Bp) return MBRF_EINVAL;
+    *Mp = up(M, 64);
+    *Np = up(N, 64);
+    *Bp = up(B, 64);
+    return MBRF_OK;
+}
+
+static int split_k(int Mp, int Np, int Bp)
+{
+    // K^T Y has only (Np/64)*(Bp/64) output tiles: split the long reduction so that ~6 CTAs land on each SM
+    const int tiles = (Np / BM) * (Bp / BN);
+    int P = (6 * 148 + tiles - 1) / tiles;
+    if (P < 1) P = 1;
+    if (P > Mp / 64) P = Mp / 64;
+    if (P > 32) P = 32;
+    return P;
+}
+
+unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp)
+{
+    const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
+    const int P = split_k(Mp, Np, Bp);
+    size_t d = 5 * zn + 4 * yn + yn + (size_t)P * zn + zn + 2 * NACC * (size_t)Bp;
+    return d * 8 + (size_t)Bp * sizeof(Ctl) + 256 + (size_t)Np * 4 + 64;
+}
+
+/*
+ * Solve a padded batch on the device.  All pointers are device pointers; per-design arrays are
+ * [dim x Bp] with the design index fastest.  info_out: [Bp x 8] doubles
+ * (status, iters, obj, dual, pr, dr, rigorous lower bound, omega).
+ */
+int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, const double *c, const double *lo,
+                           const double *hi, const double *bl, const double *bu, const int *pair_i,
+                           const int *pair_j, int npairs, const double *rho, int Bp, int B,
+                           const double *obj_upper, int max_iter, int check_every, double eps_pr,
+                           double eps_dr, double eps_gap, double *z_out, double *y_out, double *info_out,
+                           void *workspace, void *stream)
+{
+    if (int rc = require_device()) return rc;
+    if (Mp % 64 || Np % 64 || Bp % 64 || B < 1 || B > Bp || ldk < Np || ldk % 2 ||
+        max_iter < 1 || check_every < 1 || npairs < 0) {
+        set_error("pdhg: bad padded sizes Mp=%d Np=%d Bp=%d B=%d ldk=%d", Mp, Np, Bp, B, ldk);
+        return MBRF_EINVAL;
+    }
+    if (!K || !KT || !c || !lo || !hi || !bl || !bu || !z_out || !info_out || !workspace || (npairs && (!pair_i || !pair_j || !rho))) {
+        set_error("pdhg: NULL required pointer");
+        return MBRF_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Problem p;
+    p.Mp = Mp; p.Np = Np; p.Bp = Bp; p.B = B; p.npairs = npairs; p.ldk = ldk; p.K = K; p.KT = KT;
+    p.c = c; p.lo = lo; p.hi = hi; p.bl = bl; p.bu = bu; p.rho = rho; p.pair_i = pair_i; p.pair_j = pair_j;
+    p.obj_upper = obj_upper; p.P = split_k(Mp, Np, Bp);
+    p.eps_pr = eps_pr; p.eps_dr = eps_dr; p.eps_gap = eps_gap; p.check_every = check_every;
+    const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
+    double *w = (double *)workspace;
+    p.z = w; w += zn; p.zbar = w; w += zn; p.zs = w; w += zn; p.z0 = w; w += zn; p.zbest = w; w += zn;
+    p.y = w; w += yn; p.ys = w; w += yn; p.y0 = w; w += yn; p.ybest = w; w += yn;
+    p.S = w; w += yn;
+    p.G = w; w += (size_t)p.P * zn;
+    p.G2 = w; w += zn;
+    p.acc = w; w += 2 * NACC * (size_t)Bp;
+    p.ctl = (Ctl *)w; w = (double *)((char *)w + (size_t)Bp * sizeof(Ctl));
+    p.active = (int *)w; w += 32;
+    int *pair_of = (int *)w;
+    p.pair_of = pair_of;
+
+    // ---- init state ----
+    MBRF_CUDA(cudaMemsetAsync(workspace, 0, (char *)pair_of - (char *)workspace, st));
+    {
+        std::vector<int> po((size_t)Np, -1), pi((size_t)npairs), pj((size_t)npairs);
+        if (npairs) {
+            MBRF_CUDA(cudaMemcpyAsync(pi.data(), pair_i, npairs * sizeof(int), cudaMemcpyDeviceToHost, st));
+            MBRF_CUDA(cudaMemcpyAsync(pj.data(), pair_j, npairs * sizeof(int), cudaMemcpyDeviceToHost, st));
+            MBRF_CUDA(cudaStreamSynchronize(st));
+            for (int q = 0; q < npairs; ++q) {
+                if (pi[q] < 0 || pi[q] >= Np || pj[q] < 0 || pj[q] >= Np || pi[q] == pj[q]) { set_error("pdhg: bad pair %d", q); return MBRF_EINVAL; }
+                po[pi[q]] = q; po[pj[q]] = q;
+            }
+        }
+        MBRF_CUDA(cudaMemcpyAsync(pair_of, po.data(), (size_t)Np * sizeof(int), cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+    }
+    // ---- ||K||_2 by power iteration on design column 0 of scratch vectors (zbar / S are free now) ----
+    double knorm2 = 1.0;
+    {
+        std::vector<double> h((size_t)Np);
+        unsigned s = 12345u;
+        for (int j = 0; j < Np; ++j) { s = s * 1664525u + 1013904223u; h[j] = ((s >> 8) & 0xffff) / 65536.0 - 0.5; }
+        MBRF_CUDA(cudaMemcpy2DAsync(p.zbar, (size_t)Bp * 8, h.data(), 8, 8, Np, cudaMemcpyHostToDevice, st));
+        double *nrm = p.acc;  // scratch scalar
+        Problem q = p;
+        q.P = 1;
+        for (int itp = 0; itp < 40; ++itp) {
+            norm2_first_col_kernel<<<1, 256, 0, st>>>(p.zbar, Np, Bp, nrm);
+            MBRF_LAUNCH_CHECK();
+            scale_first_col_kernel<<<(Np + 255) / 256, 256, 0, st>>>(p.zbar, Np, Bp, nrm);
+            MBRF_LAUNCH_CHECK();
+            if (int rc = gemm_nn(q, p.zbar, p.S, st)) return rc;
+            if (int rc = gemm_tn(q, p.S, p.G, st)) return rc;     // P = 1: G slab 0 = K^T K v
+            MBRF_CUDA(cudaMemcpyAsync(p.zbar, p.G, zn * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        norm2_first_col_kernel<<<1, 256, 0, st>>>(p.zbar, Np, Bp, nrm);
+        MBRF_LAUNCH_CHECK();
+        double hn = 0.0;
+        MBRF_CUDA(cudaMemcpyAsync(&hn, nrm, 8, cudaMemcpyDeviceToHost, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+        knorm2 = sqrt(hn);       // ||K^T K v|| with ||v|| = 1  ->  largest eigenvalue of K^T K
+        if (!(knorm2 > 0.0) || !std::isfinite(knorm2)) { set_error("pdhg: ||K|| estimate failed (%g)", knorm2); return MBRF_EINVAL; }
+        MBRF_CUDA(cudaMemsetAsync(p.zbar, 0, zn * 8, st));
+        MBRF_CUDA(cudaMemsetAsync(p.S, 0, yn * 8, st));
+        MBRF_CUDA(cudaMemsetAsync(p.G, 0, (size_t)p.P * zn * 8, st));
+        MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)Bp * 8, st));
+    }
+    p.eta = 0.9 / sqrt(knorm2);
+    {
+        std::vector<Ctl> hc((size_t)Bp);
+        for (int b = 0; b < Bp; ++b) {
+            Ctl &c0 = hc[b];
+            memset(&c0, 0, sizeof(Ctl));
+            c0.omega = 1.0; c0.tau = p.eta; c0.sigma = p.eta;
+            c0.last_err = DBL_MAX; c0.prev_err = DBL_MAX;
+            c0.status = b < B ? 0.0 : 1.0;
+        }
+        MBRF_CUDA(cudaMemcpyAsync(p.ctl, hc.data(), (size_t)Bp * sizeof(Ctl), cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaMemcpyAsync(p.active, &B, sizeof(int), cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+    }
+    // z starts at P_X(0): one z-update with tau = 0 equivalent -> run it with G = 0, c contributes tau*c; instead
+    // project zero directly: boxes containing 0 and disks are satisfied by 0 except boxes with bl > 0 or bu < 0.
+    // (handled by the first iteration's projection; z = 0 is only a starting point.)
+
+    const int TPB = 256;
+    const unsigned gz = (unsigned)((zn + TPB - 1) / TPB), gy = (unsigned)((yn + TPB - 1) / TPB);
+    const dim3 gm((Bp + 63) / 64, 64);
+
+    auto iteration = [&]() -> int {
+        if (int rc = gemm_tn(p, p.y, p.G, st)) return rc;
+        z_update_kernel<<<gz, TPB, 0, st>>>(p);
+        MBRF_LAUNCH_CHECK();
+        if (int rc = gemm_nn(p, p.zbar, p.S, st)) return rc;
+        y_update_kernel<<<gy, TPB, 0, st>>>(p);
+        MBRF_LAUNCH_CHECK();
+        return MBRF_OK;
+    };
+    auto check = [&](int iter_now) -> int {
+        MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)Bp * 8, st));
+        advance_kernel<<<(Bp + 63) / 64, 64, 0, st>>>(p);
+        MBRF_LAUNCH_CHECK();
+        for (int cand = 0; cand < 2; ++cand) {
+            if (int rc = gemm_nn(p, cand == 0 ? p.zs : p.z, p.S, st)) return rc;
+            row_metrics_kernel<<<gm, 64, 0, st>>>(p, cand);
+            MBRF_LAUNCH_CHECK();
+            if (int rc = gemm_tn(p, cand == 0 ? p.ys : p.y, p.G, st)) return rc;
+            reduce_slabs_kernel<<<gz, TPB, 0, st>>>(p);
+            MBRF_LAUNCH_CHECK();
+            col_metrics_kernel<<<gm, 64, 0, st>>>(p, cand);
+            MBRF_LAUNCH_CHECK();
+        }
+        control_kernel<<<(Bp + 63) / 64, 64, 0, st>>>(p, iter_now, max_iter);
+        MBRF_LAUNCH_CHECK();
+        apply_kernel<<<gz, TPB, 0, st>>>(p, 0);
+        MBRF_LAUNCH_CHECK();
+        apply_kernel<<<gy, TPB, 0, st>>>(p, 1);
+        MBRF_LAUNCH_CHECK();
+        reset_cnt_kernel<<<(Bp + 63) / 64, 64, 0, st>>>(p);
+        MBRF_LAUNCH_CHECK();
+        return MBRF_OK;
+    };
+
+    // Capture one block of `check_every` iterations as a CUDA graph: the inner loop is launch-bound for
+    // small batches (4 kernels of a few microseconds each per iteration).
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool use_graph = true;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        int rc = MBRF_OK;
+        for (int i = 0; i < check_every && rc == MBRF_OK; ++i) rc = iteration();
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc != MBRF_OK || e != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) use_graph = false;
+    } else {
+        use_graph = false;
+    }
+    if (!use_graph) cudaGetLastError();
+
+    int active = B, rcode = MBRF_OK;
+    for (int it = 0; it < max_iter && active > 0 && rcode == MBRF_OK;) {
+        if (use_graph) {
+            if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("pdhg: graph launch failed"); rcode = MBRF_ECUDA; break; }
+            g_launches.fetch_add(4ull * check_every, std::memory_order_relaxed);
+        } else {
+            for (int i = 0; i < check_every && rcode == MBRF_OK; ++i) rcode = iteration();
+        }
+        it += check_every;
+        if (rcode == MBRF_OK) rcode = check(it);
+        if (rcode != MBRF_OK) break;
+        if (cudaMemcpyAsync(&active, p.active, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { set_error("pdhg: status readback failed: %s", cudaGetErrorString(cudaGetLastError())); rcode = MBRF_ECUDA; }
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (rcode != MBRF_OK) return rcode;
+
+    MBRF_CUDA(cudaMemcpyAsync(z_out, p.zbest, zn * 8, cudaMemcpyDeviceToDevice, st));
+    if (y_out) MBRF_CUDA(cudaMemcpyAsync(y_out, p.ybest, yn * 8, cudaMemcpyDeviceToDevice, st));
+    {
+        std::vector<Ctl> hc((size_t)Bp);
+        MBRF_CUDA(cudaMemcpyAsync(hc.data(), p.ctl, (size_t)Bp * sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+        std::vector<double> info((size_t)Bp * 8);
+        for (int b = 0; b < Bp; ++b) {
+            const Ctl &c0 = hc[b];
+            double *o = &info[(size_t)b * 8];
+            o[0] = c0.status == 0.0 ? 3.0 : c0.status; o[1] = c0.iters; o[2] = c0.obj; o[3] = c0.dual;
+            o[4] = c0.pr; o[5] = c0.dr; o[6] = c0.rigorous; o[7] = c0.omega;
+        }
+        MBRF_CUDA(cudaMemcpyAsync(info_out, info.data(), info.size() * 8, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+    }
+    return MBRF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,459 @@
+"""Host-side mirror of the reference's convex FIR design step.
+
+    [h, status] = fir_ap_cvx(n, f, a, d, obj, Peak, dbg)            fir_ap_cvx.m
+    [h, status, n_op, f_op] = fir_ap(n, f, a, d, Peak, min_order, min_tran, min_peak, dbg)   fir_ap.m
+    [h, status] = fir_linprog(n, f, a, d, h0, dbg)                  ss/fir_linprog.m
+    [h, status] = fir_min_order_linprog(n, f, a, d, even_odd, dbg)  ss/fir_min_order_linprog.m
+    [h, status] = fir_min_order(n, f, a, d, even_odd, a_min, dbg)   ss/fir_min_order.m (LP feasibility form)
+
+Same names, positional arguments, defaults and status strings ('Solved' / 'Failed', h = [] on failure).
+The reference hands the problem to CVX (SeDuMi/SDPT3) or MATLAB linprog; here the identical problem is
+assembled on the host exactly as the .m file does (grid, band masks, bounds — O(m) scalar work) and
+solved on the GPU by libmbrf's batched restarted PDHG (`mbrf_fir_pdhg_solve`): the Fourier matrix is
+generated on the device, several designs that share n are solved as one batch.  No CPU solve exists.
+
+`fir_ap_cvx_batch` is the batched entry the sweeps use (fir_ap.m's bisections, trade-off sweeps).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import c_double_p, check, lib
+
+c_int_p = C.POINTER(C.c_int)
+
+# solver defaults: tolerances of BASELINE.json's north star with a safety margin
+EPS_PR = 5e-7      # max constraint violation (absolute, in |H|^2 units)      (<= 1e-6 required)
+EPS_DR = 2e-6      # natural residual in column-scaled units
+EPS_GAP = 5e-5     # |primal - dual| / |primal|                              (<= 1e-4 required)
+MAX_ITER = 200000
+CHECK_EVERY = 64
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+# --------------------------------------------------------------------------------------------
+# problem assembly — fir_ap_cvx.m:44-142
+# --------------------------------------------------------------------------------------------
+def _bands(w, f, a, d):
+    """fir_ap_cvx.m:51-82: band membership, linearly interpolated amplitude +- ripple, transition rows."""
+    nband = len(f) // 2
+    idx_band, U, L = [], [], []
+    for b in range(nband):
+        lo, hi = f[2 * b], f[2 * b + 1]
+        idx = np.nonzero((w >= lo) & (w <= hi))[0]                       # :54
+        idx_band.append(idx)
+        if lo == hi:
+            amp = np.full(idx.size, a[2 * b])                             # :57-58
+        else:
+            amp = a[2 * b] + (a[2 * b + 1] - a[2 * b]) * ((w[idx] - lo) / (hi - lo))   # :60
+        U.append(amp + d[b])
+        L.append(amp - d[b])
+    idx_band = np.concatenate(idx_band) if idx_band else np.zeros(0, int)
+    U = np.concatenate(U) if U else np.zeros(0)
+    L = np.concatenate(L) if L else np.zeros(0)
+    mask = np.ones(w.size, bool)
+    mask[idx_band] = False
+    return idx_band, np.nonzero(mask)[0], U, L
+
+
+def assemble_fir_ap(n, f, a, d, obj, peak, oversamp=15):
+    """One design -> (w rows, lo, hi, stop mask, objective weight, radii) in the reference's row order."""
+    f = np.asarray(f, float).ravel() * np.pi                              # :44
+    a = np.asarray(a, float).ravel()
+    d = np.asarray(d, float).ravel()
+    m = 2 * n * oversamp                                                  # :45-46
+    base = np.linspace(-np.pi, np.pi, m)
+    w = np.sort(np.concatenate([base, f]))                                # :47-48
+    idx_band, idx_tran, U, L = _bands(w, f, a, d)
+    if idx_tran.size:                                                     # :67-75
+        U_tran = np.full(idx_tran.size, U.max())
+        L_tran = np.full(idx_tran.size, min(0.0, L.min()))
+    else:
+        U_tran = L_tran = np.zeros(0)
+    w = np.concatenate([w[idx_band], w[idx_tran]])                        # :86-91
+    U_b = np.concatenate([U, U_tran]) ** 2                                # :103-106
+    L_b = np.concatenate([L, L_tran])
+    L_b[L_b < 0] = 0                                                      # :110-112
+    L_b = L_b ** 2
+    L_b[L_b < 1e-20] = 1e-20                                              # :115-116 (epsilon^2)
+    stop = np.sqrt(U_b) < np.sqrt(U_b).min() + 1e-2                       # :125
+    radius = (n - np.arange(1, n + 1) + 1) * float(peak)                  # :166-168
+    return dict(n=n, w=w, lo=L_b, hi=U_b, stop=stop, obj=float(obj), radius=radius)
+
+
+def _solve_batch_ap(n, designs, max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR,
+                    eps_gap=EPS_GAP):
+    """Solve designs (assemble_fir_ap dicts with one n) as ONE batch sharing one matrix.
+
+    Rows of the shared matrix = union over the batch of the designs' grid points (the base grid is common,
+    band-edge samples differ), followed by one duplicate of every row that is a stop-band row of at least
+    one design (the `A_U(idx_stop,:)*x <= ripple_stop` block, fir_ap_cvx.m:165).  A row a design does not
+    own gets the bounds (-inf, +inf) for that design.
+    Returns x [B, 2n-1], ripple_stop [B], info [B, 8].
+    """
+    B = len(designs)
+    allw = np.unique(np.concatenate([p["w"] for p in designs]))
+    M1 = allw.size
+    pos = [np.searchsorted(allw, p["w"]) for p in designs]
+    stop_any = np.zeros(M1, bool)
+    for p, ix in zip(designs, pos):
+        stop_any[ix[p["stop"]]] = True
+    srows = np.nonzero(stop_any)[0]
+    srank = -np.ones(M1, int)
+    srank[srows] = np.arange(srows.size)
+    M = M1 + srows.size
+    nx = 2 * n - 1
+    N = nx + 1
+    w_row = np.concatenate([allw, allw[srows]])
+    tcoef = np.concatenate([np.zeros(M1), -np.ones(srows.size)])
+    lo = np.full((M, B), -np.inf)
+    hi = np.full((M, B), np.inf)
+    c = np.zeros((N, B))
+    bl = np.full((N, B), -np.inf)
+    bu = np.full((N, B), np.inf)
+    rho = np.zeros((n - 1, B))
+    upper = np.zeros(B)
+    for b, (p, ix) in enumerate(zip(designs, pos)):
+        # a grid point may occur twice in a design (band edge coinciding with a base sample): keep the tighter
+        np.maximum.at(lo[:, b], ix, p["lo"])
+        np.minimum.at(hi[:, b], ix, p["hi"])
+        st = M1 + srank[ix[p["stop"]]]
+        hi[st, b] = 0.0                                                   # A(stop) x - t <= 0
+        c[0, b] = 1.0                                                     # minimise x(1) + obj*ripple_stop, :163
+        c[nx, b] = p["obj"]
+        bl[0, b], bu[0, b] = -p["radius"][0], p["radius"][0]              # |x1| <= n Peak, :167 (i = 1)
+        tmax = p["hi"][p["stop"]].max()
+        bl[nx, b], bu[nx, b] = 0.0, tmax     # implied: t >= S >= L_b > 0 and t = max S <= max U_b(stop) at the optimum
+        rho[:, b] = p["radius"][1:]
+        upper[b] = p["radius"][0] + p["obj"] * tmax                       # no feasible point has a larger objective
+    col_type = np.concatenate([[0], np.full(n - 1, 1), np.full(n - 1, 2), [3]]).astype(np.int32)
+    k = np.arange(1, n, dtype=float)
+    col_kappa = np.concatenate([[0.0], k, k, [0.0]])
+    col_amp = np.concatenate([[1.0], np.full(2 * n - 2, 2.0), [0.0]])    # A = [1, 2cos, 2sin], :100
+    pair_i = np.arange(1, n, dtype=np.int32)                              # (x_i, x_{n+i-1}), :133-139
+    pair_j = np.arange(n, 2 * n - 1, dtype=np.int32)
+    z = np.zeros((N, B))
+    info = np.zeros((B, 8))
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (w_row, tcoef, col_kappa, col_amp, c, lo, hi, bl, bu,
+                                                                  rho, upper)]
+    w_row, tcoef, col_kappa, col_amp, c, lo, hi, bl, bu, rho, upper = arrs
+    check(lib().mbrf_fir_pdhg_solve(_dp(w_row), _dp(tcoef), M, _ip(col_type), _dp(col_kappa), _dp(col_amp), N, nx,
+                                    _ip(pair_i), _ip(pair_j), n - 1, _dp(c), _dp(lo), _dp(hi), _dp(bl), _dp(bu),
+                                    _dp(rho), B, _dp(upper), int(max_iter), int(check_every), float(eps_pr),
+                                    float(eps_dr), float(eps_gap), _dp(z), _dp(info), None))
+    return z[:nx].T.copy(), z[nx].copy(), info
+
+
+# --------------------------------------------------------------------------------------------
+# spectral factorisation — fir_ap_cvx.m:185-202, 254-304 (host; SURVEY.md 8(f) "next #1")
+# --------------------------------------------------------------------------------------------
+def _mag2mp(x):
+    nn = x.size                                                           # fir_ap_cvx.m:293-303
+    xlf = np.fft.fft(np.log(x))
+    xlfp = np.zeros(nn, complex)
+    xlfp[0] = xlf[0]
+    xlfp[1:nn // 2] = 2 * xlf[1:nn // 2]
+    xlfp[nn // 2] = xlf[nn // 2]
+    return np.exp(np.fft.ifft(xlfp))
+
+
+def fmp2(r):
+    """Minimum-phase spectral factor of the autocorrelation r (length 2n-1) — fir_ap_cvx.m:262-283."""
+    h = np.asarray(r, complex).ravel()
+    ln = h.size
+    lp = int(round(8 * np.exp(np.ceil(np.log(ln) / np.log(2)) * np.log(2))))
+    hp = np.concatenate([np.zeros(int(np.ceil((lp - ln) / 2))), h, np.zeros(int(np.floor((lp - ln) / 2)))])
+    hpf = np.fft.fftshift(np.fft.fft(np.fft.fftshift(hp)))                # fftc, :253-255
+    hpfmp = _mag2mp(np.sqrt(np.abs(hpf)))
+    hpmp = np.fft.ifft(np.fft.fftshift(np.conj(hpfmp)))
+    return hpmp[:(ln + 1) // 2]
+
+
+def _x_to_h(x, n):
+    r = np.concatenate([[x[0]], x[1:n] + 1j * x[n:2 * n - 1]])            # :185
+    r = np.concatenate([np.conj(r[:0:-1]), r])                            # :186
+    return fmp2(r)
+
+
+# --------------------------------------------------------------------------------------------
+# public mirrors
+# --------------------------------------------------------------------------------------------
+def fir_ap_cvx_batch(n, f_list, a, d, obj_list, peak_list, return_info=False, **solver_kw):
+    """Batched fir_ap_cvx: designs i = 0..B-1 with band edges f_list[i], trade-off obj_list[i], Peak peak_list[i]
+    (a, d shared or per-design lists).  Returns (h_list, status_list[, info]); h is None where 'Failed'."""
+    B = len(f_list)
+    a_list = a if isinstance(a, (list, tuple)) and np.ndim(a[0]) else [a] * B
+    d_list = d if isinstance(d, (list, tuple)) and np.ndim(d[0]) else [d] * B
+    designs = [assemble_fir_ap(n, f_list[i], a_list[i], d_list[i], obj_list[i], peak_list[i]) for i in range(B)]
+    x, t, info = _solve_batch_ap(n, designs, **solver_kw)
+    hs, status = [], []
+    for b in range(B):
+        ok = info[b, 0] == 1.0            # 1 solved; 2 infeasible certificate; 3 iteration limit -> 'Failed'
+        status.append("Solved" if ok else "Failed")   # fir_ap_cvx.m:176-182
+        hs.append(_x_to_h(x[b], n) if ok else None)
+    if return_info:
+        return hs, status, dict(x=x, ripple_stop=t, info=info)
+    return hs, status
+
+
+def fir_ap_cvx(n, f, a, d, obj=0, Peak=1e-3, dbg=0, **solver_kw):
+    """[h, status] = fir_ap_cvx(n, f, a, d, obj, Peak, dbg) — fir_ap_cvx.m:1-245."""
+    if obj < 0:
+        raise ValueError("invalid input of obj")                          # :172-174
+    hs, st = fir_ap_cvx_batch(int(n), [f], a, d, [obj], [Peak], **solver_kw)
+    return (hs[0] if hs[0] is not None else np.zeros(0)), st[0]
+
+
+def fir_ap(n, f, a, d, Peak=1e-3, min_order=0, min_tran=0, min_peak=0, dbg=0, **solver_kw):
+    """[h, status, n_op, f_op] = fir_ap(...) — fir_ap.m:1-213: bisection on transition width and/or order.
+
+    Each bisection step of the reference is one serial fir_ap_cvx solve; here every step probes a whole
+    bracket of candidates in ONE batch (k-ary search), which needs fewer rounds and fills the GPU.
+    min_peak (fir_flip_zero) is not part of the accelerated path and raises if requested.
+    """
+    if min_peak:
+        raise NotImplementedError("fir_flip_zero (min_peak) is outside the accelerated path (SURVEY.md 2.3 M9)")
+    f = np.asarray(f, float).ravel()
+    lam, df_thre = 0.1, 0.0005                                            # fir_ap.m:45-46
+    n_op, f_op = int(n), f.copy()
+    h1, status1 = fir_ap_cvx(n, f, a, d, lam, Peak, **solver_kw)          # :51
+    if status1 == "Failed":
+        raise RuntimeError("original parameters are too tight")          # :52-54
+    h, status = h1, status1
+    if min_tran == 0 and min_order == 0:
+        return h, status, n_op, f_op
+
+    def widen(fa):
+        fn = f.copy()
+        fn[0::2] -= fa                                                    # :71-73
+        fn[1::2] += fa
+        return fn
+
+    if min_tran > 0:
+        df_min = (f[2:-1:2] - f[1:-2:2]).min()                            # :60-61
+        bot, top = 0.0, df_min / 2                                        # :62-63
+        # fir_ap.m:78-105 is a binary bisection, one serial solve per step.  The next three steps can only
+        # probe the 7 nodes bot + (top-bot)*j/8 of the bisection tree, whatever the outcomes: solve them as
+        # one batch, then walk the tree exactly as the reference loop would (same probes, same decisions).
+        while True:
+            span = top - bot
+            nodes = {j: bot + span * j / 8 for j in range(1, 8)}
+            hs, sts = fir_ap_cvx_batch(n, [widen(nodes[j]) for j in range(1, 8)], a, d, [lam] * 7, [Peak] * 7,
+                                       **solver_kw)
+            res = {j: (hs[j - 1], sts[j - 1]) for j in range(1, 8)}
+            lo_j, hi_j, done = 0, 8, False
+            for _ in range(3):
+                mid = (lo_j + hi_j) // 2                                  # f_add_mid = (bot+top)/2, :79
+                h0, st0 = res[mid]
+                if st0 == "Failed":
+                    hi_j = mid                                            # :86-88
+                else:
+                    h, status, lo_j = h0, st0, mid                        # :89-93
+                if span * (hi_j - lo_j) / 8 < df_thre:                    # :100-102
+                    done = True
+                    break
+            bot, top = bot + span * lo_j / 8, bot + span * hi_j / 8
+            if done:
+                break
+        if not (0 < min_tran <= 1):
+            raise ValueError("invalid input of min_tran")                 # :131-133
+        fa = bot * min_tran                                               # :110
+        h0, st0 = fir_ap_cvx(n, widen(fa), a, d, lam, Peak, **solver_kw)  # :116
+        if st0 == "Failed":
+            fa = bot                                                      # :117-121
+        else:
+            h, status = h0, st0
+        f = widen(fa)
+        f_op = f.copy()
+    if min_order > 0:
+        n_top, n_bot = int(n), 2                                          # :140-141
+        while n_top - n_bot > 1:                                          # :143-162, one probe per round: orders differ -> no shared matrix
+            n_mid = int(np.ceil((n_top + n_bot) / 2))
+            h0, st0 = fir_ap_cvx(n_mid, f, a, d, lam, Peak, **solver_kw)
+            if st0 == "Failed":
+                n_bot = n_mid
+            else:
+                h, status, n_top = h0, st0, n_mid
+        if min_order == 1:
+            n_op = n_top                                                  # :164-166
+        elif 0 < min_order < 1:
+            n_new = int(np.ceil(n * (1 - min_order) + n_top * min_order)) # :169-173
+            h, status = fir_ap_cvx(n_new, f, a, d, lam, Peak, **solver_kw)
+            n_op = n_new
+        else:
+            raise ValueError("invalid input of min_order")                # :174-176
+    return h, status, n_op, f_op
+
+
+# --------------------------------------------------------------------------------------------
+# ss/fir_linprog.m — linear-phase (real or complex-Hermitian) FIR by LP
+# --------------------------------------------------------------------------------------------
+def assemble_fir_linprog(n, f, a, d):
+    """ss/fir_linprog.m:46-240 -> rows w, bounds, column description, objective.  Returns None for the
+    'n even and amplitude 1 at fs/2' case the reference rejects up front (:63-75)."""
+    f = np.asarray(f, float).ravel() * np.pi                              # :46
+    a = np.asarray(a, float).ravel()
+    d = np.asarray(d, float).ravel()
+    real_filter = not (f.min() < 0)                                       # :48-52
+    odd = (n & 1) == 1                                                    # :56-60
+    if not odd:
+        idx = np.nonzero(np.abs(f) == np.pi)[0]                           # :66-75
+        if np.any(a[idx] == 1):
+            return None
+    nhalf = int(np.ceil(n / 2))                                           # :79
+    oversamp = 15                                                         # :92
+    if real_filter:
+        w = np.linspace(0, np.pi, oversamp * n)                           # :96-98
+    else:
+        w = np.linspace(-np.pi, np.pi, 2 * oversamp * n)                  # :99-101
+    w = np.sort(np.concatenate([w, f]))                                   # :107
+    idx_band, idx_tran, U, L = _bands(w, f, a, d)
+    if idx_tran.size:                                                     # :163-171
+        U_tran = np.full(idx_tran.size, U.max())
+        L_tran = np.full(idx_tran.size, min(0.0, L.min()))
+    else:
+        U_tran = L_tran = np.zeros(0)
+    w = np.concatenate([w[idx_band], w[idx_tran]])                        # :175-180
+    hi = np.concatenate([U, U_tran])                                      # :221-226 (amplitude, not power)
+    lo = np.concatenate([L, L_tran])
+    ntran = idx_tran.size
+    if odd:                                                               # :195-217
+        kc = np.arange(1, nhalf, dtype=float)
+        types = [0] + [1] * (nhalf - 1)
+        kappa = [0.0] + list(kc)
+        amp = [1.0] + [2.0] * (nhalf - 1)
+        if not real_filter:
+            types += [2] * (nhalf - 1)
+            kappa += list(kc)
+            amp += [2.0] * (nhalf - 1)
+    else:
+        kc = np.arange(0, nhalf, dtype=float) + 0.5
+        types = [1] * nhalf
+        kappa = list(kc)
+        amp = [2.0] * nhalf
+        if not real_filter:
+            types += [2] * nhalf
+            kappa += list(kc)
+            amp += [2.0] * nhalf
+    return dict(n=n, nhalf=nhalf, real=real_filter, odd=odd, w=w, lo=lo, hi=hi, nband_rows=idx_band.size, ntran=ntran,
+                col_type=np.array(types, np.int32), col_kappa=np.array(kappa, float), col_amp=np.array(amp, float))
+
+
+def _lp_objective(p):
+    """fmin = sum(A(idx_tran,:), 1)  (fir_linprog.m:231) evaluated from the column description."""
+    wt = p["w"][p["nband_rows"]:]
+    c = np.zeros(p["col_type"].size)
+    for j, (t, k, am) in enumerate(zip(p["col_type"], p["col_kappa"], p["col_amp"])):
+        c[j] = am * (wt.size if t == 0 else (np.cos(wt * k).sum() if t == 1 else np.sin(wt * k).sum()))
+    return c
+
+
+def _fill_h(x, p):
+    """fill_h, fir_linprog.m:274-296."""
+    nh = p["nhalf"]
+    if p["real"]:
+        return np.concatenate([x[:0:-1], x]) if p["odd"] else np.concatenate([x[::-1], x])
+    if p["odd"]:
+        h = x[:nh] + 1j * np.concatenate([[0.0], x[nh:]])
+        return np.concatenate([np.conj(h[:0:-1]), h])
+    h = x[:nh] + 1j * x[nh:]
+    return np.concatenate([np.conj(h[::-1]), h])
+
+
+def fir_linprog(n, f, a, d, h0=None, dbg=0, return_info=False, **solver_kw):
+    """[h, status] = fir_linprog(n, f, a, d, h0, dbg) — ss/fir_linprog.m:2-272.
+
+    The LP `min fmin*x s.t. [A;-A]x <= [U,-L]` (:246-252) is solved on the GPU.  h0 (the reference's warm
+    start for linprog, :157) is accepted and ignored: the first-order solver starts from zero.
+    The redundant box |x_j| <= 2*max|bounds| is added so that the dual bound certifies infeasibility
+    (|H| <= max U on a 15x oversampled grid bounds every Fourier coefficient by it)."""
+    n = int(n)
+    p = assemble_fir_linprog(n, f, a, d)
+    if p is None:
+        return np.zeros(0), "Failed"                                      # :68-72
+    M, N = p["w"].size, p["col_type"].size
+    c = _lp_objective(p)
+    big = 2.0 * max(np.abs(p["hi"]).max(), np.abs(p["lo"]).max())
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.float64)            # noqa: E731
+    lo, hi, cc = arr(p["lo"].reshape(M, 1)), arr(p["hi"].reshape(M, 1)), arr(c.reshape(N, 1))
+    bl, bu = arr(np.full((N, 1), -big)), arr(np.full((N, 1), big))
+    upper = arr([p["ntran"] * p["hi"].max() + 1e-9])                      # fmin*x = sum_tran H <= ntran*max U
+    z, info = np.zeros((N, 1)), np.zeros((1, 8))
+    kw = dict(max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR, eps_gap=EPS_GAP)
+    kw.update(solver_kw)
+    w_row, kap, amp = arr(p["w"]), arr(p["col_kappa"]), arr(p["col_amp"])
+    check(lib().mbrf_fir_pdhg_solve(_dp(w_row), None, M, _ip(p["col_type"]), _dp(kap), _dp(amp), N, -1, None, None, 0,
+                                    _dp(cc), _dp(lo), _dp(hi), _dp(bl), _dp(bu), None, 1, _dp(upper),
+                                    int(kw["max_iter"]), int(kw["check_every"]), float(kw["eps_pr"]),
+                                    float(kw["eps_dr"]), float(kw["eps_gap"]), _dp(z), _dp(info), None))
+    ok = info[0, 0] == 1.0                                                # exitflag == 1, :265
+    h = _fill_h(z[:, 0], p) if ok else np.zeros(0)
+    st = "Solved" if ok else "Failed"
+    if return_info:
+        return h, st, dict(x=z[:, 0].copy(), info=info[0].copy(), problem=p, c=c)
+    return h, st
+
+
+def _min_order_search(n, f, a, d, even_odd, solve, pick_longer):
+    """The bisection of ss/fir_min_order_linprog.m:84-232 (and ss/fir_min_order.m:84-226): odd lengths, then
+    even lengths capped by the best odd one; `solve(n_tap, h_warm)` is one feasibility probe."""
+    if even_odd not in (1, 2):
+        even_odd = 0                                                      # :65-69
+    hbest_odd, hbest_even = None, None
+    n_odd_max = 2 * ((n - 1) // 2) + 1                                    # :78-79
+    n_even_max = 2 * (n // 2)
+
+    def bisect(n_top, tap_of, hbest):
+        n_bot, n_cur = 1, n_top                                           # :91-93 / :152-160
+        while n_top - n_bot > 1:
+            h, st = solve(tap_of(n_cur), hbest)
+            if st == "Solved":
+                hbest = h
+                n_top = n_cur
+                n_cur = n_bot if n_top == n_bot + 1 else int(np.ceil((n_top + n_bot) / 2))   # :131-136
+            else:
+                n_bot = n_cur
+                n_cur = int(np.ceil((n_bot + n_top) / 2))                 # :141-142
+        return hbest
+
+    if even_odd != 2:
+        hbest_odd = bisect((n_odd_max + 1) // 2, lambda k: 2 * k - 1, None)
+    if even_odd != 1:
+        n_top = n_even_max // 2 if hbest_odd is None else min(n_even_max // 2, (len(hbest_odd) + 1) // 2)
+        hbest_even = bisect(n_top, lambda k: 2 * k, None)
+    if hbest_odd is None and hbest_even is None:
+        return np.zeros(0), "Failed"
+    if pick_longer:                                                       # fir_min_order.m:222-226 (its quirk)
+        lo_, le_ = (0 if hbest_odd is None else len(hbest_odd)), (0 if hbest_even is None else len(hbest_even))
+        return (hbest_odd if lo_ > le_ else hbest_even), "Solved"
+    if hbest_odd is None:
+        return hbest_even, "Solved"
+    if hbest_even is None or len(hbest_odd) < len(hbest_even):            # fir_min_order_linprog.m:220-228
+        return hbest_odd, "Solved"
+    return hbest_even, "Solved"
+
+
+def fir_min_order_linprog(n, f, a, d, even_odd=0, dbg=0, **solver_kw):
+    """[h, status] = fir_min_order_linprog(n, f, a, d, even_odd, dbg) — ss/fir_min_order_linprog.m:54-234."""
+    return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: fir_linprog(nt, f, a, d, hw, dbg, **solver_kw),
+                             pick_longer=False)
+
+
+def fir_min_order(n, f, a, d, even_odd=0, a_min=None, dbg=0, **solver_kw):
+    """[h, status] = fir_min_order(n, f, a, d, even_odd, a_min, dbg) — ss/fir_min_order.m:55-230.
+
+    The reference probes with fir_pm -> cfirpm (closed-source Parks-McClellan, ss/fir_pm.m:175), which cannot
+    be reproduced; per BASELINE.json's north star the search is re-expressed as LP feasibility: the same
+    bisection (and the same 'longer of odd/even' selection, :222-226) with fir_linprog probes.  a_min is
+    fir_pm's minimum-amplitude option and has no LP counterpart; it is accepted and ignored."""
+    return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: fir_linprog(nt, f, a, d, hw, dbg, **solver_kw),
+                             pick_longer=True)

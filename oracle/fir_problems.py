@@ -1,0 +1,170 @@
+"""TEST INFRASTRUCTURE ONLY — numpy restatement of how the reference BUILDS its convex FIR design
+problems (the solve itself happens in third-party code that is not under /root/reference:
+CVX 2.0 beta -> SeDuMi/SDPT3, MATLAB linprog).
+
+  build_fir_ap   : fir_ap_cvx.m:44-142 (grid, bands, A, bounds, stop rows, peak cones)
+  build_fir_lp   : ss/fir_linprog.m:46-240 (real / complex-Hermitian linear-phase LP)
+  build_fir_qp   : fir_qp_cvx.m:34-139
+
+Parity status: PARITY UNPINNED by the reference (no solver, no golden vectors).
+What is pinned: the known-answer of the cone-free fir_ap_cvx LP at N=256 on the dual-band H-1 spec
+(15 490 rows x 513 vars, objective 0.0160332 with HiGHS) — checked in tests/test_oracle_fir.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# dual-band H-1 saturation spec after shift_f (specsat_H1_dualband.m:5-32 -> dzrf_mb.m:100-147), SURVEY.md 8(d)
+H1_DUALBAND = dict(
+    f=np.array([-0.047006, -0.027115, -0.016335, 0.013779, 0.029671, 0.047006]),
+    a=np.array([0.865905, 0.865905, 0.0, 0.0, 0.706886, 0.706886]),
+    d=np.array([0.014436, 0.022361, 0.017683]),
+)
+
+
+def _bands(w, f, a, d):
+    """fir_ap_cvx.m:51-82 / fir_qp_cvx.m:41-73: band membership, interpolated amplitude, bounds."""
+    nband = len(f) // 2
+    idx_band, U, L, M, D = [], [], [], [], []
+    for b in range(nband):
+        lo, hi = f[2 * b], f[2 * b + 1]
+        idx = np.nonzero((w >= lo) & (w <= hi))[0]
+        idx_band.append(idx)
+        if lo == hi:
+            amp = np.full(idx.size, a[2 * b])
+        else:
+            amp = a[2 * b] + (a[2 * b + 1] - a[2 * b]) * ((w[idx] - lo) / (hi - lo))
+        U.append(amp + d[b]); L.append(amp - d[b]); M.append(amp); D.append(np.full(idx.size, d[b]))
+    idx_band = np.concatenate(idx_band)
+    U, L, M, D = map(np.concatenate, (U, L, M, D))
+    mask = np.ones(w.size, bool)
+    mask[idx_band] = False
+    idx_tran = np.nonzero(mask)[0]
+    return idx_band, idx_tran, U, L, M, D
+
+
+def build_fir_ap(n, f, a, d, obj=0.0, peak=1e-3, oversamp=15):
+    """fir_ap_cvx.m.  Variables z = [x (2n-1); ripple_stop].  Returns dict with
+       w (m,)           reordered grid, band rows first then transition rows (:86-91)
+       lo, hi (m,)      L_b <= A x <= U_b                                        (:103-120)
+       stop (k,) int    rows with A x <= ripple_stop                               (:125)
+       c (2n,)          objective x1 + obj*ripple_stop                             (:163)
+       radius (n,)      |x1| <= n*Peak ; ||(x_i, x_{n+i-1})|| <= (n-i+1)*Peak       (:166-168)
+    """
+    f = np.asarray(f, float) * np.pi                       # :44
+    a = np.asarray(a, float); d = np.asarray(d, float)
+    m = 2 * n * oversamp                                   # :45-46
+    w = np.sort(np.concatenate([np.linspace(-np.pi, np.pi, m), f]))   # :47-48
+    idx_band, idx_tran, U, L, _, _ = _bands(w, f, a, d)
+    if idx_tran.size:                                      # :67-75
+        U_tran = np.full(idx_tran.size, U.max())
+        L_tran = np.full(idx_tran.size, min(0.0, L.min()))
+    else:
+        U_tran = L_tran = np.zeros(0)
+    w = np.concatenate([w[idx_band], w[idx_tran]])         # :86-91
+    U_b = np.concatenate([U, U_tran]) ** 2                 # :103-106
+    L_b = np.concatenate([L, L_tran])
+    L_b[L_b < 0] = 0                                       # :110-112
+    L_b = L_b ** 2
+    L_b[L_b < 1e-20] = 1e-20                               # :115-116  epsilon^2
+    stop = np.nonzero(np.sqrt(U_b) < np.sqrt(U_b).min() + 1e-2)[0]   # :125
+    c = np.zeros(2 * n)
+    c[0] = 1.0
+    c[-1] = obj
+    radius = (n - np.arange(1, n + 1) + 1) * peak         # :166-168, i = 1..n
+    return dict(kind="ap", n=n, w=w, lo=L_b, hi=U_b, stop=stop, c=c, radius=radius, nband_rows=idx_band.size)
+
+
+def matrix_fir_ap(w, n):
+    """A = [1, 2cos(w k), 2sin(w k)], k = 1..n-1   (fir_ap_cvx.m:100)."""
+    k = np.arange(1, n)
+    wk = np.outer(w, k)
+    return np.hstack([np.ones((w.size, 1)), 2 * np.cos(wk), 2 * np.sin(wk)])
+
+
+def violation_fir_ap(p, z):
+    """Max constraint violation of z = [x; ripple_stop] in the problem's own units (absolute)."""
+    n = p["n"]
+    x, t = z[:2 * n - 1], z[-1]
+    S = matrix_fir_ap(p["w"], n) @ x
+    v = max(0.0, (S - p["hi"]).max(), (p["lo"] - S).max(), (S[p["stop"]] - t).max())
+    nx = np.abs(x[0])
+    nr = np.hypot(x[1:n], x[n:2 * n - 1])
+    v = max(v, nx - p["radius"][0], (nr - p["radius"][1:]).max())
+    return v
+
+
+def solve_fir_ap_highs(p, cone_sides=0):
+    """Independent CPU solve of the fir_ap_cvx problem with HiGHS.
+    cone_sides = 0 drops the 2-D peak cones (the cone-free LP of SURVEY.md 8d);
+    cone_sides = K > 0 replaces each disk by its circumscribed (outer) K-gon -> a lower bound on the
+    optimum; the inscribed K-gon (radius*cos(pi/K)) gives an upper bound (returned as second value).
+    """
+    from scipy.optimize import linprog
+    n = p["n"]
+    A = matrix_fir_ap(p["w"], n)
+    m = A.shape[0]
+    nv = 2 * n
+    rows = [np.hstack([A, np.zeros((m, 1))]), np.hstack([-A, np.zeros((m, 1))])]
+    rhs = [p["hi"], -p["lo"]]
+    S = np.hstack([A[p["stop"]], -np.ones((p["stop"].size, 1))])
+    rows.append(S); rhs.append(np.zeros(p["stop"].size))
+
+    def run(scale):
+        r2, b2 = list(rows), list(rhs)
+        bounds = [(None, None)] * nv
+        if cone_sides:
+            bounds = list(bounds)
+            bounds[0] = (-p["radius"][0], p["radius"][0])
+            ang = 2 * np.pi * np.arange(cone_sides) / cone_sides
+            for i in range(1, n):
+                blk = np.zeros((cone_sides, nv))
+                blk[:, i] = np.cos(ang); blk[:, n + i - 1] = np.sin(ang)
+                r2.append(blk); b2.append(np.full(cone_sides, p["radius"][i] * scale))
+        res = linprog(p["c"], A_ub=np.vstack(r2), b_ub=np.concatenate(b2), bounds=bounds, method="highs")
+        return res
+    outer = run(1.0)
+    if not cone_sides:
+        return outer, None
+    inner = run(np.cos(np.pi / cone_sides))
+    return outer, inner
+
+
+# --------------------------------------------------------------------------------------------
+# ss/fir_linprog.m
+# --------------------------------------------------------------------------------------------
+def build_fir_lp(n, f, a, d):
+    """ss/fir_linprog.m:46-240: returns dict(A (m, nx), lo, hi, c=fmin, meta) or None when the reference
+    refuses the spec (even n with amplitude 1 at fs/2, :63-75)."""
+    f = np.asarray(f, float) * np.pi
+    a = np.asarray(a, float); d = np.asarray(d, float)
+    real_filter = f.min() >= 0                               # :48-52
+    odd = n % 2 == 1                                         # :56-60
+    if not odd and np.any(a[np.abs(f) == np.pi] == 1):       # :63-75
+        return None
+    nhalf = -(-n // 2)                                       # :79
+    w = np.linspace(0, np.pi, 15 * n) if real_filter else np.linspace(-np.pi, np.pi, 30 * n)   # :92-101
+    w = np.sort(np.concatenate([w, f]))                      # :107
+    idx_band, idx_tran, U, L, _, _ = _bands(w, f, a, d)
+    U_tran = np.full(idx_tran.size, U.max())                 # :163-171
+    L_tran = np.full(idx_tran.size, min(0.0, L.min()))
+    w = np.concatenate([w[idx_band], w[idx_tran]])           # :175-180
+    if odd:                                                  # :195-217
+        k = np.arange(1, nhalf)
+        Acos = np.hstack([np.ones((w.size, 1)), 2 * np.cos(np.outer(w, k))])
+        Asin = 2 * np.sin(np.outer(w, k))
+    else:
+        k = np.arange(0, nhalf) + 0.5
+        Acos = 2 * np.cos(np.outer(w, k))
+        Asin = 2 * np.sin(np.outer(w, k))
+    A = Acos if real_filter else np.hstack([Acos, Asin])
+    c = A[idx_band.size:].sum(0)                             # :231
+    return dict(kind="lp", n=n, A=A, w=w, lo=np.concatenate([L, L_tran]), hi=np.concatenate([U, U_tran]), c=c,
+                real=real_filter, odd=odd, nhalf=nhalf)
+
+
+def solve_fir_lp_highs(p):
+    from scipy.optimize import linprog
+    A = p["A"]
+    return linprog(p["c"], A_ub=np.vstack([A, -A]), b_ub=np.concatenate([p["hi"], -p["lo"]]),
+                   bounds=[(None, None)] * A.shape[1], method="highs")

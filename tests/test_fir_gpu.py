@@ -1,0 +1,137 @@
+"""GPU tests of the convex FIR design step (batched restarted PDHG), through the C ABI (mbrf_fir_pdhg_solve).
+
+Tolerances of BASELINE.json's north star: optimal objective within 1e-4 relative of the reference solve,
+constraint violation <= 1e-6.  The reference solve is HiGHS on the restated problem (cone-free LP, and
+outer/inner 32-gon brackets of the peak cones) — tests/golden/fir_ap_known.json."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+KNOWN = json.load(open(os.path.join(GOLDEN, "fir_ap_known.json")))
+TOL_OBJ = 1e-4     # relative
+TOL_VIOL = 1e-6    # absolute, in the problem's own units (|H|^2, |r_k|)
+
+
+def _solve(mbrf, k, **kw):
+    from multiband_rf_pulse_design_b200 import fir
+    hs, st, ex = fir.fir_ap_cvx_batch(k["n"], [k["f"]], k["a"], k["d"], [k["obj"]], [k["peak"]], return_info=True, **kw)
+    return hs[0], st[0], ex
+
+
+@pytest.mark.parametrize("case", ["lowpass_n24", "lowpass_n24_obj10", "lowpass_n24_tightpeak", "twoband_n40"])
+def test_small_designs_vs_highs(mbrf, case):
+    from oracle.fir_problems import build_fir_ap, violation_fir_ap
+    k = KNOWN[case]
+    h, st, ex = _solve(mbrf, k)
+    assert st == "Solved" and h.size == k["n"]
+    p = build_fir_ap(k["n"], k["f"], k["a"], k["d"], k["obj"], k["peak"])
+    z = np.concatenate([ex["x"][0], [ex["ripple_stop"][0]]])
+    obj = p["c"] @ z
+    assert k["outer_obj"] * (1 - TOL_OBJ) <= obj <= k["inner_obj"] * (1 + TOL_OBJ), (obj, k["outer_obj"], k["inner_obj"])
+    assert violation_fir_ap(p, z) <= TOL_VIOL
+
+
+def test_n256_dualband_known_answer(mbrf):
+    """BASELINE config 4's spec at N=256: 7686 grid rows, objective 0.0160330 (HiGHS, cones inactive)."""
+    from oracle.fir_problems import build_fir_ap, violation_fir_ap
+    k = KNOWN["h1_dualband_n256"]
+    h, st, ex = _solve(mbrf, k)
+    assert st == "Solved"
+    p = build_fir_ap(k["n"], k["f"], k["a"], k["d"], k["obj"], k["peak"])
+    z = np.concatenate([ex["x"][0], [ex["ripple_stop"][0]]])
+    assert abs(p["c"] @ z - k["cone_free_obj"]) <= TOL_OBJ * k["cone_free_obj"]
+    assert violation_fir_ap(p, z) <= TOL_VIOL
+    # the returned taps are the minimum-phase spectral factor: |H(w)|^2 reproduces the solved spectrum A x
+    from oracle.fir_problems import matrix_fir_ap
+    w = np.linspace(-np.pi, np.pi, 512, endpoint=False)
+    S = matrix_fir_ap(w, k["n"]) @ ex["x"][0]
+    H = np.array([np.sum(h * np.exp(-1j * wi * np.arange(k["n"]))) for wi in w])
+    assert np.abs(np.abs(H) ** 2 - S).max() < 2e-2 * S.max()      # fmp2 is a 4096-point FFT/Hilbert approximation (~1 %)
+
+
+@pytest.mark.parametrize("case", ["lowpass_n24_peak_infeasible", "lowpass_n10_infeasible", "h1_dualband_n128_infeasible"])
+def test_infeasible_designs_fail_like_cvx(mbrf, case):
+    """fir_ap_cvx.m:176-182: anything but 'Solved' is 'Failed' with h = []."""
+    k = KNOWN[case]
+    h, st = mbrf.fir_ap_cvx(k["n"], k["f"], k["a"], k["d"], k["obj"], k["peak"], max_iter=40000)
+    assert st == "Failed" and h.size == 0
+
+
+def test_batch_equals_single_and_ragged_edges(mbrf):
+    """Designs with different band edges share one matrix (union of grid rows); results equal single solves."""
+    from multiband_rf_pulse_design_b200 import fir
+    k = KNOWN["lowpass_n24"]
+    f0 = np.array(k["f"], float)
+    fl = []
+    for fa in (0.0, 0.01, 0.03):
+        f = f0.copy()
+        f[0::2] -= fa
+        f[1::2] += fa
+        f = np.clip(f, -1, 1)
+        fl.append(f)
+    objs, peaks = [0.1, 1.0, 0.1], [0.02, 0.02, 0.03]
+    hs, st, ex = fir.fir_ap_cvx_batch(k["n"], fl, k["a"], k["d"], objs, peaks, return_info=True)
+    assert st == ["Solved"] * 3
+    for b in range(3):
+        h1, s1, e1 = fir.fir_ap_cvx_batch(k["n"], [fl[b]], k["a"], k["d"], [objs[b]], [peaks[b]], return_info=True)
+        assert s1 == ["Solved"]
+        o_b, o_1 = ex["info"][b, 2], e1["info"][0, 2]
+        assert abs(o_b - o_1) <= 2 * TOL_OBJ * abs(o_1)
+
+
+def test_fir_ap_min_transition_search(mbrf):
+    """fir_ap.m:57-134: widen the bands until the design fails; the returned spec is feasible, a wider one is not."""
+    k = KNOWN["lowpass_n24"]
+    h, st, n_op, f_op = mbrf.fir_ap(k["n"], k["f"], k["a"], k["d"], 0.02, 0, 1.0, 0, 0, max_iter=60000)
+    assert st == "Solved" and n_op == k["n"] and h.size == k["n"]
+    widened = f_op[1] - np.array(k["f"])[1]
+    assert widened > 0.0
+    f_more = np.array(f_op, float)
+    f_more[0::2] -= 2e-3
+    f_more[1::2] += 2e-3
+    _, st_more = mbrf.fir_ap_cvx(k["n"], np.clip(f_more, -1, 1), k["a"], k["d"], 0.1, 0.02, max_iter=60000)
+    assert st_more == "Failed"
+
+
+# ---- ss/fir_linprog.m family ---------------------------------------------------------------------
+LPK = json.load(open(os.path.join(GOLDEN, "fir_lp_known.json")))
+
+
+@pytest.mark.parametrize("case", ["lp_real_odd_n31", "lp_real_even_n30", "lp_cplx_odd_n41", "lp_cplx_even_n40"])
+def test_fir_linprog_vs_highs(mbrf, case):
+    from oracle.fir_problems import build_fir_lp
+    k = LPK[case]
+    h, st, ex = mbrf.fir_linprog(k["n"], k["f"], k["a"], k["d"], return_info=True)
+    assert st == "Solved" and h.size == k["n"]
+    p = build_fir_lp(k["n"], k["f"], k["a"], k["d"])
+    x = ex["x"]
+    H = p["A"] @ x
+    assert max((H - p["hi"]).max(), (p["lo"] - H).max()) <= TOL_VIOL
+    assert abs(p["c"] @ x - k["obj"]) <= TOL_OBJ * abs(k["obj"])
+    # linear phase: Hermitian taps (fill_h, fir_linprog.m:274-296)
+    assert np.abs(h - np.conj(h[::-1])).max() < 1e-12
+
+
+def test_fir_linprog_failures(mbrf):
+    k = LPK["lp_real_odd_n11_infeasible"]
+    h, st = mbrf.fir_linprog(k["n"], k["f"], k["a"], k["d"], max_iter=40000)
+    assert st == "Failed" and h.size == 0
+    # even length with amplitude 1 at fs/2 is refused up front (fir_linprog.m:63-75)
+    h, st = mbrf.fir_linprog(20, [0, 0.3, 0.5, 1], [0, 0, 1, 1], [0.01, 0.01])
+    assert st == "Failed" and h.size == 0
+
+
+@pytest.mark.parametrize("case", ["minorder_real_n40", "minorder_cplx_n48"])
+def test_min_order_searches(mbrf, case):
+    """ss/fir_min_order_linprog.m and ss/fir_min_order.m (LP-feasibility form): same bisection, same answer as
+    the search driven by HiGHS probes; fir_min_order keeps the reference's 'longer of odd/even' selection."""
+    k = LPK[case]
+    h, st = mbrf.fir_min_order_linprog(k["n"], k["f"], k["a"], k["d"], 0, 0, max_iter=60000)
+    assert st == k["linprog_status"] and h.size == k["linprog_len"]
+    h, st = mbrf.fir_min_order(k["n"], k["f"], k["a"], k["d"], 0, None, 0, max_iter=60000)
+    assert st == k["minorder_status"] and h.size == k["minorder_len"]

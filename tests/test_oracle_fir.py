@@ -1,0 +1,57 @@
+"""CPU tests of the solver-path oracle: problem construction restated from fir_ap_cvx.m, the numpy twin of the
+GPU's PDHG, and their agreement with the independent HiGHS known answers (tests/golden/fir_ap_known.json).
+Parity with the reference's own solver (CVX) is UNPINNED: it does not exist offline."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+KNOWN = json.load(open(os.path.join(GOLDEN, "fir_ap_known.json")))
+
+
+def test_product_assembly_equals_oracle_restatement():
+    """Host assembly in the product (fir.py) and the oracle's independent restatement build the same problem."""
+    from multiband_rf_pulse_design_b200 import fir
+    from oracle.fir_problems import H1_DUALBAND, build_fir_ap
+    for n, obj, peak in ((256, 0.1, 1e-3), (64, 3.0, 5e-3)):
+        a = fir.assemble_fir_ap(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], obj, peak)
+        b = build_fir_ap(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], obj, peak)
+        assert np.array_equal(a["w"], b["w"]) and np.array_equal(a["lo"], b["lo"]) and np.array_equal(a["hi"], b["hi"])
+        assert np.array_equal(np.nonzero(a["stop"])[0], b["stop"]) and np.array_equal(a["radius"], b["radius"])
+    k = KNOWN["h1_dualband_n256"]
+    assert k["rows"] == 7686 and k["stop_rows"] == 118            # 264 band + 7422 transition rows
+
+
+def test_known_answer_anchor():
+    """the cone-free N=256 LP on the dual-band H-1 spec has objective 0.01603 (HiGHS)."""
+    k = KNOWN["h1_dualband_n256"]
+    assert k["cone_free_status"] == 0 and abs(k["cone_free_obj"] - 0.0160330) < 2e-7
+    assert KNOWN["h1_dualband_n128_infeasible"]["cone_free_status"] != 0
+    assert KNOWN["lowpass_n10_infeasible"]["cone_free_status"] == 2
+
+
+@pytest.mark.parametrize("case", ["lowpass_n24", "lowpass_n24_tightpeak"])
+def test_numpy_pdhg_twin_matches_highs(case):
+    from oracle import pdhg_reference as P
+    from oracle.fir_problems import build_fir_ap, violation_fir_ap
+    k = KNOWN[case]
+    p = build_fir_ap(k["n"], k["f"], k["a"], k["d"], k["obj"], k["peak"])
+    r = P.solve(P.assemble_fir_ap([p]), max_iter=60000)
+    assert r["status"][0] == 1
+    z = r["z"][:, 0]
+    lo, hi = k["outer_obj"], k["inner_obj"]                        # bounds on the true SOCP optimum
+    assert lo * (1 - 1e-4) <= p["c"] @ z <= hi * (1 + 1e-4)
+    assert violation_fir_ap(p, z) <= 1e-6
+
+
+def test_numpy_pdhg_twin_certifies_infeasibility():
+    from oracle import pdhg_reference as P
+    from oracle.fir_problems import build_fir_ap
+    k = KNOWN["lowpass_n24_peak_infeasible"]
+    p = build_fir_ap(k["n"], k["f"], k["a"], k["d"], k["obj"], k["peak"])
+    upper = np.array([p["radius"][0] + p["c"][-1] * p["hi"][p["stop"]].max()])
+    r = P.solve(P.assemble_fir_ap([p]), max_iter=5000, obj_upper=upper)
+    assert r["status"][0] == 2
