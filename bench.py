@@ -197,6 +197,54 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------
+# solver leg (reported inside the same JSON line under "solver")
+# ----------------------------------------------------------------------------
+H1_DUALBAND = dict(f=[-0.047006, -0.027115, -0.016335, 0.013779, 0.029671, 0.047006],       # SURVEY.md 8(d):
+                   a=[0.865905, 0.865905, 0.0, 0.0, 0.706886, 0.706886],                     # specsat_H1_dualband.m:5-32
+                   d=[0.014436, 0.022361, 0.017683])                                         # after dzrf_mb's shift_f
+
+
+def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
+    """BASELINE config 4 shape: N=256 fir_ap_cvx designs of the dual-band H-1 saturation spec, a slice of the
+    obj x Peak trade-off grid (band edges fixed), `--solver-designs` per GPU, sharded by design instance.
+    One untimed warm-up batch of 64 designs, then ONE timed solve of the whole local share through the public
+    API fir_ap_cvx_sweep (host assembly + H2D + GPU solve + D2H inside the timed region)."""
+    from multiband_rf_pulse_design_b200 import fir
+    n = 256
+    per_gpu = args.solver_designs
+    total = per_gpu * world
+    n_obj = max(1, total // 8)
+    objs = np.logspace(-2, 1, n_obj)                    # stop-band weight; SURVEY.md 8(d) asks logspace(-2,4): above ~10 the
+                                                        # ripple-dominated objective converges too slowly for a bench leg (DESIGN.md 6)
+    peaks = np.logspace(-3.2, -2, 8)                    # Peak values that keep the spec feasible at N=256
+    fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], objs[:8], peaks, [0.0],
+                         max_iter=512)                  # warm-up: context, buffers, kernels
+    barrier()
+    l0 = lib.mbrf_launch_count()
+    t0 = time.perf_counter()
+    r = fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], objs, peaks, [0.0], rank=rank,
+                             world=world, batch=per_gpu, max_iter=60000)
+    sec = max_over_ranks(time.perf_counter() - t0)
+    launches = lib.mbrf_launch_count() - l0
+    barrier()
+    info = r["info"]
+    solved = int((info[:, 0] == 1).sum())
+    iters = float(info[:, 1].max()) if info.size else 0.0
+    # the dominant kernels are the two fp64 GEMMs of every iteration: 2 * 2*Mp*Np*Bp flops per iteration
+    Mp, Np, Bp = C.c_int(), C.c_int(), C.c_int()
+    lib.mbrf_pdhg_padded_sizes(7686 + 118, 2 * n, per_gpu, C.byref(Mp), C.byref(Np), C.byref(Bp))
+    flops = 4.0 * Mp.value * Np.value * Bp.value * iters
+    return {"metric": "N=256 FIR pulse designs solved/sec", "value": total / sec, "unit": "designs/s",
+            "designs": total, "designs_per_gpu": per_gpu, "solved_on_rank0": solved, "local_designs_rank0": int(info.shape[0]),
+            "seconds": sec, "iterations_max": iters, "gpu_launches": int(launches),
+            "workload": "cfg4 slice: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, obj x Peak trade-off grid",
+            "tolerances": {"eps_pr": fir.EPS_PR, "eps_gap_rel": fir.EPS_GAP, "eps_dr": fir.EPS_DR},
+            "gemm_tflops_lower_bound": flops / sec / 1e12,
+            "note": "fp64 restarted PDHG; products on the FP64 tensor path (mma.sync m8n8k4); whole call timed on the host "
+                    "(assembly + PCIe + solve); tflops = GEMM flops of the slowest design's iteration count / wall time"}
+
+
+# ----------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------
 def run_ours(args):
@@ -323,6 +371,11 @@ def run_ours(args):
     # the e2e result must be the same numbers as the device-resident leg
     chk = float(np.abs(h_out_np[2][:4096] - out[2][:4096].cpu().numpy()).max())
 
+    # ---- second hot path: convex FIR design step (BASELINE metric "N=256 FIR pulse designs solved/sec") --------
+    solver = None
+    if not args.no_solver:
+        solver = solver_leg(args, m, lib, rank, world, max_over_ranks, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -385,6 +438,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "solver": solver,
     }
     print(json.dumps(line))
     if world > 1:
@@ -399,6 +453,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solver", action="store_true", help="skip the FIR-design leg")
+    ap.add_argument("--solver-designs", type=int, default=128, help="fir_ap_cvx designs per GPU in the solver leg")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:

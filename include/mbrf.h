@@ -200,12 +200,12 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M,
 /* Device-resident core of the above on a padded batch (Mp, Np, Bp multiples of 64; arrays [dim x Bp]);
  * K row-major [Mp x ldk] with columns already scaled, KT its transpose [Np x Mp]. */
 int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
+int mbrf_pdhg_set_gemm(int use_dmma);   /* 1 (default): FP64 tensor tiles mma.sync.m8n8k4, 0: SIMT DFMA tiles */
 unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
 int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk,
-                           const double *c, const double *lo, const double *hi,
-                           const double *bl, const double *bu,
-                           const int *pair_i, const int *pair_j, int npairs, const double *rho,
-                           int Bp, int B, const double *obj_upper,
+                           double *c, double *lo, double *hi, double *bl, double *bu,   /* destroyed: compacted */
+                           const int *pair_i, const int *pair_j, int npairs, double *rho,
+                           int Bp, int B, double *obj_upper,
                            int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
                            double *z_out, double *y_out, double *info_out,
                            void *workspace, void *stream);

@@ -16,10 +16,10 @@
 extern "C" {
 int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
 unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
-int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, const double *c, const double *lo,
-                           const double *hi, const double *bl, const double *bu, const int *pair_i,
-                           const int *pair_j, int npairs, const double *rho, int Bp, int B,
-                           const double *obj_upper, int max_iter, int check_every, double eps_pr,
+int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, double *c, double *lo,
+                           double *hi, double *bl, double *bu, const int *pair_i,
+                           const int *pair_j, int npairs, double *rho, int Bp, int B,
+                           double *obj_upper, int max_iter, int check_every, double eps_pr,
                            double eps_dr, double eps_gap, double *z_out, double *y_out, double *info_out,
                            void *workspace, void *stream);
 }

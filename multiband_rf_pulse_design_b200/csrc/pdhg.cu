@@ -135,6 +135,91 @@ dgemm_kernel(const double *__restrict__ AT, int ldat,         // [kdim x R] row-
 }
 
 // ---------------------------------------------------------------------------
+// Same product on the FP64 tensor path: mma.sync.m8n8k4.f64 (DMMA).  tcgen05 has no fp64 kind, so this is
+// the only tensor-core route that keeps the solver's fp64 tolerance.  One warp instruction performs
+// 8x8x4 = 256 FMAs, i.e. 8 per thread for 2 operand doubles, which takes the issue-slot pressure of the
+// SIMT kernel away (there: 32 DFMA + 6 LDS per thread and k).
+// CTA 64 x 64, 4 warps in a 2 x 2 arrangement, warp tile 32 x 32 = 4 x 4 mma tiles, BK = 16.
+// Fragment layout (PTX ISA, m8n8k4 .f64): A(row = lane/4, k = lane%4), B(k = lane%4, col = lane/4),
+// C(row = lane/4, cols 2*(lane%4) + {0,1}).  Shared rows are padded to 72 doubles so that the four k-rows a
+// fragment load touches fall into the two halves of the banks: 2 wavefronts per LDS.64, the minimum for
+// 256 bytes.
+// ---------------------------------------------------------------------------
+constexpr int MMA_LD = 72;
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128)
+dgemm_mma_kernel(const double *__restrict__ AT, int ldat, const double *__restrict__ X, int Bp,
+                 double *__restrict__ C, int kdim_total, int kchunk, long long slab)
+{
+    __shared__ __align__(16) double As[2][BK][MMA_LD];
+    __shared__ __align__(16) double Bs[2][BK][MMA_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * kchunk;
+    const int k_end = min(kdim_total, k_begin + kchunk);
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;   // warp tile origin inside the CTA tile
+    const int lr = lane >> 2, lk = lane & 3;
+
+    auto load_slice = [&](int buf, int k0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int piece = e * 128 + tid;
+            const int kk = piece >> 5, c = (piece & 31) * 2;
+            cp_async16(&As[buf][kk][c], AT + (size_t)(k0 + kk) * ldat + row0 + c);
+            cp_async16(&Bs[buf][kk][c], X + (size_t)(k0 + kk) * Bp + col0 + c);
+        }
+        cp_async_commit();
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    int buf = 0;
+    if (k_begin < k_end) load_slice(0, k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        const bool more = k0 + BK < k_end;
+        if (more) {
+            load_slice(buf ^ 1, k0 + BK);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[buf][k4 + lk][wm + i * 8 + lr];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[buf][k4 + lk][wn + j * 8 + lr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    double *Cz = C + (size_t)blockIdx.z * slab;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2 *>(Cz + (size_t)(row0 + wm + i * 8 + lr) * Bp + col0 + wn + j * 8 + 2 * lk) =
+                make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+// ---------------------------------------------------------------------------
 // solver state
 // ---------------------------------------------------------------------------
 struct Ctl {           // per-design control block (device), doubles for simplicity
@@ -151,10 +236,10 @@ struct Problem {
     int Mp, Np, Bp, B, npairs, P;       // padded sizes, live designs, pairs, split-K slabs
     int ldk;
     const double *K, *KT;                       // K [Mp x ldk] and its transpose [Np x Mp]
-    const double *c, *lo, *hi, *bl, *bu, *rho;  // [dim x Bp]
+    double *c, *lo, *hi, *bl, *bu, *rho;        // [dim x Bp]  (compacted in place when designs finish)
     const int *pair_i, *pair_j;                 // [npairs]
     const int *pair_of;                         // [Np]: pair index of a coordinate or -1
-    const double *obj_upper;                    // [Bp] or null
+    double *obj_upper;                          // [Bp] or null
     double *z, *zbar, *zs, *z0, *zbest;         // [Np x Bp]
     double *y, *ys, *y0, *ybest;                // [Mp x Bp]
     double *S;                                  // [Mp x Bp]   K*zbar, K*z, K*zs
@@ -399,6 +484,28 @@ __global__ void reset_cnt_kernel(Problem p)
     if (p.ctl[b].restart == 2.0) p.ctl[b].cnt = 0.0;
 }
 
+// Batch compaction: finished designs leave the batch so that the GEMMs shrink with the work that is left.
+// dst[r][nb] = src[r][slot[nb]] for nb < keep, pad otherwise  (dst != src)
+__global__ void gather_cols_kernel(const double *__restrict__ src, int ld_old, double *__restrict__ dst, int ld_new,
+                                   const int *__restrict__ slot, int keep, long long rows, double pad)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * ld_new) return;
+    const long long r = idx / ld_new;
+    const int nb = (int)(idx % ld_new);
+    dst[idx] = nb < keep ? src[r * ld_old + slot[nb]] : pad;
+}
+// dst[r][orig[b]] = src[r][b] for b < live  (results back to the caller's design order)
+__global__ void scatter_cols_kernel(const double *__restrict__ src, int ld_cur, double *__restrict__ dst, int ld0,
+                                    const int *__restrict__ orig, int live, long long rows)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * live) return;
+    const long long r = idx / live;
+    const int b = (int)(idx % live);
+    dst[r * ld0 + orig[b]] = src[r * ld_cur + b];
+}
+
 // power iteration helpers for ||K||_2
 __global__ void scale_first_col_kernel(double *v, int n, int Bp, const double *nrm2)
 {
@@ -419,10 +526,13 @@ __global__ void norm2_first_col_kernel(const double *v, int n, int Bp, double *o
 
 static inline int up(int v, int a) { return (v + a - 1) / a * a; }
 
+static int g_use_dmma = 1;   // 1: mma.sync m8n8k4 f64 tiles, 0: SIMT DFMA tiles (mbrf_pdhg_set_gemm)
+
 static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st)   // C[Mp x Bp] = K X
 {
     dim3 grid(p.Bp / BN, p.Mp / BM, 1);
-    dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
+    if (g_use_dmma) dgemm_mma_kernel<<<grid, 128, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
+    else dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
     MBRF_LAUNCH_CHECK();
     return MBRF_OK;
 }
@@ -430,7 +540,8 @@ static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st
 {
     const int kchunk = up((p.Mp + p.P - 1) / p.P, BK);
     dim3 grid(p.Bp / BN, p.Np / BM, p.P);
-    dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.K, p.ldk, Y, p.Bp, G, p.Mp, kchunk, (long long)p.Np * p.Bp);
+    if (g_use_dmma) dgemm_mma_kernel<<<grid, 128, 0, st>>>(p.K, p.ldk, Y, p.Bp, G, p.Mp, kchunk, (long long)p.Np * p.Bp);
+    else dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.K, p.ldk, Y, p.Bp, G, p.Mp, kchunk, (long long)p.Np * p.Bp);
     MBRF_LAUNCH_CHECK();
     return MBRF_OK;
 }
@@ -442,6 +553,13 @@ using namespace mbrf;
 using namespace mbrf::pdhg;
 
 extern "C" {
+
+// choose the GEMM tile kernel: 1 = FP64 tensor path (mma.sync m8n8k4), 0 = SIMT DFMA
+int mbrf_pdhg_set_gemm(int use_dmma)
+{
+    g_use_dmma = use_dmma ? 1 : 0;
+    return MBRF_OK;
+}
 
 // sizes of the padded problem and of the workspace (bytes) for given live sizes
 int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp)
@@ -464,12 +582,22 @@ static int split_k(int Mp, int Np, int Bp)
     return P;
 }
 
+// doubles needed for the split-K slabs at any batch width the compaction can reach
+static size_t slab_doubles(int Mp, int Np, int Bp)
+{
+    size_t mx = 0;
+    for (int b = 64; b <= Bp; b += 64) {
+        const size_t v = (size_t)split_k(Mp, Np, b) * Np * b;
+        if (v > mx) mx = v;
+    }
+    return mx;
+}
+
 unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp)
 {
     const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
-    const int P = split_k(Mp, Np, Bp);
-    size_t d = 5 * zn + 4 * yn + yn + (size_t)P * zn + zn + 2 * NACC * (size_t)Bp;
-    return d * 8 + (size_t)Bp * sizeof(Ctl) + 256 + (size_t)Np * 4 + 64;
+    size_t d = 5 * zn + 4 * yn + yn + slab_doubles(Mp, Np, Bp) + zn + 2 * NACC * (size_t)Bp;
+    return d * 8 + (size_t)Bp * sizeof(Ctl) + 256 + (size_t)Np * 4 + 2 * (size_t)Bp * 4 + 128;
 }
 
 /*
@@ -477,10 +605,10 @@ unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp)
  * [dim x Bp] with the design index fastest.  info_out: [Bp x 8] doubles
  * (status, iters, obj, dual, pr, dr, rigorous lower bound, omega).
  */
-int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, const double *c, const double *lo,
-                           const double *hi, const double *bl, const double *bu, const int *pair_i,
-                           const int *pair_j, int npairs, const double *rho, int Bp, int B,
-                           const double *obj_upper, int max_iter, int check_every, double eps_pr,
+int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, double *c, double *lo,
+                           double *hi, double *bl, double *bu, const int *pair_i,
+                           const int *pair_j, int npairs, double *rho, int Bp, int B,
+                           double *obj_upper, int max_iter, int check_every, double eps_pr,
                            double eps_dr, double eps_gap, double *z_out, double *y_out, double *info_out,
                            void *workspace, void *stream)
 {
@@ -505,13 +633,14 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     p.z = w; w += zn; p.zbar = w; w += zn; p.zs = w; w += zn; p.z0 = w; w += zn; p.zbest = w; w += zn;
     p.y = w; w += yn; p.ys = w; w += yn; p.y0 = w; w += yn; p.ybest = w; w += yn;
     p.S = w; w += yn;
-    p.G = w; w += (size_t)p.P * zn;
+    p.G = w; w += slab_doubles(Mp, Np, Bp);
     p.G2 = w; w += zn;
     p.acc = w; w += 2 * NACC * (size_t)Bp;
     p.ctl = (Ctl *)w; w = (double *)((char *)w + (size_t)Bp * sizeof(Ctl));
     p.active = (int *)w; w += 32;
     int *pair_of = (int *)w;
     p.pair_of = pair_of;
+    int *d_slot = pair_of + Np, *d_orig = d_slot + Bp;   // compaction maps
 
     // ---- init state ----
     MBRF_CUDA(cudaMemsetAsync(workspace, 0, (char *)pair_of - (char *)workspace, st));
@@ -538,15 +667,16 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         MBRF_CUDA(cudaMemcpy2DAsync(p.zbar, (size_t)Bp * 8, h.data(), 8, 8, Np, cudaMemcpyHostToDevice, st));
         double *nrm = p.acc;  // scratch scalar
         Problem q = p;
-        q.P = 1;
         for (int itp = 0; itp < 40; ++itp) {
             norm2_first_col_kernel<<<1, 256, 0, st>>>(p.zbar, Np, Bp, nrm);
             MBRF_LAUNCH_CHECK();
             scale_first_col_kernel<<<(Np + 255) / 256, 256, 0, st>>>(p.zbar, Np, Bp, nrm);
             MBRF_LAUNCH_CHECK();
             if (int rc = gemm_nn(q, p.zbar, p.S, st)) return rc;
-            if (int rc = gemm_tn(q, p.S, p.G, st)) return rc;     // P = 1: G slab 0 = K^T K v
-            MBRF_CUDA(cudaMemcpyAsync(p.zbar, p.G, zn * 8, cudaMemcpyDeviceToDevice, st));
+            if (int rc = gemm_tn(q, p.S, p.G, st)) return rc;
+            reduce_slabs_kernel<<<(unsigned)((zn + 255) / 256), 256, 0, st>>>(p);   // G2 = K^T K v
+            MBRF_LAUNCH_CHECK();
+            MBRF_CUDA(cudaMemcpyAsync(p.zbar, p.G2, zn * 8, cudaMemcpyDeviceToDevice, st));
         }
         norm2_first_col_kernel<<<1, 256, 0, st>>>(p.zbar, Np, Bp, nrm);
         MBRF_LAUNCH_CHECK();
@@ -557,7 +687,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         if (!(knorm2 > 0.0) || !std::isfinite(knorm2)) { set_error("pdhg: ||K|| estimate failed (%g)", knorm2); return MBRF_EINVAL; }
         MBRF_CUDA(cudaMemsetAsync(p.zbar, 0, zn * 8, st));
         MBRF_CUDA(cudaMemsetAsync(p.S, 0, yn * 8, st));
-        MBRF_CUDA(cudaMemsetAsync(p.G, 0, (size_t)p.P * zn * 8, st));
+        MBRF_CUDA(cudaMemsetAsync(p.G, 0, slab_doubles(Mp, Np, Bp) * 8, st));
         MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)Bp * 8, st));
     }
     p.eta = 0.9 / sqrt(knorm2);
@@ -579,8 +709,8 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     // (handled by the first iteration's projection; z = 0 is only a starting point.)
 
     const int TPB = 256;
-    const unsigned gz = (unsigned)((zn + TPB - 1) / TPB), gy = (unsigned)((yn + TPB - 1) / TPB);
-    const dim3 gm((Bp + 63) / 64, 64);
+    unsigned gz = (unsigned)((zn + TPB - 1) / TPB), gy = (unsigned)((yn + TPB - 1) / TPB);
+    dim3 gm((Bp + 63) / 64, 64);
 
     auto iteration = [&]() -> int {
         if (int rc = gemm_tn(p, p.y, p.G, st)) return rc;
@@ -592,8 +722,8 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         return MBRF_OK;
     };
     auto check = [&](int iter_now) -> int {
-        MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)Bp * 8, st));
-        advance_kernel<<<(Bp + 63) / 64, 64, 0, st>>>(p);
+        MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)p.Bp * 8, st));
+        advance_kernel<<<(p.Bp + 63) / 64, 64, 0, st>>>(p);
         MBRF_LAUNCH_CHECK();
         for (int cand = 0; cand < 2; ++cand) {
             if (int rc = gemm_nn(p, cand == 0 ? p.zs : p.z, p.S, st)) return rc;
@@ -605,31 +735,109 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             col_metrics_kernel<<<gm, 64, 0, st>>>(p, cand);
             MBRF_LAUNCH_CHECK();
         }
-        control_kernel<<<(Bp + 63) / 64, 64, 0, st>>>(p, iter_now, max_iter);
+        control_kernel<<<(p.Bp + 63) / 64, 64, 0, st>>>(p, iter_now, max_iter);
         MBRF_LAUNCH_CHECK();
         apply_kernel<<<gz, TPB, 0, st>>>(p, 0);
         MBRF_LAUNCH_CHECK();
         apply_kernel<<<gy, TPB, 0, st>>>(p, 1);
         MBRF_LAUNCH_CHECK();
-        reset_cnt_kernel<<<(Bp + 63) / 64, 64, 0, st>>>(p);
+        reset_cnt_kernel<<<(p.Bp + 63) / 64, 64, 0, st>>>(p);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     };
 
     // Capture one block of `check_every` iterations as a CUDA graph: the inner loop is launch-bound for
-    // small batches (4 kernels of a few microseconds each per iteration).
+    // small batches (4 kernels of a few microseconds each per iteration).  Re-captured after a compaction.
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     bool use_graph = true;
-    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        int rc = MBRF_OK;
-        for (int i = 0; i < check_every && rc == MBRF_OK; ++i) rc = iteration();
-        cudaError_t e = cudaStreamEndCapture(st, &graph);
-        if (rc != MBRF_OK || e != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) use_graph = false;
-    } else {
-        use_graph = false;
-    }
-    if (!use_graph) cudaGetLastError();
+    auto capture = [&]() {
+        if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+        if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+        use_graph = true;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rc = MBRF_OK;
+            for (int i = 0; i < check_every && rc == MBRF_OK; ++i) rc = iteration();
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc != MBRF_OK || e != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) use_graph = false;
+        } else {
+            use_graph = false;
+        }
+        if (!use_graph) cudaGetLastError();
+    };
+    capture();
+
+    // results are kept in the caller's design order: z_out / y_out are [dim x Bp0], final control blocks on the host
+    const int Bp0 = Bp;
+    std::vector<int> orig((size_t)Bp0);
+    for (int b = 0; b < Bp0; ++b) orig[b] = b;
+    std::vector<Ctl> final_ctl((size_t)Bp0);
+    for (auto &f : final_ctl) { memset(&f, 0, sizeof(Ctl)); f.status = 1.0; }
+    MBRF_CUDA(cudaMemcpyAsync(d_orig, orig.data(), (size_t)Bp0 * 4, cudaMemcpyHostToDevice, st));
+    MBRF_CUDA(cudaMemsetAsync(z_out, 0, zn * 8, st));
+    if (y_out) MBRF_CUDA(cudaMemsetAsync(y_out, 0, yn * 8, st));
+
+    std::vector<Ctl> hc;
+    auto flush_results = [&]() -> int {   // snapshot every live slot into the caller-ordered outputs
+        hc.resize((size_t)p.Bp);
+        MBRF_CUDA(cudaMemcpyAsync(hc.data(), p.ctl, (size_t)p.Bp * sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+        const long long nz = (long long)p.Np * p.B, ny = (long long)p.Mp * p.B;
+        scatter_cols_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(p.zbest, p.Bp, z_out, Bp0, d_orig, p.B, p.Np);
+        MBRF_LAUNCH_CHECK();
+        if (y_out) {
+            scatter_cols_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(p.ybest, p.Bp, y_out, Bp0, d_orig, p.B, p.Mp);
+            MBRF_LAUNCH_CHECK();
+        }
+        MBRF_CUDA(cudaStreamSynchronize(st));
+        for (int b = 0; b < p.B; ++b) final_ctl[orig[b]] = hc[b];
+        return MBRF_OK;
+    };
+    auto compact = [&]() -> int {
+        if (int rc = flush_results()) return rc;
+        std::vector<int> slot;
+        for (int b = 0; b < p.B; ++b)
+            if (hc[b].status == 0.0) slot.push_back(b);
+        const int keep = (int)slot.size();
+        const int nBp = up(keep > 0 ? keep : 1, 64);
+        if (keep == 0 || nBp >= p.Bp) return MBRF_OK;
+        MBRF_CUDA(cudaMemcpyAsync(d_slot, slot.data(), (size_t)keep * 4, cudaMemcpyHostToDevice, st));
+        auto regather = [&](double *arr, long long rows, double *tmp, double pad) -> int {
+            if (!arr || rows == 0) return MBRF_OK;
+            const long long n = rows * nBp;
+            gather_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(arr, p.Bp, tmp, nBp, d_slot, keep, rows, pad);
+            MBRF_LAUNCH_CHECK();
+            MBRF_CUDA(cudaMemcpyAsync(arr, tmp, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+            return MBRF_OK;
+        };
+        double *nside[] = {p.z, p.zs, p.z0, p.zbest, p.c, p.bl, p.bu};
+        for (double *a : nside)
+            if (int rc = regather(a, p.Np, p.G2, 0.0)) return rc;
+        if (int rc = regather(p.rho, p.npairs, p.G2, 0.0)) return rc;
+        if (int rc = regather(p.obj_upper, 1, p.G2, INFINITY)) return rc;
+        double *mside[] = {p.y, p.ys, p.y0, p.ybest};
+        for (double *a : mside)
+            if (int rc = regather(a, p.Mp, p.S, 0.0)) return rc;
+        if (int rc = regather(p.lo, p.Mp, p.S, -INFINITY)) return rc;
+        if (int rc = regather(p.hi, p.Mp, p.S, INFINITY)) return rc;
+        std::vector<Ctl> nc((size_t)nBp);
+        std::vector<int> norig((size_t)Bp0, 0);
+        for (int b = 0; b < nBp; ++b) {
+            if (b < keep) { nc[b] = hc[slot[b]]; norig[b] = orig[slot[b]]; }
+            else { memset(&nc[b], 0, sizeof(Ctl)); nc[b].omega = 1.0; nc[b].tau = nc[b].sigma = p.eta; nc[b].status = 1.0; }
+        }
+        orig = norig;
+        MBRF_CUDA(cudaMemcpyAsync(p.ctl, nc.data(), (size_t)nBp * sizeof(Ctl), cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaMemcpyAsync(d_orig, orig.data(), (size_t)Bp0 * 4, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+        p.B = keep;
+        p.Bp = nBp;
+        p.P = split_k(p.Mp, p.Np, nBp);
+        gz = (unsigned)(((size_t)p.Np * nBp + TPB - 1) / TPB);
+        gy = (unsigned)(((size_t)p.Mp * nBp + TPB - 1) / TPB);
+        gm = dim3((nBp + 63) / 64, 64);
+        capture();
+        return MBRF_OK;
+    };
 
     int active = B, rcode = MBRF_OK;
     for (int it = 0; it < max_iter && active > 0 && rcode == MBRF_OK;) {
@@ -643,21 +851,19 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         if (rcode == MBRF_OK) rcode = check(it);
         if (rcode != MBRF_OK) break;
         if (cudaMemcpyAsync(&active, p.active, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess) { set_error("pdhg: status readback failed: %s", cudaGetErrorString(cudaGetLastError())); rcode = MBRF_ECUDA; }
+            cudaStreamSynchronize(st) != cudaSuccess) { set_error("pdhg: status readback failed: %s", cudaGetErrorString(cudaGetLastError())); rcode = MBRF_ECUDA; break; }
+        // finished designs leave the batch once they would free at least one 64-design column block
+        if (active > 0 && p.Bp > 64 && up(active, 64) < p.Bp && it < max_iter) rcode = compact();
     }
+    if (rcode == MBRF_OK) rcode = flush_results();
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
     if (rcode != MBRF_OK) return rcode;
 
-    MBRF_CUDA(cudaMemcpyAsync(z_out, p.zbest, zn * 8, cudaMemcpyDeviceToDevice, st));
-    if (y_out) MBRF_CUDA(cudaMemcpyAsync(y_out, p.ybest, yn * 8, cudaMemcpyDeviceToDevice, st));
     {
-        std::vector<Ctl> hc((size_t)Bp);
-        MBRF_CUDA(cudaMemcpyAsync(hc.data(), p.ctl, (size_t)Bp * sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-        MBRF_CUDA(cudaStreamSynchronize(st));
-        std::vector<double> info((size_t)Bp * 8);
-        for (int b = 0; b < Bp; ++b) {
-            const Ctl &c0 = hc[b];
+        std::vector<double> info((size_t)Bp0 * 8);
+        for (int b = 0; b < Bp0; ++b) {
+            const Ctl &c0 = final_ctl[b];
             double *o = &info[(size_t)b * 8];
             o[0] = c0.status == 0.0 ? 3.0 : c0.status; o[1] = c0.iters; o[2] = c0.obj; o[3] = c0.dual;
             o[4] = c0.pr; o[5] = c0.dr; o[6] = c0.rigorous; o[7] = c0.omega;

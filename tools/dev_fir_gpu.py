@@ -28,6 +28,8 @@ def run(n, spec, objs, peaks, **kw):
     print(f"  batch of {B}: {dt:.2f} s wall  ({B / dt:.2f} designs/s), launches so far {m.lib().mbrf_launch_count()}")
 
 
+import os as _os
+m.lib().mbrf_pdhg_set_gemm(int(_os.environ.get("MBRF_DMMA", "1")))
 which = sys.argv[1] if len(sys.argv) > 1 else "small"
 if which in ("small", "all"):
     run(24, LOWPASS, [0.1, 10.0, 0.1, 0.1], [0.02, 0.02, 0.0105, 1e-3])
