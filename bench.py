@@ -213,7 +213,7 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
     n = 256
     per_gpu = args.solver_designs
     total = per_gpu * world
-    n_obj = max(1, total // 8)
+    n_obj = max(1, total // 8)                          # 8 Peak values x n_obj weights
     objs = np.logspace(-2, 1, n_obj)                    # stop-band weight; SURVEY.md 8(d) asks logspace(-2,4): above ~10 the
                                                         # ripple-dominated objective converges too slowly for a bench leg
     peaks = np.logspace(-3.2, -2, 8)                    # Peak values that keep the spec feasible at N=256
@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solver", action="store_true", help="skip the FIR-design leg")
-    ap.add_argument("--solver-designs", type=int, default=128, help="fir_ap_cvx designs per GPU in the solver leg")
+    ap.add_argument("--solver-designs", type=int, default=512, help="fir_ap_cvx designs per GPU in the solver leg")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:

@@ -180,12 +180,15 @@ unsigned long long mbrf_abr_workspace_bytes(int ns);
  *      K[i][j] = col_amp[j] * {1, cos, sin}[col_type[j]] (w_row[i] * col_kappa[j]),  col_type 3 = zero,
  *      K[i][tcol] = tcoef[i]   (tcol < 0: no such column)
  * which covers A = [1, 2cos(w k), 2sin(w k)] (fir_ap_cvx.m:100), [Acos Asin] (fir_linprog.m:195-217)
- * and the ripple_stop column of fir_ap_cvx.m:165.  HOST pointers; per-design arrays are [dim x B]
+ * and an optional explicit column.  Rows [simplex_row0, simplex_row0+simplex_rows) add the term
+ * simplex_w[b] * max_i (K z)_i (over the rows of the block with hi == 0) to design b's objective: this is
+ * `obj*ripple_stop` with `A_U(idx_stop,:)*x <= ripple_stop` (fir_ap_cvx.m:163-165) with ripple_stop eliminated
+ * (its multipliers live on a simplex, handled exactly in the dual step).  HOST pointers; per-design arrays are [dim x B]
  * row-major (design index fastest).  obj_upper[b] (optional): an upper bound on the objective of any
  * feasible point; a dual bound above it certifies infeasibility (status 2).
  *   z_out [N x B]: solutions in the caller's units;  info_out [B x 8]: status (1 solved, 2 infeasible,
  *   3 iteration limit), iterations, objective, dual objective, max row violation, natural residual,
- *   rigorous lower bound on the optimum, primal weight;  colscale_out [N] optional.
+ *   rigorous lower bound on the optimum, max_i (K z)_i of the simplex block (= ripple_stop);  colscale_out [N] optional.
  * The status maps onto the reference's strings: 1 -> 'Solved', 2/3 -> 'Failed' (fir_ap_cvx.m:176-182).
  */
 int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M,
@@ -193,7 +196,9 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M,
                         const int *pair_i, const int *pair_j, int npairs,
                         const double *c, const double *lo, const double *hi,
                         const double *bl, const double *bu, const double *rho, int B,
-                        const double *obj_upper, int max_iter, int check_every,
+                        const double *obj_upper,
+                        int simplex_row0, int simplex_rows, const double *simplex_w,
+                        int max_iter, int check_every,
                         double eps_pr, double eps_dr, double eps_gap,
                         double *z_out, double *info_out, double *colscale_out);
 
@@ -206,6 +211,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
                            double *c, double *lo, double *hi, double *bl, double *bu,   /* destroyed: compacted */
                            const int *pair_i, const int *pair_j, int npairs, double *rho,
                            int Bp, int B, double *obj_upper,
+                           int simplex_row0, int simplex_rows, double *simplex_w,
                            int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
                            double *z_out, double *y_out, double *info_out,
                            void *workspace, void *stream);

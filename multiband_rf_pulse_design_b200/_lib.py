@@ -59,9 +59,10 @@ SIGNATURES = {
     "mbrf_pdhg_set_gemm": (_i, [_i]),
     "mbrf_pdhg_workspace_bytes": (C.c_ulonglong, [_i, _i, _i]),
     "mbrf_pdhg_solve_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp,
-                                    _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
+                                    _i, _i, _vp, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "mbrf_fir_pdhg_solve": (_i, [_dp, _dp, _i, c_int_p, _dp, _dp, _i, _i, c_int_p, c_int_p, _i,
-                                 _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _i, _i, _d, _d, _d, _dp, _dp, _dp]),
+                                 _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _i, _i, _dp, _i, _i, _d, _d, _d,
+                                 _dp, _dp, _dp]),
 }
 
 

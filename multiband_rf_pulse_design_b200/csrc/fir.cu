@@ -19,9 +19,9 @@ unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
 int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, double *c, double *lo,
                            double *hi, double *bl, double *bu, const int *pair_i,
                            const int *pair_j, int npairs, double *rho, int Bp, int B,
-                           double *obj_upper, int max_iter, int check_every, double eps_pr,
-                           double eps_dr, double eps_gap, double *z_out, double *y_out, double *info_out,
-                           void *workspace, void *stream);
+                           double *obj_upper, int srow0, int ns, double *simplex_w, int max_iter, int check_every,
+                           double eps_pr, double eps_dr, double eps_gap, double *z_out, double *y_out,
+                           double *info_out, void *workspace, void *stream);
 }
 
 namespace mbrf {
@@ -100,19 +100,22 @@ extern "C" {
  *   minimise c^T z  s.t.  lo <= K z <= hi,  bl <= z <= bu,  ||(z_pi, z_pj)|| <= rho
  * per-design arrays are [dim x B] row-major (design index fastest).  The solver scales the columns of K
  * to unit norm internally (pair members share a scale) and returns z in the caller's units.
+ * Rows [simplex_row0, simplex_row0 + simplex_rows) add  simplex_w[b] * max_i (K z)_i  to design b's objective
+ * (over the rows whose hi is 0; hi = +inf excludes a row from a design).
  * info: [B x 8] = status (1 solved, 2 infeasible, 3 iteration limit), iterations, objective, dual objective,
- *       max row violation, natural residual, rigorous lower bound on the optimum, primal weight.
+ *       max row violation, natural residual, rigorous lower bound on the optimum, max_i (K z)_i of the block.
  */
 int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const int *col_type,
                         const double *col_kappa, const double *col_amp, int N, int tcol, const int *pair_i,
                         const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
                         const double *bl, const double *bu, const double *rho, int B, const double *obj_upper,
-                        int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
+                        int simplex_row0, int simplex_rows, const double *simplex_w, int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
                         double *z_out, double *info_out, double *colscale_out)
 {
     if (int rc = require_device()) return rc;
     if (M <= 0 || N <= 0 || B <= 0 || !w_row || !col_type || !col_kappa || !col_amp || !c || !lo || !hi || !bl ||
-        !bu || !z_out || !info_out || npairs < 0 || (npairs && (!pair_i || !pair_j || !rho)) || tcol >= N) {
+        !bu || !z_out || !info_out || npairs < 0 || (npairs && (!pair_i || !pair_j || !rho)) || tcol >= N ||
+        simplex_rows < 0 || (simplex_rows > 0 && (!simplex_w || simplex_row0 < 0 || simplex_row0 + simplex_rows > M))) {
         set_error("fir_pdhg_solve: bad arguments");
         return MBRF_EINVAL;
     }
@@ -134,7 +137,7 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const i
                  brho = al((size_t)(npairs > 0 ? npairs : 1) * Bp * 8), binfo = al((size_t)Bp * 8 * 8),
                  bws = al(mbrf_pdhg_workspace_bytes(Mp, Np, Bp));
     const size_t total = 2 * bK + 2 * bw + 4 * bcol + 4 * bz /*c,bl,bu,zout*/ + 2 * by /*lo,hi*/ + 2 * bpair + brho +
-                         binfo + al((size_t)Bp * 8) + bws;
+                         binfo + 2 * al((size_t)Bp * 8) + bws;
     if (int rc = cx.dev.reserve(total)) return rc;
     char *d = (char *)cx.dev.ptr;
     auto take = [&](size_t b) { char *p = d; d += b; return p; };
@@ -144,7 +147,8 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const i
     double *dc = (double *)take(bz), *dbl = (double *)take(bz), *dbu = (double *)take(bz), *dz = (double *)take(bz);
     double *dlo = (double *)take(by), *dhi = (double *)take(by);
     int *dpi = (int *)take(bpair), *dpj = (int *)take(bpair);
-    double *drho = (double *)take(brho), *dinfo = (double *)take(binfo), *dupper = (double *)take(al((size_t)Bp * 8));
+    double *drho = (double *)take(brho), *dinfo = (double *)take(binfo), *dupper = (double *)take(al((size_t)Bp * 8)),
+           *dsw = (double *)take(al((size_t)Bp * 8));
     void *dws = take(bws);
 
     // ---- matrix: build, column norms, scale ----
@@ -219,9 +223,17 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const i
         MBRF_CUDA(cudaStreamSynchronize(st));
     }
 
+    if (simplex_rows > 0) {
+        h.assign((size_t)Bp, 0.0);
+        for (int b = 0; b < B; ++b) h[b] = simplex_w[b];
+        MBRF_CUDA(cudaMemcpyAsync(dsw, h.data(), (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+    }
+
     int rc = mbrf_pdhg_solve_device(dK, dKT, Mp, Np, ldk, dc, dlo, dhi, dbl, dbu, npairs ? dpi : nullptr,
                                     npairs ? dpj : nullptr, npairs, npairs ? drho : nullptr, Bp, B,
-                                    obj_upper ? dupper : nullptr, max_iter, check_every, eps_pr, eps_dr, eps_gap, dz,
+                                    obj_upper ? dupper : nullptr, simplex_row0, simplex_rows,
+                                    simplex_rows > 0 ? dsw : nullptr, max_iter, check_every, eps_pr, eps_dr, eps_gap, dz,
                                     nullptr, dinfo, dws, st);
     if (rc) return rc;
     h.assign(zn, 0.0);

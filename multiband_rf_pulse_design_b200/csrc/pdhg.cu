@@ -228,7 +228,7 @@ struct Ctl {           // per-design control block (device), doubles for simplic
     double since, cnt;          // iterations since last restart / samples in the running sums
     double status;              // 0 running, 1 solved, 2 infeasible (certificate), 3 iteration limit
     double iters;               // iteration at which status was decided
-    double obj, dual, pr, dr, rigorous;
+    double obj, dual, pr, dr, rigorous, tmax;
     double restart, use_avg;    // decisions of the last check
 };
 
@@ -240,6 +240,8 @@ struct Problem {
     const int *pair_i, *pair_j;                 // [npairs]
     const int *pair_of;                         // [Np]: pair index of a coordinate or -1
     double *obj_upper;                          // [Bp] or null
+    int srow0, ns;                              // simplex block: rows [srow0, srow0+ns) carry  w_b * max_i (K z)_i
+    double *sw;                                 // [Bp] weights w_b of that block (null when ns == 0)
     double *z, *zbar, *zs, *z0, *zbest;         // [Np x Bp]
     double *y, *ys, *y0, *ybest;                // [Mp x Bp]
     double *S;                                  // [Mp x Bp]   K*zbar, K*z, K*zs
@@ -252,7 +254,7 @@ struct Problem {
     int check_every;
 };
 
-enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, NACC };
+enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, NACC };
 
 __device__ __forceinline__ void atomic_max_pos(double *addr, double v)
 {
@@ -308,6 +310,8 @@ __global__ void y_update_kernel(Problem p)
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.Mp * p.Bp) return;
     const int b = (int)(idx % p.Bp);
+    const int row = (int)(idx / p.Bp);
+    if (row >= p.srow0 && row < p.srow0 + p.ns) return;   // simplex block: simplex_update_kernel
     const double sig = p.ctl[b].sigma;
     const double v = p.y[idx] + sig * p.S[idx];
     const double w = v / sig, lo = p.lo[idx], hi = p.hi[idx];
@@ -315,6 +319,60 @@ __global__ void y_update_kernel(Problem p)
     const double yn = w > hi ? v - sig * hi : (w < lo ? v - sig * lo : 0.0);
     p.y[idx] = yn;
     p.ys[idx] += yn;
+}
+
+// The term  w * max_{i in stop rows} (K z)_i  of the objective (fir_ap_cvx.m:163-165: obj*ripple_stop with
+// A_U(idx_stop,:) x <= ripple_stop) is handled through its conjugate: the multipliers of those rows live on the
+// scaled simplex {y >= 0, sum y = w}, so the dual step is  y+ = Proj_simplex(y + sigma K zbar)  and ripple_stop
+// never appears as a variable (it is the multiplier of the simplex constraint; its value is max_i (K z)_i).
+// Rows of the block that do not belong to a design (hi = +inf) keep y = 0.  One warp per design; Michelot's
+// fixed-point iteration  theta <- (sum_{v > theta} v - w) / #{v > theta}  (monotone, finite).
+__global__ void simplex_update_kernel(Problem p)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= p.Bp) return;
+    const double sig = p.ctl[b].sigma, w = p.sw[b];
+    double sum = 0.0;
+    int cnt = 0;
+    for (int i = lane; i < p.ns; i += 32) {
+        const size_t o = (size_t)(p.srow0 + i) * p.Bp + b;
+        if (p.hi[o] == 0.0) {
+            const double v = p.y[o] + sig * p.S[o];
+            p.y[o] = v;              // stage v in place
+            sum += v;
+            ++cnt;
+        } else {
+            p.y[o] = -INFINITY;      // not a member
+        }
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, k); cnt += __shfl_xor_sync(0xffffffffu, cnt, k); }
+    double theta = cnt > 0 ? (sum - w) / cnt : 0.0;
+    if (cnt > 0 && w > 0.0) {
+        int prev = cnt;
+        for (int pass = 0; pass < 64; ++pass) {
+            double s2 = 0.0;
+            int c2 = 0;
+            for (int i = lane; i < p.ns; i += 32) {
+                const double v = p.y[(size_t)(p.srow0 + i) * p.Bp + b];
+                if (v > theta) { s2 += v; ++c2; }
+            }
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, k); c2 += __shfl_xor_sync(0xffffffffu, c2, k); }
+            if (c2 == 0) break;      // cannot happen for w > 0 (the largest v always exceeds theta); guard anyway
+            theta = (s2 - w) / c2;
+            if (c2 == prev) break;
+            prev = c2;
+        }
+    }
+    for (int i = lane; i < p.ns; i += 32) {
+        const size_t o = (size_t)(p.srow0 + i) * p.Bp + b;
+        const double v = p.y[o];
+        const double yn = (w > 0.0 && v > theta) ? v - theta : 0.0;
+        p.y[o] = yn;
+        p.ys[o] += yn;
+    }
 }
 
 // reduce split-K slabs: G2 = sum_p G_p
@@ -336,10 +394,16 @@ __global__ void row_metrics_kernel(Problem p, int cand)
     if (b >= p.Bp) return;
     const double inv = cand == 0 ? 1.0 / fmax(p.ctl[b].cnt, 1.0) : 1.0;
     const double *yv = cand == 0 ? p.ys : p.y;
-    double pr = 0.0, hs = 0.0, dy2 = 0.0;
+    double pr = 0.0, hs = 0.0, dy2 = 0.0, tmax = 0.0;
     for (int i = blockIdx.y; i < p.Mp; i += gridDim.y) {
         const size_t o = (size_t)i * p.Bp + b;
         const double kz = p.S[o] * inv, y = yv[o] * inv, lo = p.lo[o], hi = p.hi[o];
+        if (i >= p.srow0 && i < p.srow0 + p.ns) {      // simplex block: no constraint of its own, h* = 0
+            if (hi == 0.0) tmax = fmax(tmax, kz);
+            const double d = y - p.y0[o];
+            dy2 = fma(d, d, dy2);
+            continue;
+        }
         pr = fmax(pr, fmax(kz - hi, lo - kz));
         if (y > 0.0) hs += hi * y;
         else if (y < 0.0) hs += lo * y;
@@ -348,6 +412,7 @@ __global__ void row_metrics_kernel(Problem p, int cand)
     }
     double *acc = p.acc + (size_t)cand * NACC * p.Bp;
     atomic_max_pos(acc + A_PR * p.Bp + b, pr);
+    atomic_max_pos(acc + A_TMAX * p.Bp + b, tmax);
     atomicAdd(acc + A_HS * p.Bp + b, hs);
     atomicAdd(acc + A_DY2 * p.Bp + b, dy2);
 }
@@ -414,12 +479,13 @@ __global__ void control_kernel(Problem p, int iter_now, int max_iter)
     Ctl &c = p.ctl[b];
     c.restart = 0.0;
     if (b >= p.B) { c.status = 1.0; return; }     // padding designs
-    double err[2], pr[2], dr[2], po[2], du[2], rig[2], dz[2], dy[2];
+    double err[2], pr[2], dr[2], po[2], du[2], rig[2], dz[2], dy[2], tm[2];
     for (int k = 0; k < 2; ++k) {
         const double *a = p.acc + (size_t)k * NACC * p.Bp;
         pr[k] = a[A_PR * p.Bp + b];
         dr[k] = a[A_DR * p.Bp + b];
-        po[k] = a[A_POBJ * p.Bp + b];
+        tm[k] = a[A_TMAX * p.Bp + b];
+        po[k] = a[A_POBJ * p.Bp + b] + (p.ns > 0 ? p.sw[b] * tm[k] : 0.0);
         du[k] = -a[A_HS * p.Bp + b] + a[A_GZ * p.Bp + b];
         rig[k] = -a[A_HS * p.Bp + b] + a[A_RIGX * p.Bp + b];
         dz[k] = sqrt(a[A_DZ2 * p.Bp + b]);
@@ -430,7 +496,7 @@ __global__ void control_kernel(Problem p, int iter_now, int max_iter)
     const int k = err[0] < err[1] ? 0 : 1;
     c.use_avg = k == 0 ? 1.0 : 0.0;
     if (c.status == 0.0) {
-        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = fmax(rig[0], rig[1]);
+        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = fmax(rig[0], rig[1]); c.tmax = tm[k];
         const bool solved = pr[k] <= p.eps_pr && dr[k] <= p.eps_dr &&
                             fabs(po[k] - du[k]) <= p.eps_gap * fmax(fabs(po[k]), 1e-12);
         const bool infeasible = !solved && p.obj_upper && c.rigorous > p.obj_upper[b];
@@ -608,11 +674,15 @@ unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp)
 int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, double *c, double *lo,
                            double *hi, double *bl, double *bu, const int *pair_i,
                            const int *pair_j, int npairs, double *rho, int Bp, int B,
-                           double *obj_upper, int max_iter, int check_every, double eps_pr,
-                           double eps_dr, double eps_gap, double *z_out, double *y_out, double *info_out,
-                           void *workspace, void *stream)
+                           double *obj_upper, int srow0, int ns, double *simplex_w, int max_iter, int check_every,
+                           double eps_pr, double eps_dr, double eps_gap, double *z_out, double *y_out,
+                           double *info_out, void *workspace, void *stream)
 {
     if (int rc = require_device()) return rc;
+    if (ns < 0 || (ns > 0 && (!simplex_w || srow0 < 0 || srow0 + ns > Mp))) {
+        set_error("pdhg: bad simplex block srow0=%d ns=%d", srow0, ns);
+        return MBRF_EINVAL;
+    }
     if (Mp % 64 || Np % 64 || Bp % 64 || B < 1 || B > Bp || ldk < Np || ldk % 2 ||
         max_iter < 1 || check_every < 1 || npairs < 0) {
         set_error("pdhg: bad padded sizes Mp=%d Np=%d Bp=%d B=%d ldk=%d", Mp, Np, Bp, B, ldk);
@@ -627,6 +697,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     p.Mp = Mp; p.Np = Np; p.Bp = Bp; p.B = B; p.npairs = npairs; p.ldk = ldk; p.K = K; p.KT = KT;
     p.c = c; p.lo = lo; p.hi = hi; p.bl = bl; p.bu = bu; p.rho = rho; p.pair_i = pair_i; p.pair_j = pair_j;
     p.obj_upper = obj_upper; p.P = split_k(Mp, Np, Bp);
+    p.srow0 = ns > 0 ? srow0 : 0; p.ns = ns; p.sw = ns > 0 ? simplex_w : nullptr;
     p.eps_pr = eps_pr; p.eps_dr = eps_dr; p.eps_gap = eps_gap; p.check_every = check_every;
     const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
     double *w = (double *)workspace;
@@ -719,6 +790,10 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         if (int rc = gemm_nn(p, p.zbar, p.S, st)) return rc;
         y_update_kernel<<<gy, TPB, 0, st>>>(p);
         MBRF_LAUNCH_CHECK();
+        if (p.ns > 0) {
+            simplex_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
+            MBRF_LAUNCH_CHECK();
+        }
         return MBRF_OK;
     };
     auto check = [&](int iter_now) -> int {
@@ -814,6 +889,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             if (int rc = regather(a, p.Np, p.G2, 0.0)) return rc;
         if (int rc = regather(p.rho, p.npairs, p.G2, 0.0)) return rc;
         if (int rc = regather(p.obj_upper, 1, p.G2, INFINITY)) return rc;
+        if (int rc = regather(p.sw, 1, p.G2, 0.0)) return rc;
         double *mside[] = {p.y, p.ys, p.y0, p.ybest};
         for (double *a : mside)
             if (int rc = regather(a, p.Mp, p.S, 0.0)) return rc;
@@ -843,7 +919,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     for (int it = 0; it < max_iter && active > 0 && rcode == MBRF_OK;) {
         if (use_graph) {
             if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("pdhg: graph launch failed"); rcode = MBRF_ECUDA; break; }
-            g_launches.fetch_add(4ull * check_every, std::memory_order_relaxed);
+            g_launches.fetch_add((p.ns > 0 ? 5ull : 4ull) * check_every, std::memory_order_relaxed);
         } else {
             for (int i = 0; i < check_every && rcode == MBRF_OK; ++i) rcode = iteration();
         }
@@ -866,7 +942,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             const Ctl &c0 = final_ctl[b];
             double *o = &info[(size_t)b * 8];
             o[0] = c0.status == 0.0 ? 3.0 : c0.status; o[1] = c0.iters; o[2] = c0.obj; o[3] = c0.dual;
-            o[4] = c0.pr; o[5] = c0.dr; o[6] = c0.rigorous; o[7] = c0.omega;
+            o[4] = c0.pr; o[5] = c0.dr; o[6] = c0.rigorous; o[7] = c0.tmax;
         }
         MBRF_CUDA(cudaMemcpyAsync(info_out, info.data(), info.size() * 8, cudaMemcpyHostToDevice, st));
         MBRF_CUDA(cudaStreamSynchronize(st));

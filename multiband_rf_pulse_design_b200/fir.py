@@ -26,7 +26,8 @@ c_int_p = C.POINTER(C.c_int)
 
 # solver defaults: tolerances of BASELINE.json's north star with a safety margin
 EPS_PR = 8e-7      # max constraint violation (absolute, in |H|^2 units)      (<= 1e-6 required)
-EPS_DR = 2e-6      # natural residual in column-scaled units
+EPS_DR = 1e-4      # natural residual ||z - P_X(z - c - K^T y)||_inf in column-scaled units (PDLP-style 1e-4 class
+                   # dual tolerance; the objective and the violation are what the north star bounds)
 EPS_GAP = 5e-5     # |primal - dual| / |primal|                              (<= 1e-4 required)
 MAX_ITER = 200000
 CHECK_EVERY = 64
@@ -112,9 +113,8 @@ def _solve_batch_ap(n, designs, max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_
     srank[srows] = np.arange(srows.size)
     M = M1 + srows.size
     nx = 2 * n - 1
-    N = nx + 1
+    N = nx
     w_row = np.concatenate([allw, allw[srows]])
-    tcoef = np.concatenate([np.zeros(M1), -np.ones(srows.size)])
     lo = np.full((M, B), -np.inf)
     hi = np.full((M, B), np.inf)
     c = np.zeros((N, B))
@@ -122,35 +122,36 @@ def _solve_batch_ap(n, designs, max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_
     bu = np.full((N, B), np.inf)
     rho = np.zeros((n - 1, B))
     upper = np.zeros(B)
+    sw = np.zeros(B)
     for b, (p, ix) in enumerate(zip(designs, pos)):
         # a grid point may occur twice in a design (band edge coinciding with a base sample): keep the tighter
         np.maximum.at(lo[:, b], ix, p["lo"])
         np.minimum.at(hi[:, b], ix, p["hi"])
-        st = M1 + srank[ix[p["stop"]]]
-        hi[st, b] = 0.0                                                   # A(stop) x - t <= 0
-        c[0, b] = 1.0                                                     # minimise x(1) + obj*ripple_stop, :163
-        c[nx, b] = p["obj"]
+        # `A_U(idx_stop,:)*x <= ripple_stop` with `obj*ripple_stop` in the objective (:163-165)
+        #   ==  obj * max_{i in idx_stop} (A x)_i : the duplicate rows form the solver's simplex block
+        hi[M1 + srank[ix[p["stop"]]], b] = 0.0                            # membership flag of the block
+        sw[b] = p["obj"]
+        c[0, b] = 1.0                                                     # minimise x(1) + ..., :163
         bl[0, b], bu[0, b] = -p["radius"][0], p["radius"][0]              # |x1| <= n Peak, :167 (i = 1)
-        tmax = p["hi"][p["stop"]].max()
-        bl[nx, b], bu[nx, b] = 0.0, tmax     # implied: t >= S >= L_b > 0 and t = max S <= max U_b(stop) at the optimum
         rho[:, b] = p["radius"][1:]
-        upper[b] = p["radius"][0] + p["obj"] * tmax                       # no feasible point has a larger objective
-    col_type = np.concatenate([[0], np.full(n - 1, 1), np.full(n - 1, 2), [3]]).astype(np.int32)
+        upper[b] = p["radius"][0] + p["obj"] * p["hi"][p["stop"]].max()   # no feasible point has a larger objective
+    col_type = np.concatenate([[0], np.full(n - 1, 1), np.full(n - 1, 2)]).astype(np.int32)
     k = np.arange(1, n, dtype=float)
-    col_kappa = np.concatenate([[0.0], k, k, [0.0]])
-    col_amp = np.concatenate([[1.0], np.full(2 * n - 2, 2.0), [0.0]])    # A = [1, 2cos, 2sin], :100
+    col_kappa = np.concatenate([[0.0], k, k])
+    col_amp = np.concatenate([[1.0], np.full(2 * n - 2, 2.0)])            # A = [1, 2cos, 2sin], :100
     pair_i = np.arange(1, n, dtype=np.int32)                              # (x_i, x_{n+i-1}), :133-139
     pair_j = np.arange(n, 2 * n - 1, dtype=np.int32)
     z = np.zeros((N, B))
     info = np.zeros((B, 8))
-    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (w_row, tcoef, col_kappa, col_amp, c, lo, hi, bl, bu,
-                                                                  rho, upper)]
-    w_row, tcoef, col_kappa, col_amp, c, lo, hi, bl, bu, rho, upper = arrs
-    check(lib().mbrf_fir_pdhg_solve(_dp(w_row), _dp(tcoef), M, _ip(col_type), _dp(col_kappa), _dp(col_amp), N, nx,
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho,
+                                                                  upper, sw)]
+    w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho, upper, sw = arrs
+    check(lib().mbrf_fir_pdhg_solve(_dp(w_row), None, M, _ip(col_type), _dp(col_kappa), _dp(col_amp), N, -1,
                                     _ip(pair_i), _ip(pair_j), n - 1, _dp(c), _dp(lo), _dp(hi), _dp(bl), _dp(bu),
-                                    _dp(rho), B, _dp(upper), int(max_iter), int(check_every), float(eps_pr),
-                                    float(eps_dr), float(eps_gap), _dp(z), _dp(info), None))
-    return z[:nx].T.copy(), z[nx].copy(), info
+                                    _dp(rho), B, _dp(upper), M1, int(srows.size), _dp(sw), int(max_iter),
+                                    int(check_every), float(eps_pr), float(eps_dr), float(eps_gap), _dp(z), _dp(info),
+                                    None))
+    return z.T.copy(), info[:, 7].copy(), info
 
 
 # --------------------------------------------------------------------------------------------
@@ -427,7 +428,7 @@ def fir_linprog(n, f, a, d, h0=None, dbg=0, return_info=False, **solver_kw):
     kw.update(solver_kw)
     w_row, kap, amp = arr(p["w"]), arr(p["col_kappa"]), arr(p["col_amp"])
     check(lib().mbrf_fir_pdhg_solve(_dp(w_row), None, M, _ip(p["col_type"]), _dp(kap), _dp(amp), N, -1, None, None, 0,
-                                    _dp(cc), _dp(lo), _dp(hi), _dp(bl), _dp(bu), None, 1, _dp(upper),
+                                    _dp(cc), _dp(lo), _dp(hi), _dp(bl), _dp(bu), None, 1, _dp(upper), 0, 0, None,
                                     int(kw["max_iter"]), int(kw["check_every"]), float(kw["eps_pr"]),
                                     float(kw["eps_dr"]), float(kw["eps_gap"]), _dp(z), _dp(info), None))
     ok = info[0, 0] == 1.0                                                # exitflag == 1, :265

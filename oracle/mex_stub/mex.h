@@ -13,7 +13,7 @@
  * back as a return code + message instead of killing the test process.
  *
  * The same header is used to syntax/ABI-check our own MEX gateways
- * (multiband_rf_pulse_design_b200/matlab/*.c).
+ * (multiband_rf_pulse_design_b200/matlab, the *_mex.c files).
  */
 #ifndef MBRF_MEX_STUB_H
 #define MBRF_MEX_STUB_H

@@ -6,12 +6,12 @@ Canonical form (one dense matrix K shared by a batch of B designs, everything el
         minimise   c^T z      subject to   lo <= K z <= hi ,   z in X
         X = product of  boxes  z_j in [bl_j, bu_j]  and 2-D disks  ||(z_i, z_j)|| <= rho
 
-fir_ap_cvx (fir_ap_cvx.m:160-169) maps onto it with z = [x (2n-1); ripple_stop]:
+fir_ap_cvx (fir_ap_cvx.m:160-169) maps onto it with z = x (2n-1):
   rows 0..m-1      A x            in [L_b, U_b]                      (:103-120)
-  rows m..m+ns-1   A(stop) x - t  in (-inf, 0]                       (:165)  (stop rows duplicated into K)
+  rows m..m+ns-1   A(stop) x      the "simplex block": obj * max_i (A x)_i is added to the objective, which is
+                                  `obj*ripple_stop` s.t. `A_U(idx_stop,:)*x <= ripple_stop` (:163-165) with
+                                  ripple_stop eliminated; its multipliers live on {y >= 0, sum y = obj}
   x1 in [-n Peak, n Peak],  ||(x_i, x_{n+i-1})|| <= (n-i+1) Peak     (:166-168)
-  t  in [0, max U_b(stop)]   (implied by the rows: t >= S >= L_b > 0 and t = max S at the optimum; makes
-                              X compact so that the dual function below is finite for every y)
 Columns are scaled to unit norm (a cos/sin pair shares one scale so disks stay disks).
 
 Dual function (exact, X compact):  q(y) = -sum(hi*y+ - lo*y-) + min_{z in X} (c + K^T y)^T z,
@@ -41,11 +41,10 @@ def assemble_fir_ap(problems):
     st = p0["stop"]
     ns = st.size
     B = len(problems)
-    N = nx + 1
+    N = nx
     K = np.zeros((m + ns, N))
-    K[:m, :nx] = A
-    K[m:, :nx] = A[st]
-    K[m:, nx] = -1.0
+    K[:m] = A
+    K[m:] = A[st]                      # simplex block: obj * max_i (A x)_i over the stop rows
     cs = np.sqrt((K ** 2).sum(0))
     pair_i = np.arange(1, n)
     pair_j = np.arange(n, 2 * n - 1)
@@ -59,15 +58,28 @@ def assemble_fir_ap(problems):
     bl = np.full((N, B), -np.inf)
     bu = np.full((N, B), np.inf)
     rho = np.zeros((n - 1, B))
+    sw = np.zeros(B)
     for b, p in enumerate(problems):
         lo[:m, b] = p["lo"]
         hi[:m, b] = p["hi"]
-        c[:, b] = p["c"] / cs
+        c[0, b] = p["c"][0] / cs[0]
+        sw[b] = p["c"][-1]
         bl[0, b], bu[0, b] = -p["radius"][0] * cs[0], p["radius"][0] * cs[0]
-        bl[nx, b], bu[nx, b] = 0.0, p["hi"][st].max() * cs[nx]
         rho[:, b] = p["radius"][1:] * pm
     return dict(K=K, lo=lo, hi=hi, c=c, bl=bl, bu=bu, pair_i=pair_i, pair_j=pair_j, rho=rho, colscale=cs,
-                n=n, m=m, ns=ns)
+                n=n, m=m, ns=ns, srow0=m, sw=sw)
+
+
+def proj_simplex(v, w):
+    """Columns of v projected onto {y >= 0, sum y = w[b]} (sort-based; the GPU uses Michelot's iteration)."""
+    ns, B = v.shape
+    u = -np.sort(-v, axis=0)
+    css = np.cumsum(u, axis=0) - w
+    k = np.arange(1, ns + 1)[:, None]
+    cond = u - css / k > 0
+    r = ns - 1 - np.argmax(cond[::-1], axis=0)
+    theta = css[r, np.arange(B)] / (r + 1)
+    return np.where(w > 0, np.maximum(v - theta, 0.0), 0.0)
 
 
 def proj_X(z, q):
@@ -80,10 +92,8 @@ def proj_X(z, q):
     return z
 
 
-def dual_value(y, g, q):
-    """q(y) with g = c + K^T y: -h*(y) + min_{z in X} g^T z  (per design)."""
-    yp, ym = np.maximum(y, 0), np.maximum(-y, 0)
-    hs = np.where(yp > 0, q["hi"] * yp, 0.0).sum(0) - np.where(ym > 0, q["lo"] * ym, 0.0).sum(0)
+def dual_value_x(g, q):
+    """min_{z in X} g^T z  (per design), g = c + K^T y."""
     inpair = np.zeros(g.shape[0], bool)
     inpair[q["pair_i"]] = True
     inpair[q["pair_j"]] = True
@@ -91,10 +101,10 @@ def dual_value(y, g, q):
         box = np.where(g > 0, g * q["bl"], np.where(g < 0, g * q["bu"], 0.0))
     box = np.where(inpair[:, None], 0.0, box)
     disk = -(q["rho"] * np.hypot(g[q["pair_i"]], g[q["pair_j"]])).sum(0)
-    return -hs + box.sum(0) + disk
+    return box.sum(0) + disk
 
 
-def solve(q, max_iter=60000, check_every=64, eps_pr=5e-7, eps_dr=2e-6, eps_gap=5e-5, obj_upper=None, verbose=False):
+def solve(q, max_iter=60000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap=5e-5, obj_upper=None, verbose=False):
     """Batched restarted PDHG.  Returns dict(z (N,B) in ORIGINAL units, obj, dual, pr, status, iters)."""
     K = q["K"]
     M, N = K.shape
@@ -124,14 +134,17 @@ def solve(q, max_iter=60000, check_every=64, eps_pr=5e-7, eps_dr=2e-6, eps_gap=5
         """pr: max row violation; dr: natural residual ||z - P_X(z - g)||_inf; pobj; dobj = -h*(y) + g^T z
         (equals c^T z exactly when the rows are complementary); rig: rigorous lower bound q(y)."""
         Kz = K @ zz
-        pr = np.maximum(np.maximum(Kz - q["hi"], q["lo"] - Kz), 0).max(0)
+        s0, ns_ = q.get("srow0", K.shape[0]), q.get("ns", 0)
+        Kr, lo_r, hi_r, y_r = Kz[:s0], q["lo"][:s0], q["hi"][:s0], yy[:s0]
+        pr = np.maximum(np.maximum(Kr - hi_r, lo_r - Kr), 0).max(0)
         g = q["c"] + K.T @ yy
         dr = np.abs(zz - proj_X(zz - g, q)).max(0)
-        pobj = (q["c"] * zz).sum(0)
-        yp, ym = np.maximum(yy, 0), np.maximum(-yy, 0)
-        hs = np.where(yp > 0, q["hi"] * yp, 0.0).sum(0) - np.where(ym > 0, q["lo"] * ym, 0.0).sum(0)
+        tmax = np.maximum(Kz[s0:s0 + ns_].max(0), 0.0) if ns_ else 0.0
+        pobj = (q["c"] * zz).sum(0) + (q["sw"] * tmax if ns_ else 0.0)
+        yp, ym = np.maximum(y_r, 0), np.maximum(-y_r, 0)
+        hs = np.where(yp > 0, hi_r * yp, 0.0).sum(0) - np.where(ym > 0, lo_r * ym, 0.0).sum(0)
         dobj = -hs + (g * zz).sum(0)
-        rig = dual_value(yy, g, q)
+        rig = -hs + dual_value_x(g, q)
         return pr, dr, pobj, dobj, rig
 
     for it in range(1, max_iter + 1):
@@ -141,6 +154,9 @@ def solve(q, max_iter=60000, check_every=64, eps_pr=5e-7, eps_dr=2e-6, eps_gap=5
         wv = vv / sig
         with np.errstate(invalid="ignore"):
             y = np.where(wv > q["hi"], vv - sig * q["hi"], np.where(wv < q["lo"], vv - sig * q["lo"], 0.0))
+        if q.get("ns", 0):
+            s0_, ns_ = q["srow0"], q["ns"]
+            y[s0_:s0_ + ns_] = proj_simplex(vv[s0_:s0_ + ns_], q["sw"])
         z = zn
         zs += z
         ys += y
@@ -200,4 +216,5 @@ def solve(q, max_iter=60000, check_every=64, eps_pr=5e-7, eps_dr=2e-6, eps_gap=5
     ybest[:, run] = y[:, run]
     done_iter[run] = tot
     pr, dr, pobj, dobj, rig = metrics(zbest, ybest)
-    return dict(z=zbest / q["colscale"][:, None], obj=pobj, dual=dobj, pr=pr, dr=dr, rigorous_lower=rig, status=status, iters=done_iter, y=ybest)
+    ripple = (K @ zbest)[q["srow0"]:q["srow0"] + q["ns"]].max(0) if q.get("ns", 0) else np.zeros(B)
+    return dict(z=np.vstack([zbest / q["colscale"][:, None], ripple[None, :]]), obj=pobj, dual=dobj, pr=pr, dr=dr, rigorous_lower=rig, status=status, iters=done_iter, y=ybest)

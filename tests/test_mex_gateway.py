@@ -16,7 +16,7 @@ MEX = os.path.join(ROOT, "multiband_rf_pulse_design_b200", "matlab")
 @pytest.fixture(scope="module")
 def gateways(mbrf):
     subprocess.check_call(["make", "-s", "-C", MEX, "check"])
-    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx")}
+    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg")}
 
 
 def test_gateways_link_and_report_errors_like_the_reference(gateways, oracle, mbrf):
@@ -63,3 +63,37 @@ def test_abrx_gateway_vs_reference_outputs(gateways, oracle, name):
     assert err is None, err
     assert outs[0].shape == g["alpha"].shape
     assert np.abs(outs[0] - g["alpha"]).max() < TOL_SLR and np.abs(outs[1] - g["beta"]).max() < TOL_SLR
+
+
+@pytest.mark.gpu
+def test_fir_pdhg_gateway_solves_like_the_python_mirror(gateways, oracle, mbrf):
+    """fir_pdhg_mex driven with the arguments matlab/fir_ap_cvx.m builds (MATLAB dim-by-B matrices, 1-based
+    indices): same optimum as the Python mirror, which goes through the same C entry point."""
+    import json
+    from multiband_rf_pulse_design_b200 import fir
+    k = json.load(open(os.path.join(ROOT, "tests", "golden", "fir_ap_known.json")))["lowpass_n24"]
+    n, obj, peak = k["n"], k["obj"], k["peak"]
+    p = fir.assemble_fir_ap(n, k["f"], k["a"], k["d"], obj, peak)
+    m, st = p["w"].size, np.nonzero(p["stop"])[0]
+    N = 2 * n - 1
+    w_row = np.concatenate([p["w"], p["w"][st]])
+    col_type = np.concatenate([[0], np.ones(n - 1), 2 * np.ones(n - 1)])
+    col_kappa = np.concatenate([[0], np.arange(1, n), np.arange(1, n)])
+    col_amp = np.concatenate([[1], 2 * np.ones(2 * n - 2)])
+    c = np.zeros((N, 1)); c[0] = 1
+    lo = np.concatenate([p["lo"], np.full(st.size, -np.inf)]).reshape(-1, 1)
+    hi = np.concatenate([p["hi"], np.zeros(st.size)]).reshape(-1, 1)
+    bl = np.full((N, 1), -np.inf); bu = np.full((N, 1), np.inf)
+    tmax = p["hi"][st].max()
+    bl[0], bu[0] = -n * peak, n * peak
+    rho = p["radius"][1:].reshape(-1, 1)
+    outs, err = oracle.mex_call(gateways["fir_pdhg"], 2, w_row, np.zeros((0, 0)), col_type, col_kappa, col_amp, 0.0,
+                                np.arange(2, n + 1, dtype=float), np.arange(n + 1, 2 * n, dtype=float), c, lo, hi, bl, bu,
+                                rho, np.array([n * peak + obj * tmax]), np.array([200000, 64, 8e-7, 1e-4, 5e-5]),
+                                np.array([m + 1, st.size, obj], dtype=float))
+    assert err is None, err
+    z, info = outs
+    assert z.shape == (N, 1) and info.shape == (8, 1) and info[0, 0] == 1.0
+    assert k["outer_obj"] * (1 - 1e-4) <= info[2, 0] <= k["inner_obj"] * (1 + 1e-4)   # x1 + obj*ripple_stop
+    out, err = oracle.mex_call(gateways["fir_pdhg"], 2, w_row)
+    assert out is None and err.startswith("Usage:")
