@@ -41,6 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = sys.stdout
 METRIC = "Bloch spin-steps/sec"
 UNIT = "spin-steps/s"
 NTIME = 512
@@ -192,7 +193,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     return 0
 
 
@@ -441,13 +442,24 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "solver": solver,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def _claim_stdout():
+    """Keep the real stdout for the ONE JSON line; anything libraries print on fd 1 (e.g. NCCL's version banner)
+    goes to stderr instead."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

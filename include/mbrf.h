@@ -202,6 +202,33 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M,
                         double eps_pr, double eps_dr, double eps_gap,
                         double *z_out, double *info_out, double *colscale_out);
 
+/* Optional structure of the rows / columns beyond plain intervals (all fields 0 / NULL = absent).
+ * Weight arrays are per design: [B] host doubles for mbrf_fir_pdhg_solve2, [Bp] device doubles for
+ * mbrf_pdhg_solve_device. */
+typedef struct mbrf_pdhg_blocks {
+    int simplex_row0, simplex_rows;   /* rows adding  simplex_w[b] * max_i (K z)_i  over rows with hi == 0   */
+    double *simplex_w;                /*   (obj*ripple_stop, fir_ap_cvx.m:163-165)                              */
+    int disk_row0, disk_pairs;        /* row pairs (r, r+1): ||(K z)_pair - (lo[r], lo[r+1])|| <= hi[r]        */
+                                      /*   (norm(A_i*x - Hd_i) <= D_i, fir_qp_cvx.m:148-157)                    */
+    int group_row0, group_pairs;      /* row pairs adding  group_w[b] * max_i ||(K z)_pair_i||                  */
+    double *group_w;                  /*   (obj*Peak with norm(F_i*x) <= Peak, fir_qp_cvx.m:147,158-160)        */
+    int norm_coords;                  /* adds  norm_w[b] * ||z[0 .. norm_coords)||_2                            */
+    double *norm_w;                   /*   (E_total with norm(x,2) <= E_total, fir_qp_cvx.m:147,161)            */
+} mbrf_pdhg_blocks;
+
+/* Matrix description with the extras fir_qp_cvx needs: K[i][j] = row_scale[i] * col_amp[j] *
+ * trig_j(w_row[i]*col_kappa[j] + row_phase[i]) (+ explicit entries K[ti[k]][tj[k]] += tv[k]); NULL arrays mean
+ * phase 0 / scale 1 / no entries.  [cos sin; -sin cos] (fir_qp_cvx.m:96-109) is phase 0 and pi/2. */
+int mbrf_fir_pdhg_solve2(const double *w_row, const double *row_phase, const double *row_scale, int M,
+                         const int *col_type, const double *col_kappa, const double *col_amp, int N,
+                         int nnz, const int *ti, const int *tj, const double *tv,
+                         const int *pair_i, const int *pair_j, int npairs,
+                         const double *c, const double *lo, const double *hi,
+                         const double *bl, const double *bu, const double *rho, int B,
+                         const double *obj_upper, const mbrf_pdhg_blocks *blocks,
+                         int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
+                         double *z_out, double *info_out, double *colscale_out);
+
 /* Device-resident core of the above on a padded batch (Mp, Np, Bp multiples of 64; arrays [dim x Bp]);
  * K row-major [Mp x ldk] with columns already scaled, KT its transpose [Np x Mp]. */
 int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
@@ -210,8 +237,7 @@ unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
 int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk,
                            double *c, double *lo, double *hi, double *bl, double *bu,   /* destroyed: compacted */
                            const int *pair_i, const int *pair_j, int npairs, double *rho,
-                           int Bp, int B, double *obj_upper,
-                           int simplex_row0, int simplex_rows, double *simplex_w,
+                           int Bp, int B, double *obj_upper, const mbrf_pdhg_blocks *blocks,
                            int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
                            double *z_out, double *y_out, double *info_out,
                            void *workspace, void *stream);

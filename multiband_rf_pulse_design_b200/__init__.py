@@ -15,8 +15,8 @@ from ._lib import lib, MbrfError, library_path  # noqa: F401
 from .bloch import bloch, blochC, blochH, blochsimfz, GAMMA_C13, GAMMA_H1  # noqa: F401
 from .slr import abr, abrm, abrx  # noqa: F401
 from .fir import (fir_ap, fir_ap_cvx, fir_ap_cvx_batch, fir_linprog, fir_min_order,  # noqa: F401
-                  fir_min_order_linprog, fmp2)
+                  fir_min_order_linprog, fir_qp_cvx, fmp2)
 
 __all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "fir_ap", "fir_ap_cvx",
-           "fir_ap_cvx_batch", "fir_linprog", "fir_min_order", "fir_min_order_linprog", "fmp2", "lib", "MbrfError",
+           "fir_ap_cvx_batch", "fir_linprog", "fir_min_order", "fir_min_order_linprog", "fir_qp_cvx", "fmp2", "lib", "MbrfError",
            "library_path", "GAMMA_C13", "GAMMA_H1"]

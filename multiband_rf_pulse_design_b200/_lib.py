@@ -59,11 +59,22 @@ SIGNATURES = {
     "mbrf_pdhg_set_gemm": (_i, [_i]),
     "mbrf_pdhg_workspace_bytes": (C.c_ulonglong, [_i, _i, _i]),
     "mbrf_pdhg_solve_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp,
-                                    _i, _i, _vp, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
+                                    _vp, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
+    "mbrf_fir_pdhg_solve2": (_i, [_dp, _dp, _dp, _i, c_int_p, _dp, _dp, _i, _i, c_int_p, c_int_p, _dp,
+                                  c_int_p, c_int_p, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _vp,
+                                  _i, _i, _d, _d, _d, _dp, _dp, _dp]),
     "mbrf_fir_pdhg_solve": (_i, [_dp, _dp, _i, c_int_p, _dp, _dp, _i, _i, c_int_p, c_int_p, _i,
                                  _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _i, _i, _dp, _i, _i, _d, _d, _d,
                                  _dp, _dp, _dp]),
 }
+
+
+class PdhgBlocks(C.Structure):
+    """mbrf_pdhg_blocks (include/mbrf.h)."""
+    _fields_ = [("simplex_row0", C.c_int), ("simplex_rows", C.c_int), ("simplex_w", c_double_p),
+                ("disk_row0", C.c_int), ("disk_pairs", C.c_int),
+                ("group_row0", C.c_int), ("group_pairs", C.c_int), ("group_w", c_double_p),
+                ("norm_coords", C.c_int), ("norm_w", c_double_p)]
 
 
 def declared_symbols() -> list[str]:

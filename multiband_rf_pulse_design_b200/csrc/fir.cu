@@ -19,7 +19,7 @@ unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
 int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, double *c, double *lo,
                            double *hi, double *bl, double *bu, const int *pair_i,
                            const int *pair_j, int npairs, double *rho, int Bp, int B,
-                           double *obj_upper, int srow0, int ns, double *simplex_w, int max_iter, int check_every,
+                           double *obj_upper, const mbrf_pdhg_blocks *blocks, int max_iter, int check_every,
                            double eps_pr, double eps_dr, double eps_gap, double *z_out, double *y_out,
                            double *info_out, void *workspace, void *stream);
 }
@@ -27,8 +27,10 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
 namespace mbrf {
 namespace fir {
 
-// K[i][j] = amp_j * trig_j(w_i * kappa_j)   (type 0: 1, 1: cos, 2: sin, 3: 0);  K[i][tcol] = tcoef[i]
-__global__ void build_matrix_kernel(const double *__restrict__ w, const double *__restrict__ tcoef, int M,
+// K[i][j] = scale_i * amp_j * trig_j(w_i * kappa_j + phase_i)   (type 0: 1, 1: cos, 2: sin, 3: 0);
+// K[i][tcol] = tcoef[i]
+__global__ void build_matrix_kernel(const double *__restrict__ w, const double *__restrict__ phase,
+                                    const double *__restrict__ scale, const double *__restrict__ tcoef, int M,
                                     const int *__restrict__ type, const double *__restrict__ kappa,
                                     const double *__restrict__ amp, int N, int tcol, double *__restrict__ K,
                                     int Mp, int ldk)
@@ -41,12 +43,20 @@ __global__ void build_matrix_kernel(const double *__restrict__ w, const double *
         if (j == tcol) v = tcoef ? tcoef[i] : 0.0;
         else {
             const int t = type[j];
-            if (t == 0) v = amp[j];
-            else if (t == 1) v = amp[j] * cos(w[i] * kappa[j]);
-            else if (t == 2) v = amp[j] * sin(w[i] * kappa[j]);
+            const double ph = phase ? phase[i] : 0.0, sc = scale ? scale[i] : 1.0;
+            if (t == 0) v = sc * amp[j];
+            else if (t == 1) v = sc * amp[j] * cos(w[i] * kappa[j] + ph);
+            else if (t == 2) v = sc * amp[j] * sin(w[i] * kappa[j] + ph);
         }
     }
     K[idx] = v;
+}
+
+__global__ void add_entries_kernel(double *__restrict__ K, int ldk, int nnz, const int *__restrict__ ti,
+                                   const int *__restrict__ tj, const double *__restrict__ tv)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) atomicAdd(&K[(size_t)ti[k] * ldk + tj[k]], tv[k]);
 }
 
 // cs2[j] = sum_i K[i][j]^2 : one block per 32 columns, threads stride the rows
@@ -105,17 +115,18 @@ extern "C" {
  * info: [B x 8] = status (1 solved, 2 infeasible, 3 iteration limit), iterations, objective, dual objective,
  *       max row violation, natural residual, rigorous lower bound on the optimum, max_i (K z)_i of the block.
  */
-int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const int *col_type,
-                        const double *col_kappa, const double *col_amp, int N, int tcol, const int *pair_i,
-                        const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
-                        const double *bl, const double *bu, const double *rho, int B, const double *obj_upper,
-                        int simplex_row0, int simplex_rows, const double *simplex_w, int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
-                        double *z_out, double *info_out, double *colscale_out)
+static int solve_impl(const double *w_row, const double *row_phase, const double *row_scale, const double *tcoef,
+                      int M, const int *col_type, const double *col_kappa, const double *col_amp, int N, int tcol,
+                      int nnz, const int *ti, const int *tj, const double *tv, const int *pair_i, const int *pair_j,
+                      int npairs, const double *c, const double *lo, const double *hi, const double *bl,
+                      const double *bu, const double *rho, int B, const double *obj_upper,
+                      const mbrf_pdhg_blocks *blocks, int max_iter, int check_every, double eps_pr, double eps_dr,
+                      double eps_gap, double *z_out, double *info_out, double *colscale_out)
 {
     if (int rc = require_device()) return rc;
     if (M <= 0 || N <= 0 || B <= 0 || !w_row || !col_type || !col_kappa || !col_amp || !c || !lo || !hi || !bl ||
-        !bu || !z_out || !info_out || npairs < 0 || (npairs && (!pair_i || !pair_j || !rho)) || tcol >= N ||
-        simplex_rows < 0 || (simplex_rows > 0 && (!simplex_w || simplex_row0 < 0 || simplex_row0 + simplex_rows > M))) {
+        !bu || !z_out || !info_out || npairs < 0 || (npairs && (!pair_i || !pair_j || !rho)) || tcol >= N || nnz < 0 ||
+        (nnz && (!ti || !tj || !tv))) {
         set_error("fir_pdhg_solve: bad arguments");
         return MBRF_EINVAL;
     }
@@ -136,12 +147,16 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const i
                  bz = al(zn * 8), by = al(yn * 8), bpair = al((size_t)(npairs > 0 ? npairs : 1) * 4),
                  brho = al((size_t)(npairs > 0 ? npairs : 1) * Bp * 8), binfo = al((size_t)Bp * 8 * 8),
                  bws = al(mbrf_pdhg_workspace_bytes(Mp, Np, Bp));
-    const size_t total = 2 * bK + 2 * bw + 4 * bcol + 4 * bz /*c,bl,bu,zout*/ + 2 * by /*lo,hi*/ + 2 * bpair + brho +
+    const size_t bnz = al((size_t)(nnz > 0 ? nnz : 1) * 8);
+    const size_t total = 3 * bnz + 2 * bw + 2 * al((size_t)Bp * 8) + 2 * bK + 2 * bw + 4 * bcol + 4 * bz /*c,bl,bu,zout*/ + 2 * by /*lo,hi*/ + 2 * bpair + brho +
                          binfo + 2 * al((size_t)Bp * 8) + bws;
     if (int rc = cx.dev.reserve(total)) return rc;
     char *d = (char *)cx.dev.ptr;
     auto take = [&](size_t b) { char *p = d; d += b; return p; };
     double *dK = (double *)take(bK), *dKT = (double *)take(bK), *dw = (double *)take(bw), *dt = (double *)take(bw);
+    double *dph = (double *)take(bw), *dsc = (double *)take(bw);
+    int *dti = (int *)take(bnz), *dtj = (int *)take(bnz);
+    double *dtv = (double *)take(bnz), *dgw = (double *)take(al((size_t)Bp * 8)), *dlam = (double *)take(al((size_t)Bp * 8));
     int *dtype = (int *)take(bcol);
     double *dkap = (double *)take(bcol), *damp = (double *)take(bcol), *dcs = (double *)take(bcol);
     double *dc = (double *)take(bz), *dbl = (double *)take(bz), *dbu = (double *)take(bz), *dz = (double *)take(bz);
@@ -158,9 +173,21 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const i
     MBRF_CUDA(cudaMemcpyAsync(dkap, col_kappa, (size_t)N * 8, cudaMemcpyHostToDevice, st));
     MBRF_CUDA(cudaMemcpyAsync(damp, col_amp, (size_t)N * 8, cudaMemcpyHostToDevice, st));
     const long long nK = (long long)Mp * ldk;
-    build_matrix_kernel<<<(unsigned)((nK + 255) / 256), 256, 0, st>>>(dw, tcoef ? dt : nullptr, M, dtype, dkap, damp, N,
-                                                                     tcol, dK, Mp, ldk);
+    if (row_phase) MBRF_CUDA(cudaMemcpyAsync(dph, row_phase, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    if (row_scale) MBRF_CUDA(cudaMemcpyAsync(dsc, row_scale, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    build_matrix_kernel<<<(unsigned)((nK + 255) / 256), 256, 0, st>>>(dw, row_phase ? dph : nullptr, row_scale ? dsc : nullptr,
+                                                                     tcoef ? dt : nullptr, M, dtype, dkap, damp, N, tcol,
+                                                                     dK, Mp, ldk);
     MBRF_LAUNCH_CHECK();
+    if (nnz) {
+        for (int k = 0; k < nnz; ++k)
+            if (ti[k] < 0 || ti[k] >= M || tj[k] < 0 || tj[k] >= N) { set_error("fir_pdhg_solve: entry %d out of range", k); return MBRF_EINVAL; }
+        MBRF_CUDA(cudaMemcpyAsync(dti, ti, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaMemcpyAsync(dtj, tj, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        MBRF_CUDA(cudaMemcpyAsync(dtv, tv, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        add_entries_kernel<<<(nnz + 255) / 256, 256, 0, st>>>(dK, ldk, nnz, dti, dtj, dtv);
+        MBRF_LAUNCH_CHECK();
+    }
     col_norm2_kernel<<<ldk / 32, dim3(32, 8), 0, st>>>(dK, Mp, ldk, dcs);
     MBRF_LAUNCH_CHECK();
     std::vector<double> cs((size_t)Np), inv((size_t)Np);
@@ -172,6 +199,16 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const i
         if (i < 0 || i >= N || j < 0 || j >= N) { set_error("fir_pdhg_solve: pair %d out of range", q); return MBRF_EINVAL; }
         const double pm = sqrt(0.5 * (cs[i] * cs[i] + cs[j] * cs[j]));
         cs[i] = cs[j] = pm;
+    }
+    mbrf_pdhg_blocks bk;
+    memset(&bk, 0, sizeof bk);
+    if (blocks) bk = *blocks;
+    if (bk.norm_coords > 0) {           // a ball must stay a ball: the norm-term coordinates share one scale
+        if (bk.norm_coords > N || npairs > 0) { set_error("fir_pdhg_solve: norm term excludes pairs and needs norm_coords <= N"); return MBRF_EINVAL; }
+        double m2 = 0.0;
+        for (int j = 0; j < bk.norm_coords; ++j) m2 += cs[j] * cs[j];
+        const double sm = sqrt(m2 / bk.norm_coords);
+        for (int j = 0; j < bk.norm_coords; ++j) cs[j] = sm;
     }
     for (int j = 0; j < Np; ++j) inv[j] = 1.0 / cs[j];
     MBRF_CUDA(cudaMemcpyAsync(dcs, inv.data(), (size_t)Np * 8, cudaMemcpyHostToDevice, st));
@@ -223,18 +260,35 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const i
         MBRF_CUDA(cudaStreamSynchronize(st));
     }
 
-    if (simplex_rows > 0) {
+    auto upload_w = [&](const double *src, double *dst, double scale) -> int {
         h.assign((size_t)Bp, 0.0);
-        for (int b = 0; b < B; ++b) h[b] = simplex_w[b];
-        MBRF_CUDA(cudaMemcpyAsync(dsw, h.data(), (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
+        for (int b = 0; b < B; ++b) h[b] = src[b] * scale;
+        MBRF_CUDA(cudaMemcpyAsync(dst, h.data(), (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
         MBRF_CUDA(cudaStreamSynchronize(st));
+        return MBRF_OK;
+    };
+    mbrf_pdhg_blocks dbk = bk;
+    if (bk.simplex_rows > 0) {
+        if (!bk.simplex_w || bk.simplex_row0 < 0 || bk.simplex_row0 + bk.simplex_rows > M) { set_error("fir_pdhg_solve: bad simplex block"); return MBRF_EINVAL; }
+        if (int rc = upload_w(bk.simplex_w, dsw, 1.0)) return rc;
+        dbk.simplex_w = dsw;
+    }
+    if (bk.group_pairs > 0) {
+        if (!bk.group_w || bk.group_row0 < 0 || bk.group_row0 + 2 * bk.group_pairs > M) { set_error("fir_pdhg_solve: bad group block"); return MBRF_EINVAL; }
+        if (int rc = upload_w(bk.group_w, dgw, 1.0)) return rc;
+        dbk.group_w = dgw;
+    }
+    if (bk.disk_pairs > 0 && (bk.disk_row0 < 0 || bk.disk_row0 + 2 * bk.disk_pairs > M)) { set_error("fir_pdhg_solve: bad disk block"); return MBRF_EINVAL; }
+    if (bk.norm_coords > 0) {
+        if (!bk.norm_w) { set_error("fir_pdhg_solve: norm_w missing"); return MBRF_EINVAL; }
+        if (int rc = upload_w(bk.norm_w, dlam, 1.0 / cs[0])) return rc;     // ||x|| = ||z|| / scale
+        dbk.norm_w = dlam;
     }
 
     int rc = mbrf_pdhg_solve_device(dK, dKT, Mp, Np, ldk, dc, dlo, dhi, dbl, dbu, npairs ? dpi : nullptr,
                                     npairs ? dpj : nullptr, npairs, npairs ? drho : nullptr, Bp, B,
-                                    obj_upper ? dupper : nullptr, simplex_row0, simplex_rows,
-                                    simplex_rows > 0 ? dsw : nullptr, max_iter, check_every, eps_pr, eps_dr, eps_gap, dz,
-                                    nullptr, dinfo, dws, st);
+                                    obj_upper ? dupper : nullptr, &dbk, max_iter, check_every, eps_pr, eps_dr, eps_gap,
+                                    dz, nullptr, dinfo, dws, st);
     if (rc) return rc;
     h.assign(zn, 0.0);
     std::vector<double> info((size_t)Bp * 8);
@@ -245,6 +299,38 @@ int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const i
         for (int b = 0; b < B; ++b) z_out[(size_t)j * B + b] = h[(size_t)j * Bp + b] / cs[j];
     memcpy(info_out, info.data(), (size_t)B * 64);
     return MBRF_OK;
+}
+
+extern "C" int mbrf_fir_pdhg_solve2(const double *w_row, const double *row_phase, const double *row_scale, int M,
+                                    const int *col_type, const double *col_kappa, const double *col_amp, int N, int nnz,
+                                    const int *ti, const int *tj, const double *tv, const int *pair_i,
+                                    const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
+                                    const double *bl, const double *bu, const double *rho, int B,
+                                    const double *obj_upper, const mbrf_pdhg_blocks *blocks, int max_iter,
+                                    int check_every, double eps_pr, double eps_dr, double eps_gap, double *z_out,
+                                    double *info_out, double *colscale_out)
+{
+    return solve_impl(w_row, row_phase, row_scale, nullptr, M, col_type, col_kappa, col_amp, N, -1, nnz, ti, tj, tv, pair_i,
+                      pair_j, npairs, c, lo, hi, bl, bu, rho, B, obj_upper, blocks, max_iter, check_every, eps_pr, eps_dr,
+                      eps_gap, z_out, info_out, colscale_out);
+}
+
+extern "C" int mbrf_fir_pdhg_solve(const double *w_row, const double *tcoef, int M, const int *col_type,
+                                   const double *col_kappa, const double *col_amp, int N, int tcol, const int *pair_i,
+                                   const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
+                                   const double *bl, const double *bu, const double *rho, int B,
+                                   const double *obj_upper, int simplex_row0, int simplex_rows,
+                                   const double *simplex_w, int max_iter, int check_every, double eps_pr, double eps_dr,
+                                   double eps_gap, double *z_out, double *info_out, double *colscale_out)
+{
+    mbrf_pdhg_blocks bk;
+    memset(&bk, 0, sizeof bk);
+    bk.simplex_row0 = simplex_row0;
+    bk.simplex_rows = simplex_rows;
+    bk.simplex_w = const_cast<double *>(simplex_w);
+    return solve_impl(w_row, nullptr, nullptr, tcoef, M, col_type, col_kappa, col_amp, N, tcol, 0, nullptr, nullptr, nullptr,
+                      pair_i, pair_j, npairs, c, lo, hi, bl, bu, rho, B, obj_upper, &bk, max_iter, check_every, eps_pr, eps_dr,
+                      eps_gap, z_out, info_out, colscale_out);
 }
 
 }  // extern "C"

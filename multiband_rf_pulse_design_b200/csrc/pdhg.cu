@@ -220,6 +220,56 @@ dgemm_mma_kernel(const double *__restrict__ AT, int ldat, const double *__restri
 }
 
 // ---------------------------------------------------------------------------
+// Single design (Bp == 1): the two products are matrix-vector products, bound by streaming the 32 MB matrix
+// from L2/HBM.  One warp per output element's row of the k-major operand (K for K z, K^T for K^T y), 16-byte
+// coalesced loads, the vector kept in shared memory, warp-shuffle reduction.
+//   out[r] = sum_k A[r][k] * x[k]      A row-major [R x ld], kdim multiple of 64
+// ---------------------------------------------------------------------------
+// RPC rows per CTA of 256 threads: 8/RPC warps share a row (k split between them, partials summed through shared
+// memory).  STAGE: copy x into shared memory first (worth it when RPC rows reuse a short x).
+template <int RPC, bool STAGE>
+__global__ void __launch_bounds__(256)
+dgemv_rows_kernel(const double *__restrict__ A, int ld, int R, int kdim, const double *__restrict__ x,
+                  double *__restrict__ out)
+{
+    extern __shared__ double xs[];
+    __shared__ double part[8];
+    if (STAGE) {
+        for (int k = threadIdx.x; k < kdim; k += blockDim.x) xs[k] = x[k];
+        __syncthreads();
+    }
+    constexpr int WPR = 8 / RPC;                       // warps per row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * RPC + warp / WPR, sub = warp % WPR;
+    double acc = 0.0;
+    if (r < R) {
+        const double2 *row = reinterpret_cast<const double2 *>(A + (size_t)r * ld);
+        const double2 *xv = reinterpret_cast<const double2 *>(STAGE ? xs : x);
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int k2 = sub * 32 + lane; k2 < kdim / 2; k2 += 32 * WPR) {
+            const double2 a = row[k2], b = xv[k2];
+            acc0 = fma(a.x, b.x, acc0);
+            acc1 = fma(a.y, b.y, acc1);
+        }
+        acc = acc0 + acc1;
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
+    }
+    if (WPR == 1) {
+        if (lane == 0 && r < R) out[r] = acc;
+    } else {
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x < RPC && blockIdx.x * RPC + threadIdx.x < R) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < WPR; ++q) t += part[threadIdx.x * WPR + q];
+            out[blockIdx.x * RPC + threadIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // solver state
 // ---------------------------------------------------------------------------
 struct Ctl {           // per-design control block (device), doubles for simplicity
@@ -242,6 +292,13 @@ struct Problem {
     double *obj_upper;                          // [Bp] or null
     int srow0, ns;                              // simplex block: rows [srow0, srow0+ns) carry  w_b * max_i (K z)_i
     double *sw;                                 // [Bp] weights w_b of that block (null when ns == 0)
+    int drow0, nd;                              // disk block: row pairs (drow0+2i, drow0+2i+1): ||K z - centre|| <= R,
+                                                //   centre in lo[pair], R in hi[first row]          (fir_qp_cvx.m:148-157)
+    int grow0, ng;                              // group block: row pairs carry  gw_b * max_i ||(K z)_pair_i||  (obj*Peak,
+    double *gw;                                 //   fir_qp_cvx.m:147,158-160); multipliers live in the l1,2 ball of radius gw_b
+    int nn;                                     // norm term: lam_b * ||z[0..nn)||_2 in the objective (E_total, :147,161)
+    double *lam;                                // [Bp]
+    double *nrm;                                // [4 x Bp] scratch: ||zhat||^2 per design (z-update), metrics sums
     double *z, *zbar, *zs, *z0, *zbest;         // [Np x Bp]
     double *y, *ys, *y0, *ybest;                // [Mp x Bp]
     double *S;                                  // [Mp x Bp]   K*zbar, K*z, K*zs
@@ -254,12 +311,47 @@ struct Problem {
     int check_every;
 };
 
-enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, NACC };
+enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, A_GMAX, A_ZZ, A_ZV, A_VV, NACC };
 
 __device__ __forceinline__ void atomic_max_pos(double *addr, double v)
 {
     if (!(v > 0.0)) return;
     atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// Norm term (fir_qp_cvx.m: E_total with norm(x,2) <= E_total): the primal prox is the block soft-threshold
+//   z+ = max(0, 1 - tau*lam/||zhat||) * zhat,   zhat = z - tau*(c + K^T y)
+// phase 1 stores zhat in zbar and accumulates ||zhat||^2 per design; phase 2 applies the shrink.
+__global__ void z_hat_kernel(Problem p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.Bp) return;
+    const double tau = p.ctl[b].tau;
+    const size_t stride = (size_t)p.Np * p.Bp;
+    double s2 = 0.0;
+    for (int j = blockIdx.y; j < p.Np; j += gridDim.y) {
+        const size_t o = (size_t)j * p.Bp + b;
+        double g = p.c[o];
+        for (int s = 0; s < p.P; ++s) g += p.G[s * stride + o];
+        double zh = p.z[o] - tau * g;
+        zh = fmin(fmax(zh, p.bl[o]), p.bu[o]);
+        p.zbar[o] = zh;
+        if (j < p.nn) s2 = fma(zh, zh, s2);
+    }
+    atomicAdd(p.nrm + b, s2);
+}
+__global__ void z_shrink_kernel(Problem p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.Np * p.Bp) return;
+    const int b = (int)(idx % p.Bp);
+    const int j = (int)(idx / p.Bp);
+    const double nv = sqrt(p.nrm[b]);
+    const double sh = (j < p.nn && nv > 0.0) ? fmax(0.0, 1.0 - p.ctl[b].tau * p.lam[b] / nv) : 1.0;
+    const double zo = p.z[idx], zn = sh * p.zbar[idx];
+    p.z[idx] = zn;
+    p.zbar[idx] = 2.0 * zn - zo;
+    p.zs[idx] += zn;
 }
 
 // z+ = P_X(z - tau (c + sum_p G_p)), zbar = 2 z+ - z, zs += z+.   One thread per (coordinate, design);
@@ -312,7 +404,25 @@ __global__ void y_update_kernel(Problem p)
     const int b = (int)(idx % p.Bp);
     const int row = (int)(idx / p.Bp);
     if (row >= p.srow0 && row < p.srow0 + p.ns) return;   // simplex block: simplex_update_kernel
+    if (row >= p.grow0 && row < p.grow0 + 2 * p.ng) return;   // group block: group_update_kernel
     const double sig = p.ctl[b].sigma;
+    if (row >= p.drow0 && row < p.drow0 + 2 * p.nd) {     // disk pair: y+ = v - sigma * P_disk(v / sigma)
+        if ((row - p.drow0) & 1) return;                  // the first row of the pair does both
+        const long long i2 = idx + p.Bp;
+        const double v1 = p.y[idx] + sig * p.S[idx], v2 = p.y[i2] + sig * p.S[i2];
+        const double c1 = p.lo[idx], c2 = p.lo[i2], R = p.hi[idx];
+        const double d1 = v1 / sig - c1, d2 = v2 / sig - c2;
+        const double dn = hypot(d1, d2);
+        double y1 = 0.0, y2 = 0.0;
+        if (dn > R) {                                     // outside: P = c + R d/|d|  ->  y = sigma (d - R d/|d|)
+            const double f = sig * (1.0 - R / dn);
+            y1 = f * d1;
+            y2 = f * d2;
+        }
+        p.y[idx] = y1; p.y[i2] = y2;
+        p.ys[idx] += y1; p.ys[i2] += y2;
+        return;
+    }
     const double v = p.y[idx] + sig * p.S[idx];
     const double w = v / sig, lo = p.lo[idx], hi = p.hi[idx];
     // exact zero inside the interval: v - sig*(v/sig) would leave rounding dust that h*(y) multiplies by +-inf
@@ -375,6 +485,58 @@ __global__ void simplex_update_kernel(Problem p)
     }
 }
 
+// Group block: the objective term  gw * max_i ||(K z)_pair_i||  (obj*Peak with ||(x_i, x_{n+i})|| <= Peak,
+// fir_qp_cvx.m:147,158-160) has as conjugate the indicator of the l1,2 ball {sum_i ||u_i|| <= gw}: the dual step
+// is the projection of v = y + sigma K zbar onto that ball (Michelot on the pair norms).  One warp per design.
+__global__ void group_update_kernel(Problem p)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= p.Bp) return;
+    const double sig = p.ctl[b].sigma, w = p.gw[b];
+    double sum = 0.0;
+    for (int i = lane; i < p.ng; i += 32) {
+        const size_t o = (size_t)(p.grow0 + 2 * i) * p.Bp + b;
+        const double v1 = p.y[o] + sig * p.S[o], v2 = p.y[o + p.Bp] + sig * p.S[o + p.Bp];
+        p.y[o] = v1; p.y[o + p.Bp] = v2;      // stage v in place
+        sum += hypot(v1, v2);
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+    double theta = 0.0;
+    if (sum > w) {                           // outside the ball: threshold the norms
+        int prev = p.ng;
+        theta = (sum - w) / p.ng;
+        for (int pass = 0; pass < 64; ++pass) {
+            double s2 = 0.0;
+            int c2 = 0;
+            for (int i = lane; i < p.ng; i += 32) {
+                const size_t o = (size_t)(p.grow0 + 2 * i) * p.Bp + b;
+                const double r = hypot(p.y[o], p.y[o + p.Bp]);
+                if (r > theta) { s2 += r; ++c2; }
+            }
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, k); c2 += __shfl_xor_sync(0xffffffffu, c2, k); }
+            if (c2 == 0) break;
+            theta = (s2 - w) / c2;
+            if (c2 == prev) break;
+            prev = c2;
+        }
+    }
+    for (int i = lane; i < p.ng; i += 32) {
+        const size_t o = (size_t)(p.grow0 + 2 * i) * p.Bp + b;
+        double v1 = p.y[o], v2 = p.y[o + p.Bp];
+        if (theta > 0.0) {
+            const double r = hypot(v1, v2);
+            const double f = r > theta ? (r - theta) / r : 0.0;
+            v1 *= f; v2 *= f;
+        }
+        if (!(w > 0.0)) { v1 = 0.0; v2 = 0.0; }
+        p.y[o] = v1; p.y[o + p.Bp] = v2;
+        p.ys[o] += v1; p.ys[o + p.Bp] += v2;
+    }
+}
+
 // reduce split-K slabs: G2 = sum_p G_p
 __global__ void reduce_slabs_kernel(Problem p)
 {
@@ -394,10 +556,27 @@ __global__ void row_metrics_kernel(Problem p, int cand)
     if (b >= p.Bp) return;
     const double inv = cand == 0 ? 1.0 / fmax(p.ctl[b].cnt, 1.0) : 1.0;
     const double *yv = cand == 0 ? p.ys : p.y;
-    double pr = 0.0, hs = 0.0, dy2 = 0.0, tmax = 0.0;
+    double pr = 0.0, hs = 0.0, dy2 = 0.0, tmax = 0.0, gmax = 0.0;
     for (int i = blockIdx.y; i < p.Mp; i += gridDim.y) {
         const size_t o = (size_t)i * p.Bp + b;
         const double kz = p.S[o] * inv, y = yv[o] * inv, lo = p.lo[o], hi = p.hi[o];
+        if (i >= p.drow0 && i < p.drow0 + 2 * p.nd) {  // disk pair (first row does both): violation, support function
+            const double d = y - p.y0[o];
+            dy2 = fma(d, d, dy2);
+            if (((i - p.drow0) & 1) == 0) {
+                const size_t o2 = o + p.Bp;
+                const double kz2 = p.S[o2] * inv, y2 = yv[o2] * inv, c1 = lo, c2 = p.lo[o2], R = hi;
+                pr = fmax(pr, hypot(kz - c1, kz2 - c2) - R);
+                hs += c1 * y + c2 * y2 + R * hypot(y, y2);
+            }
+            continue;
+        }
+        if (i >= p.grow0 && i < p.grow0 + 2 * p.ng) {  // group block: h* = 0, track max pair norm of K z
+            const double d = y - p.y0[o];
+            dy2 = fma(d, d, dy2);
+            if (((i - p.grow0) & 1) == 0) gmax = fmax(gmax, hypot(kz, p.S[o + p.Bp] * inv));
+            continue;
+        }
         if (i >= p.srow0 && i < p.srow0 + p.ns) {      // simplex block: no constraint of its own, h* = 0
             if (hi == 0.0) tmax = fmax(tmax, kz);
             const double d = y - p.y0[o];
@@ -413,6 +592,7 @@ __global__ void row_metrics_kernel(Problem p, int cand)
     double *acc = p.acc + (size_t)cand * NACC * p.Bp;
     atomic_max_pos(acc + A_PR * p.Bp + b, pr);
     atomic_max_pos(acc + A_TMAX * p.Bp + b, tmax);
+    atomic_max_pos(acc + A_GMAX * p.Bp + b, gmax);
     atomicAdd(acc + A_HS * p.Bp + b, hs);
     atomicAdd(acc + A_DY2 * p.Bp + b, dy2);
 }
@@ -425,13 +605,20 @@ __global__ void col_metrics_kernel(Problem p, int cand)
     if (b >= p.Bp) return;
     const double inv = cand == 0 ? 1.0 / fmax(p.ctl[b].cnt, 1.0) : 1.0;
     const double *zv = cand == 0 ? p.zs : p.z;
-    double pobj = 0.0, gz = 0.0, dr = 0.0, dz2 = 0.0, rigx = 0.0;
+    double pobj = 0.0, gz = 0.0, dr = 0.0, dz2 = 0.0, rigx = 0.0, s_zz = 0.0, s_zv = 0.0, s_vv = 0.0;
     for (int j = blockIdx.y; j < p.Np; j += gridDim.y) {
         const int pr = p.pair_of[j];
         if (pr >= 0 && p.pair_j[pr] == j) continue;
         const size_t o = (size_t)j * p.Bp + b;
         const double z = zv[o] * inv, c = p.c[o], g = c + p.G2[o] * inv;
-        if (pr < 0) {
+        if (pr < 0 && j < p.nn) {   // norm-term coordinate: residual needs ||z - g|| first; collect the three inner products
+            s_zz = fma(z, z, s_zz); s_zv = fma(z, z - g, s_zv); s_vv = fma(z - g, z - g, s_vv);
+            pobj = fma(c, z, pobj);
+            gz = fma(g, z, gz);
+            const double d = z - p.z0[o];
+            dz2 = fma(d, d, dz2);
+            rigx += g > 0.0 ? g * p.bl[o] : (g < 0.0 ? g * p.bu[o] : 0.0);
+        } else if (pr < 0) {
             const double bl = p.bl[o], bu = p.bu[o];
             const double t = fmin(fmax(z - g, bl), bu);
             dr = fmax(dr, fabs(z - t));
@@ -460,6 +647,11 @@ __global__ void col_metrics_kernel(Problem p, int cand)
     atomicAdd(acc + A_GZ * p.Bp + b, gz);
     atomicAdd(acc + A_DZ2 * p.Bp + b, dz2);
     atomicAdd(acc + A_RIGX * p.Bp + b, rigx);
+    if (p.nn > 0) {
+        atomicAdd(acc + A_ZZ * p.Bp + b, s_zz);
+        atomicAdd(acc + A_ZV * p.Bp + b, s_zv);
+        atomicAdd(acc + A_VV * p.Bp + b, s_vv);
+    }
 }
 
 // Advance the per-design counters by one block of iterations (before the metrics use cnt).
@@ -485,8 +677,16 @@ __global__ void control_kernel(Problem p, int iter_now, int max_iter)
         pr[k] = a[A_PR * p.Bp + b];
         dr[k] = a[A_DR * p.Bp + b];
         tm[k] = a[A_TMAX * p.Bp + b];
-        po[k] = a[A_POBJ * p.Bp + b] + (p.ns > 0 ? p.sw[b] * tm[k] : 0.0);
+        po[k] = a[A_POBJ * p.Bp + b] + (p.ns > 0 ? p.sw[b] * tm[k] : 0.0) + (p.ng > 0 ? p.gw[b] * a[A_GMAX * p.Bp + b] : 0.0);
         du[k] = -a[A_HS * p.Bp + b] + a[A_GZ * p.Bp + b];
+        if (p.nn > 0) {            // norm term: lam*||z|| in both, residual ||z - shrink(z - g)||_2 from the inner products
+            const double zz = a[A_ZZ * p.Bp + b], zv = a[A_ZV * p.Bp + b], vv = a[A_VV * p.Bp + b], lam = p.lam[b];
+            const double nz = sqrt(fmax(zz, 0.0)), nv = sqrt(fmax(vv, 0.0));
+            const double sh = nv > 0.0 ? fmax(0.0, 1.0 - lam / nv) : 1.0;
+            po[k] += lam * nz;
+            du[k] += lam * nz;
+            dr[k] = fmax(a[A_DR * p.Bp + b], sqrt(fmax(zz - 2.0 * sh * zv + sh * sh * vv, 0.0)));
+        }
         rig[k] = -a[A_HS * p.Bp + b] + a[A_RIGX * p.Bp + b];
         dz[k] = sqrt(a[A_DZ2 * p.Bp + b]);
         dy[k] = sqrt(a[A_DY2 * p.Bp + b]);
@@ -496,7 +696,8 @@ __global__ void control_kernel(Problem p, int iter_now, int max_iter)
     const int k = err[0] < err[1] ? 0 : 1;
     c.use_avg = k == 0 ? 1.0 : 0.0;
     if (c.status == 0.0) {
-        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = fmax(rig[0], rig[1]); c.tmax = tm[k];
+        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = p.nn > 0 ? -DBL_MAX : fmax(rig[0], rig[1]);
+        c.tmax = p.ng > 0 ? p.acc[(size_t)k * NACC * p.Bp + A_GMAX * p.Bp + b] : tm[k];
         const bool solved = pr[k] <= p.eps_pr && dr[k] <= p.eps_dr &&
                             fabs(po[k] - du[k]) <= p.eps_gap * fmax(fabs(po[k]), 1e-12);
         const bool infeasible = !solved && p.obj_upper && c.rigorous > p.obj_upper[b];
@@ -596,6 +797,11 @@ static int g_use_dmma = 1;   // 1: mma.sync m8n8k4 f64 tiles, 0: SIMT DFMA tiles
 
 static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st)   // C[Mp x Bp] = K X
 {
+    if (p.Bp == 1) {   // K z: rows of K (row-major [Mp x ldk]) against z
+        dgemv_rows_kernel<8, true><<<(p.Mp + 7) / 8, 256, (size_t)p.Np * 8, st>>>(p.K, p.ldk, p.Mp, p.Np, X, C);
+        MBRF_LAUNCH_CHECK();
+        return MBRF_OK;
+    }
     dim3 grid(p.Bp / BN, p.Mp / BM, 1);
     if (g_use_dmma) dgemm_mma_kernel<<<grid, 128, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
     else dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
@@ -604,6 +810,11 @@ static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st
 }
 static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st)   // G[P][Np x Bp] = K^T Y
 {
+    if (p.Bp == 1) {   // K^T y: rows of K^T (row-major [Np x Mp]) against y; P == 1, slab 0
+        dgemv_rows_kernel<1, false><<<p.Np, 256, 0, st>>>(p.KT, p.Mp, p.Np, p.Mp, Y, G);
+        MBRF_LAUNCH_CHECK();
+        return MBRF_OK;
+    }
     const int kchunk = up((p.Mp + p.P - 1) / p.P, BK);
     dim3 grid(p.Bp / BN, p.Np / BM, p.P);
     if (g_use_dmma) dgemm_mma_kernel<<<grid, 128, 0, st>>>(p.K, p.ldk, Y, p.Bp, G, p.Mp, kchunk, (long long)p.Np * p.Bp);
@@ -633,12 +844,13 @@ int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp)
     if (M <= 0 || N <= 0 || B <= 0 || !Mp || !Np || !Bp) return MBRF_EINVAL;
     *Mp = up(M, 64);
     *Np = up(N, 64);
-    *Bp = up(B, 64);
+    *Bp = B == 1 ? 1 : up(B, 64);
     return MBRF_OK;
 }
 
 static int split_k(int Mp, int Np, int Bp)
 {
+    if (Bp == 1) return 1;
     // K^T Y has only (Np/64)*(Bp/64) output tiles: split the long reduction so that ~6 CTAs land on each SM
     const int tiles = (Np / BM) * (Bp / BN);
     int P = (6 * 148 + tiles - 1) / tiles;
@@ -651,7 +863,7 @@ static int split_k(int Mp, int Np, int Bp)
 // doubles needed for the split-K slabs at any batch width the compaction can reach
 static size_t slab_doubles(int Mp, int Np, int Bp)
 {
-    size_t mx = 0;
+    size_t mx = (size_t)Np;
     for (int b = 64; b <= Bp; b += 64) {
         const size_t v = (size_t)split_k(Mp, Np, b) * Np * b;
         if (v > mx) mx = v;
@@ -662,7 +874,7 @@ static size_t slab_doubles(int Mp, int Np, int Bp)
 unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp)
 {
     const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
-    size_t d = 5 * zn + 4 * yn + yn + slab_doubles(Mp, Np, Bp) + zn + 2 * NACC * (size_t)Bp;
+    size_t d = 5 * zn + 4 * yn + yn + slab_doubles(Mp, Np, Bp) + zn + 2 * NACC * (size_t)Bp + 4 * (size_t)Bp;
     return d * 8 + (size_t)Bp * sizeof(Ctl) + 256 + (size_t)Np * 4 + 2 * (size_t)Bp * 4 + 128;
 }
 
@@ -674,16 +886,25 @@ unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp)
 int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, double *c, double *lo,
                            double *hi, double *bl, double *bu, const int *pair_i,
                            const int *pair_j, int npairs, double *rho, int Bp, int B,
-                           double *obj_upper, int srow0, int ns, double *simplex_w, int max_iter, int check_every,
+                           double *obj_upper, const mbrf_pdhg_blocks *blocks, int max_iter, int check_every,
                            double eps_pr, double eps_dr, double eps_gap, double *z_out, double *y_out,
                            double *info_out, void *workspace, void *stream)
 {
     if (int rc = require_device()) return rc;
-    if (ns < 0 || (ns > 0 && (!simplex_w || srow0 < 0 || srow0 + ns > Mp))) {
-        set_error("pdhg: bad simplex block srow0=%d ns=%d", srow0, ns);
+    mbrf_pdhg_blocks bk;
+    memset(&bk, 0, sizeof bk);
+    if (blocks) bk = *blocks;
+    const int srow0 = bk.simplex_row0, ns = bk.simplex_rows;
+    double *simplex_w = bk.simplex_w;
+    if (ns < 0 || (ns > 0 && (!simplex_w || srow0 < 0 || srow0 + ns > Mp)) || bk.disk_pairs < 0 ||
+        (bk.disk_pairs > 0 && (bk.disk_row0 < 0 || bk.disk_row0 + 2 * bk.disk_pairs > Mp)) || bk.group_pairs < 0 ||
+        (bk.group_pairs > 0 && (!bk.group_w || bk.group_row0 < 0 || bk.group_row0 + 2 * bk.group_pairs > Mp)) ||
+        bk.norm_coords < 0 || bk.norm_coords > Np || (bk.norm_coords > 0 && (!bk.norm_w || npairs > 0))) {
+        set_error("pdhg: bad row/column blocks (simplex %d+%d, disks %d+2*%d, groups %d+2*%d, norm %d)", srow0, ns,
+                  bk.disk_row0, bk.disk_pairs, bk.group_row0, bk.group_pairs, bk.norm_coords);
         return MBRF_EINVAL;
     }
-    if (Mp % 64 || Np % 64 || Bp % 64 || B < 1 || B > Bp || ldk < Np || ldk % 2 ||
+    if (Mp % 64 || Np % 64 || (Bp % 64 && Bp != 1) || B < 1 || B > Bp || ldk < Np || ldk % 2 ||
         max_iter < 1 || check_every < 1 || npairs < 0) {
         set_error("pdhg: bad padded sizes Mp=%d Np=%d Bp=%d B=%d ldk=%d", Mp, Np, Bp, B, ldk);
         return MBRF_EINVAL;
@@ -698,6 +919,9 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     p.c = c; p.lo = lo; p.hi = hi; p.bl = bl; p.bu = bu; p.rho = rho; p.pair_i = pair_i; p.pair_j = pair_j;
     p.obj_upper = obj_upper; p.P = split_k(Mp, Np, Bp);
     p.srow0 = ns > 0 ? srow0 : 0; p.ns = ns; p.sw = ns > 0 ? simplex_w : nullptr;
+    p.drow0 = bk.disk_pairs > 0 ? bk.disk_row0 : 0; p.nd = bk.disk_pairs;
+    p.grow0 = bk.group_pairs > 0 ? bk.group_row0 : 0; p.ng = bk.group_pairs; p.gw = bk.group_pairs > 0 ? bk.group_w : nullptr;
+    p.nn = bk.norm_coords; p.lam = bk.norm_coords > 0 ? bk.norm_w : nullptr;
     p.eps_pr = eps_pr; p.eps_dr = eps_dr; p.eps_gap = eps_gap; p.check_every = check_every;
     const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
     double *w = (double *)workspace;
@@ -707,6 +931,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     p.G = w; w += slab_doubles(Mp, Np, Bp);
     p.G2 = w; w += zn;
     p.acc = w; w += 2 * NACC * (size_t)Bp;
+    p.nrm = w; w += 4 * (size_t)Bp;
     p.ctl = (Ctl *)w; w = (double *)((char *)w + (size_t)Bp * sizeof(Ctl));
     p.active = (int *)w; w += 32;
     int *pair_of = (int *)w;
@@ -785,13 +1010,25 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
 
     auto iteration = [&]() -> int {
         if (int rc = gemm_tn(p, p.y, p.G, st)) return rc;
-        z_update_kernel<<<gz, TPB, 0, st>>>(p);
-        MBRF_LAUNCH_CHECK();
+        if (p.nn > 0) {
+            MBRF_CUDA(cudaMemsetAsync(p.nrm, 0, (size_t)p.Bp * 8, st));
+            z_hat_kernel<<<dim3((p.Bp + 63) / 64, 16), 64, 0, st>>>(p);
+            MBRF_LAUNCH_CHECK();
+            z_shrink_kernel<<<gz, TPB, 0, st>>>(p);
+            MBRF_LAUNCH_CHECK();
+        } else {
+            z_update_kernel<<<gz, TPB, 0, st>>>(p);
+            MBRF_LAUNCH_CHECK();
+        }
         if (int rc = gemm_nn(p, p.zbar, p.S, st)) return rc;
         y_update_kernel<<<gy, TPB, 0, st>>>(p);
         MBRF_LAUNCH_CHECK();
         if (p.ns > 0) {
             simplex_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
+            MBRF_LAUNCH_CHECK();
+        }
+        if (p.ng > 0) {
+            group_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
         }
         return MBRF_OK;
@@ -890,6 +1127,8 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         if (int rc = regather(p.rho, p.npairs, p.G2, 0.0)) return rc;
         if (int rc = regather(p.obj_upper, 1, p.G2, INFINITY)) return rc;
         if (int rc = regather(p.sw, 1, p.G2, 0.0)) return rc;
+        if (int rc = regather(p.gw, 1, p.G2, 0.0)) return rc;
+        if (int rc = regather(p.lam, 1, p.G2, 0.0)) return rc;
         double *mside[] = {p.y, p.ys, p.y0, p.ybest};
         for (double *a : mside)
             if (int rc = regather(a, p.Mp, p.S, 0.0)) return rc;
@@ -919,7 +1158,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     for (int it = 0; it < max_iter && active > 0 && rcode == MBRF_OK;) {
         if (use_graph) {
             if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("pdhg: graph launch failed"); rcode = MBRF_ECUDA; break; }
-            g_launches.fetch_add((p.ns > 0 ? 5ull : 4ull) * check_every, std::memory_order_relaxed);
+            g_launches.fetch_add((4ull + (p.ns > 0) + (p.ng > 0) + (p.nn > 0)) * check_every, std::memory_order_relaxed);
         } else {
             for (int i = 0; i < check_every && rcode == MBRF_OK; ++i) rcode = iteration();
         }

@@ -20,7 +20,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import c_double_p, check, lib
+from ._lib import PdhgBlocks, c_double_p, check, lib
 
 c_int_p = C.POINTER(C.c_int)
 
@@ -314,19 +314,20 @@ def sweep_grid(f, objs, peaks, f_adds):
 
 
 def fir_ap_cvx_sweep(n, f, a, d, objs, peaks, f_adds, rank=0, world=1, batch=512, **solver_kw):
-    """Solve this rank's share of the sweep grid (contiguous block of design instances) in
-    batches of at most `batch` designs.  Returns dict(index, x, ripple_stop, info) for the local designs."""
-    from .shard import shard_bounds
+    """Solve this rank's share of the sweep grid in batches of at most `batch` designs.  Design instance i goes
+    to rank i mod world: neighbouring instances differ in one parameter and cost about the same, so
+    the interleaving balances the ranks; nothing is exchanged until the caller gathers the results.
+    Returns dict(index, x, ripple_stop, info) for the local designs."""
     fl, ol, pl = sweep_grid(f, objs, peaks, f_adds)
-    s0, cnt = shard_bounds(len(fl), world)[rank]
+    mine = np.arange(rank, len(fl), world)
     xs, ts, infos = [], [], []
-    for b0 in range(s0, s0 + cnt, batch):
-        b1 = min(s0 + cnt, b0 + batch)
-        designs = [assemble_fir_ap(n, fl[i], a, d, ol[i], pl[i]) for i in range(b0, b1)]
+    for b0 in range(0, mine.size, batch):
+        ids = mine[b0:b0 + batch]
+        designs = [assemble_fir_ap(n, fl[i], a, d, ol[i], pl[i]) for i in ids]
         x, t, info = _solve_batch_ap(n, designs, **solver_kw)
         xs.append(x); ts.append(t); infos.append(info)
     cat = lambda v, w: np.concatenate(v) if v else np.zeros((0, w))   # noqa: E731
-    return dict(index=np.arange(s0, s0 + cnt), x=cat(xs, 2 * n - 1), ripple_stop=np.concatenate(ts) if ts else np.zeros(0),
+    return dict(index=mine, x=cat(xs, 2 * n - 1), ripple_stop=np.concatenate(ts) if ts else np.zeros(0),
                 info=cat(infos, 8))
 
 
@@ -493,3 +494,94 @@ def fir_min_order(n, f, a, d, even_odd=0, a_min=None, dbg=0, **solver_kw):
     fir_pm's minimum-amplitude option and has no LP counterpart; it is accepted and ignored."""
     return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: fir_linprog(nt, f, a, d, hw, dbg, **solver_kw),
                              pick_longer=True)
+
+
+# --------------------------------------------------------------------------------------------
+# fir_qp_cvx.m — min-energy / min-peak FIR with quadratic phase target (SOCP)
+# --------------------------------------------------------------------------------------------
+def assemble_fir_qp(n, f, a, d, k=100.0, oversamp=10):
+    """fir_qp_cvx.m:34-121: grid, bands, desired response Hd, radii.  Rows ordered band then transition."""
+    f = np.asarray(f, float).ravel() * np.pi                              # :34
+    a = np.asarray(a, float).ravel()
+    d = np.asarray(d, float).ravel()
+    m = n * oversamp                                                      # :35-36
+    w = np.sort(np.concatenate([np.linspace(-np.pi, np.pi, m), f]))       # :37-38
+    nband = len(f) // 2
+    idx_band, M_band, D_band = [], [], []
+    for b in range(nband):                                                # :46-61
+        lo_, hi_ = f[2 * b], f[2 * b + 1]
+        idx = np.nonzero((w >= lo_) & (w <= hi_))[0]
+        idx_band.append(idx)
+        amp = np.full(idx.size, a[2 * b]) if lo_ == hi_ else \
+            a[2 * b] + (a[2 * b + 1] - a[2 * b]) * ((w[idx] - lo_) / (hi_ - lo_))
+        M_band.append(amp)
+        D_band.append(np.full(idx.size, d[b]))
+    idx_band = np.concatenate(idx_band)
+    M_band, D_band = np.concatenate(M_band), np.concatenate(D_band)
+    mask = np.ones(w.size, bool)
+    mask[idx_band] = False
+    wband, wtran = w[idx_band], w[mask]                                   # :75-76
+    Hd = M_band * np.exp(1j * (k * wband ** 2 - wband * (n - 1) / 2))     # :113-121
+    return dict(n=n, w=np.concatenate([wband, wtran]), center=np.concatenate([Hd, np.zeros(wtran.size, complex)]),
+                radius=np.concatenate([D_band, np.full(wtran.size, 1 + d.max() * 5)]), nband=wband.size)   # :151,156
+
+
+def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, **solver_kw):
+    """[h, status] = fir_qp_cvx(n, f, a, d, k, obj, dbg) — fir_qp_cvx.m:1-243, scalar `obj` form (:145-166):
+
+        minimise E_total + obj*Peak   s.t.  ||A_i x - Hd_i|| <= D_i  (bands),  ||A_i x|| <= 1+5 max(d)  (transitions),
+                                            ||(x_i, x_{n+i})|| <= Peak,  ||x|| <= E_total.
+
+    E_total and Peak are eliminated (E_total = ||x||, Peak = max_i ||(x_i, x_{n+i})|| at the optimum): the solver sees
+    the norm term, a group block over identity rows, and one disk per grid point — no epigraph variables.
+    The two-element `obj` form (:170-191, minimax with delta) is not implemented."""
+    if np.ndim(obj) != 0 and np.size(obj) != 1:
+        raise NotImplementedError("fir_qp_cvx with length(obj) == 2 (minimax form, fir_qp_cvx.m:170-191)")
+    n = int(n)
+    obj = float(np.ravel(obj)[0])
+    p = assemble_fir_qp(n, f, a, d, float(k))
+    m = p["w"].size
+    N, M = 2 * n, 2 * m + 2 * n
+    w_row = np.concatenate([np.repeat(p["w"], 2), np.zeros(2 * n)])
+    row_phase = np.concatenate([np.tile([0.0, np.pi / 2], m), np.zeros(2 * n)])   # [cos sin; -sin cos], :96-109
+    row_scale = np.concatenate([np.ones(2 * m), np.zeros(2 * n)])
+    kk = np.arange(n, dtype=float)
+    col_type = np.concatenate([np.full(n, 1), np.full(n, 2)]).astype(np.int32)
+    col_kappa = np.concatenate([kk, kk])
+    col_amp = np.ones(N)
+    ti = (2 * m + np.arange(2 * n)).astype(np.int32)                      # identity rows, pair i = (x_i, x_{n+i}), :126-139
+    tj = np.empty(2 * n, np.int32)
+    tj[0::2] = np.arange(n)
+    tj[1::2] = n + np.arange(n)
+    tv = np.ones(2 * n)
+    lo = np.full((M, 1), -np.inf)
+    hi = np.full((M, 1), np.inf)
+    lo[0:2 * m:2, 0] = p["center"].real
+    lo[1:2 * m:2, 0] = p["center"].imag
+    hi[0:2 * m:2, 0] = p["radius"]
+    big = 2.0 * p["radius"].max() + 2.0 * np.abs(p["center"]).max()
+    c = np.zeros((N, 1))
+    bl, bu = np.full((N, 1), -big), np.full((N, 1), big)
+    gw, lam = np.array([obj]), np.array([1.0])
+    blocks = PdhgBlocks()
+    blocks.disk_row0, blocks.disk_pairs = 0, m
+    blocks.group_row0, blocks.group_pairs, blocks.group_w = 2 * m, n, _dp(gw)
+    blocks.norm_coords, blocks.norm_w = N, _dp(lam)
+    kw = dict(max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR, eps_gap=EPS_GAP)
+    kw.update(solver_kw)
+    z, info = np.zeros((N, 1)), np.zeros((1, 8))
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.float64)            # noqa: E731
+    w_row, row_phase, row_scale, col_kappa, col_amp, tv, lo, hi = map(arr, (w_row, row_phase, row_scale, col_kappa,
+                                                                             col_amp, tv, lo, hi))
+    check(lib().mbrf_fir_pdhg_solve2(_dp(w_row), _dp(row_phase), _dp(row_scale), M, _ip(col_type), _dp(col_kappa),
+                                     _dp(col_amp), N, 2 * n, _ip(ti), _ip(tj), _dp(tv), None, None, 0, _dp(c), _dp(lo),
+                                     _dp(hi), _dp(bl), _dp(bu), None, 1, None, C.byref(blocks), int(kw["max_iter"]),
+                                     int(kw["check_every"]), float(kw["eps_pr"]), float(kw["eps_dr"]),
+                                     float(kw["eps_gap"]), _dp(z), _dp(info), None))
+    ok = info[0, 0] == 1.0
+    x = z[:, 0]
+    h = x[:n] + 1j * x[n:] if ok else np.zeros(0)                         # :209
+    st = "Solved" if ok else "Failed"                                     # :200-206
+    if return_info:
+        return h, st, dict(x=x.copy(), info=info[0].copy(), problem=p)
+    return h, st

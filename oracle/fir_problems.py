@@ -168,3 +168,81 @@ def solve_fir_lp_highs(p):
     A = p["A"]
     return linprog(p["c"], A_ub=np.vstack([A, -A]), b_ub=np.concatenate([p["hi"], -p["lo"]]),
                    bounds=[(None, None)] * A.shape[1], method="highs")
+
+
+# --------------------------------------------------------------------------------------------
+# fir_qp_cvx.m (variant with scalar obj, fir_qp_cvx.m:145-166)
+# --------------------------------------------------------------------------------------------
+def build_fir_qp(n, f, a, d, k=100.0, obj=0.0, oversamp=10):
+    """fir_qp_cvx.m:34-139.  Variables x = [Re h; Im h] (2n), E_total, Peak.
+       minimise E_total + obj*Peak
+       s.t. ||A_i x - Hd_i|| <= D_i (band), ||A_i x|| <= 1 + 5*max(d) (transition),
+            ||(x_i, x_{n+i})|| <= Peak, ||x|| <= E_total.
+    Returns dict(w (m,), center (m,) complex, radius (m,), nband, n, obj)."""
+    f = np.asarray(f, float) * np.pi                        # :34
+    a = np.asarray(a, float); d = np.asarray(d, float)
+    m = n * oversamp                                        # :35-36
+    w = np.sort(np.concatenate([np.linspace(-np.pi, np.pi, m), f]))   # :37-38
+    idx_band, idx_tran, U, L, M, D = _bands(w, f, a, d)
+    wband, wtran = w[idx_band], w[idx_tran]                 # :75-76
+    Hd = M * np.exp(1j * (k * wband ** 2 - wband * (n - 1) / 2))      # :113-121
+    center = np.concatenate([Hd, np.zeros(wtran.size, complex)])
+    radius = np.concatenate([D, np.full(wtran.size, 1 + d.max() * 5)])   # :151,156
+    return dict(kind="qp", n=n, w=np.concatenate([wband, wtran]), center=center, radius=radius, nband=wband.size,
+                obj=float(obj))
+
+
+def response_fir_qp(w, n, x):
+    """H(w) = sum_k h_k exp(-j w k), h = x[:n] + j x[n:]: rows [cos sin; -sin cos] of fir_qp_cvx.m:96-109."""
+    kk = np.arange(n)
+    E = np.exp(-1j * np.outer(w, kk))
+    return E @ (x[:n] + 1j * x[n:])
+
+
+def objective_fir_qp(p, x):
+    n = p["n"]
+    return np.linalg.norm(x) + p["obj"] * np.hypot(x[:n], x[n:]).max()
+
+
+def violation_fir_qp(p, x):
+    H = response_fir_qp(p["w"], p["n"], x)
+    return max(0.0, (np.abs(H - p["center"]) - p["radius"]).max())
+
+
+def solve_fir_qp_reference(p, x0=None, maxiter=3000):
+    """Independent CPU solve (SciPy trust-constr on the smooth squared-norm form with epigraph variables)."""
+    from scipy.optimize import NonlinearConstraint, minimize
+    n = p["n"]
+    kk = np.arange(n)
+    Ew = np.exp(-1j * np.outer(p["w"], kk))
+    Ar = np.hstack([Ew.real, -Ew.imag])          # Re H = Ar x ; Im H = Ai x   (H = Ew (xr + j xi))
+    Ai = np.hstack([Ew.imag, Ew.real])
+    cr, ci, R2 = p["center"].real, p["center"].imag, p["radius"] ** 2
+
+    def fun(v):
+        return v[2 * n] + p["obj"] * v[2 * n + 1]
+
+    def grad(v):
+        g = np.zeros_like(v); g[2 * n] = 1; g[2 * n + 1] = p["obj"]; return g
+
+    def cons(v):
+        x, E, P = v[:2 * n], v[2 * n], v[2 * n + 1]
+        hr, hi = Ar @ x - cr, Ai @ x - ci
+        return np.concatenate([R2 - hr ** 2 - hi ** 2, P ** 2 - x[:n] ** 2 - x[n:] ** 2, [E ** 2 - x @ x], [E, P]])
+
+    def jac(v):
+        x, E, P = v[:2 * n], v[2 * n], v[2 * n + 1]
+        hr, hi = Ar @ x - cr, Ai @ x - ci
+        J1 = np.hstack([-2 * (hr[:, None] * Ar + hi[:, None] * Ai), np.zeros((hr.size, 2))])
+        J2 = np.zeros((n, 2 * n + 2))
+        J2[np.arange(n), np.arange(n)] = -2 * x[:n]; J2[np.arange(n), n + np.arange(n)] = -2 * x[n:]; J2[:, 2 * n + 1] = 2 * P
+        J3 = np.concatenate([-2 * x, [2 * E, 0]])[None, :]
+        J4 = np.zeros((2, 2 * n + 2)); J4[0, 2 * n] = 1; J4[1, 2 * n + 1] = 1
+        return np.vstack([J1, J2, J3, J4])
+    if x0 is None:
+        # least-squares fit of the band targets as a start
+        x0 = np.linalg.lstsq(np.vstack([Ar[:p["nband"]], Ai[:p["nband"]]]), np.concatenate([cr[:p["nband"]], ci[:p["nband"]]]), rcond=None)[0]
+    v0 = np.concatenate([x0, [np.linalg.norm(x0) * 1.01 + 1e-3, np.hypot(x0[:n], x0[n:]).max() * 1.01 + 1e-3]])
+    res = minimize(fun, v0, jac=grad, method="trust-constr", constraints=[NonlinearConstraint(cons, 0, np.inf, jac=jac)],
+                   options=dict(maxiter=maxiter, gtol=1e-10, xtol=1e-12, barrier_tol=1e-12, verbose=0))
+    return res

@@ -139,3 +139,37 @@ def test_min_order_searches(mbrf, case):
     assert st == k["linprog_status"] and h.size == k["linprog_len"]
     h, st = mbrf.fir_min_order(k["n"], k["f"], k["a"], k["d"], 0, None, 0, max_iter=60000)
     assert st == k["minorder_status"] and h.size == k["minorder_len"]
+
+
+# ---- fir_qp_cvx.m (scalar-obj SOCP) ------------------------------------------------------------------
+def _qp_known():
+    return json.load(open(os.path.join(GOLDEN, "fir_qp_known.json")))
+
+
+@pytest.mark.parametrize("case", ["qp_n16_obj1", "qp_n16_obj0", "qp_n20_obj5"])
+def test_fir_qp_cvx_vs_scipy_reference(mbrf, case):
+    """Objective E_total + obj*Peak within 1e-4 relative of SciPy trust-constr, every disk satisfied to 1e-6."""
+    from oracle.fir_problems import build_fir_qp, objective_fir_qp, violation_fir_qp
+    k = _qp_known()[case]
+    h, st, ex = mbrf.fir_qp_cvx(k["n"], k["f"], k["a"], k["d"], k["k"], k["obj"], return_info=True)
+    assert st == "Solved" and h.size == k["n"]
+    p = build_fir_qp(k["n"], k["f"], k["a"], k["d"], k["k"], k["obj"])
+    x = ex["x"]
+    assert np.array_equal(h, x[:k["n"]] + 1j * x[k["n"]:])                  # fir_qp_cvx.m:209
+    assert abs(objective_fir_qp(p, x) - k["objective"]) <= TOL_OBJ * k["objective"]
+    assert violation_fir_qp(p, x) <= TOL_VIOL
+
+
+def test_fir_qp_cvx_config3(mbrf):
+    """BASELINE config 3: min-energy multiband FIR, N=256, dual-band H-1 spec, k=120 (dzrf_mb.m:211-213)."""
+    from oracle.fir_problems import H1_DUALBAND, build_fir_qp, objective_fir_qp, violation_fir_qp
+    h, st, ex = mbrf.fir_qp_cvx(256, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 120, 1.0, return_info=True)
+    assert st == "Solved" and h.size == 256
+    p = build_fir_qp(256, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 120, 1.0)
+    assert p["w"].size == 2560 + 6                                           # SURVEY.md 8(a) F2: m = 2560 + 2*nband
+    assert violation_fir_qp(p, ex["x"]) <= TOL_VIOL
+    # the solver's own objective and its dual value bracket the optimum to 1e-4
+    assert abs(ex["info"][2] - objective_fir_qp(p, ex["x"])) <= 1e-9
+    assert abs(ex["info"][2] - ex["info"][3]) <= TOL_OBJ * ex["info"][2]
+    with pytest.raises(NotImplementedError):
+        mbrf.fir_qp_cvx(16, [-0.5, 0.5], [1, 1], [0.1], 2, [1.0, 1.0])

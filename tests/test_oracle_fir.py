@@ -55,3 +55,15 @@ def test_numpy_pdhg_twin_certifies_infeasibility():
     upper = np.array([p["radius"][0] + p["c"][-1] * p["hi"][p["stop"]].max()])
     r = P.solve(P.assemble_fir_ap([p]), max_iter=5000, obj_upper=upper)
     assert r["status"][0] == 2
+
+
+def test_numpy_qp_twin_matches_scipy_reference():
+    """fir_qp_cvx SOCP: the numpy twin of the GPU algorithm against SciPy trust-constr (small design)."""
+    from oracle import pdhg_qp_reference as Q
+    from oracle.fir_problems import build_fir_qp, objective_fir_qp, violation_fir_qp
+    k = json.load(open(os.path.join(GOLDEN, "fir_qp_known.json")))["qp_n16_obj1"]
+    p = build_fir_qp(k["n"], k["f"], k["a"], k["d"], k["k"], k["obj"])
+    x, _, iters = Q.solve_qp_twin(p)
+    assert iters < 100000
+    assert abs(objective_fir_qp(p, x) - k["objective"]) <= 1e-4 * k["objective"]
+    assert violation_fir_qp(p, x) <= 1e-6

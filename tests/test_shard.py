@@ -65,3 +65,15 @@ def test_gather_world2_gloo(n):
         p.join(120)
         assert p.exitcode == 0
     assert q.get() is True
+
+
+def test_sweep_partition_is_a_partition():
+    """fir_ap_cvx_sweep gives design i to rank i mod world: every instance exactly once."""
+    import numpy as np
+    from multiband_rf_pulse_design_b200.fir import sweep_grid
+    fl, ol, pl = sweep_grid([-0.5, -0.2, 0.2, 0.5], [0.1, 1.0, 10.0], [1e-3, 2e-3], [0.0, 0.01, 0.02, 0.03])
+    assert len(fl) == len(ol) == len(pl) == 24
+    assert fl[1][0] == -0.51 and fl[1][1] == -0.19          # f_add fastest, widens every band on both sides
+    for world in (1, 2, 3, 8):
+        seen = np.concatenate([np.arange(r, len(fl), world) for r in range(world)])
+        assert sorted(seen.tolist()) == list(range(24))
