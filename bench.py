@@ -228,6 +228,13 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
     sec = max_over_ranks(time.perf_counter() - t0)
     launches = lib.mbrf_launch_count() - l0
     barrier()
+    single = None
+    if rank == 0:
+        t1 = time.perf_counter()
+        _, st3, ex3 = fir.fir_qp_cvx(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 120, 1.0, return_info=True)
+        single = {"workload": "cfg3: fir_qp_cvx min-energy multiband FIR, N=256, dual-band H-1 spec, k=120, obj=1, single design",
+                  "status": st3, "seconds": time.perf_counter() - t1, "iterations": float(ex3["info"][1]),
+                  "objective": float(ex3["info"][2]), "max_violation": float(ex3["info"][4])}
     info = r["info"]
     solved = int((info[:, 0] == 1).sum())
     iters = float(info[:, 1].max()) if info.size else 0.0
@@ -240,6 +247,7 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
             "designs": total, "designs_per_gpu": per_gpu, "solved_on_rank0": solved, "local_designs_rank0": int(info.shape[0]),
             "seconds": sec, "iterations_max": iters, "gpu_launches": int(launches),
             "workload": "cfg4 slice: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, obj x Peak trade-off grid",
+            "single_design": single,
             "tolerances": {"eps_pr": fir.EPS_PR, "eps_gap_rel": fir.EPS_GAP, "eps_dr": fir.EPS_DR},
             "gemm_tflops_useful": flops / sec / 1e12, "iterations_mean": float(info[:, 1].mean()) if info.size else 0.0,
             "note": "fp64 restarted PDHG; products on the FP64 tensor path (mma.sync m8n8k4); whole call timed on the host "
@@ -373,6 +381,37 @@ def run_ours(args):
     # the e2e result must be the same numbers as the device-resident leg
     chk = float(np.abs(h_out_np[2][:4096] - out[2][:4096].cpu().numpy()).max())
 
+    # ---- forward SLR (abrx) on the same pulse: 10^6 positions x 512 samples, device-resident -------------
+    slr = None
+    if rank == 0:
+        rf = np.load(os.path.join(ROOT, "tests", "golden", "pulses.npz"))["rf512_rad"] \
+            if os.path.exists(os.path.join(ROOT, "tests", "golden", "pulses.npz")) else wl["b1"] * (2 * np.pi * 1.0705 * wl["dt"] * 1e3)
+        ns, nx = rf.size, 1_000_000
+        d_rfr, d_rfi = T(rf.real), T(rf.imag)
+        d_g, d_x = T(np.full(ns, 2 * np.pi / ns)), T(np.linspace(-40, 40, nx))
+        ab = torch.empty((4, nx), dtype=torch.float64, device=dev)
+        ws2 = torch.empty(int(lib.mbrf_abr_workspace_bytes(ns)), dtype=torch.uint8, device=dev)
+
+        def step_slr():
+            check(lib.mbrf_abr_device(d_rfr.data_ptr(), d_rfi.data_ptr(), d_g.data_ptr(), None, ns, d_x.data_ptr(), nx,
+                                      None, 1, 0, 0, nx, ab[0].data_ptr(), ab[1].data_ptr(), ab[2].data_ptr(),
+                                      ab[3].data_ptr(), ws2.data_ptr(), stream.cuda_stream))
+        for _ in range(3):
+            step_slr()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record(stream)
+        for _ in range(reps):
+            step_slr()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_slr = e0.elapsed_time(e1) / reps
+        unit = float((ab[0] ** 2 + ab[1] ** 2 + ab[2] ** 2 + ab[3] ** 2 - 1).abs().max().item())
+        slr = {"metric": "SLR position-steps/sec", "value": nx * ns / (ms_slr * 1e-3), "unit": "position-steps/s",
+               "ms_per_call": ms_slr, "positions": nx, "samples": ns, "unitarity_max_err": unit,
+               "flops_per_position_step": 50, "call": "mbrf_abr_device (abrx convention), device-resident"}
+
     # ---- second hot path: convex FIR design step (BASELINE metric "N=256 FIR pulse designs solved/sec") --------
     solver = None
     if not args.no_solver:
@@ -416,6 +455,10 @@ def run_ours(args):
                 "note": "56 algorithmic bytes per spin per call: the path is FP64-bound, not HBM-bound"},
     }
 
+    if slr:
+        slr["roofline"] = {"bound": "fp64", "achieved": slr["value"] * 50 / 1e12, "peak": tf.value, "unit": "TFLOP/s",
+                           "frac": slr["value"] * 50 / 1e12 / tf.value}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -441,6 +484,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "solver": solver,
+        "slr": slr,
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:

@@ -204,12 +204,45 @@ __device__ void steady_state(Spin &s)
     s.mz = adj[2] * s.b[0] + adj[5] * s.b[1] + adj[8] * s.b[2];
 }
 
+// Mode bit 1 (record every sample, blochC.c:381-391) writes element [t + ntime*spin]: consecutive threads are
+// ntime doubles apart, so direct stores touch one 8-byte word per 32-byte sector (measured 0.6 TB/s).  Each warp
+// therefore stages RT = 8 samples of its 32 spins per component in shared memory and writes them transposed:
+// 8 consecutive samples of one spin = 64 contiguous bytes, i.e. whole sectors.
+constexpr int RT = 8;              // samples staged per flush
+constexpr int RLD = RT + 1;        // padded row: conflict-free column access
+
+template <int SPT>
+__device__ __forceinline__ void record_flush(double (*stage)[32 * RLD], int count, int t_first, long long warp_ls0,
+                                             long long nspins, int ntime, double *mx, double *my, double *mz, int lane)
+{
+    __syncwarp();
+    double *const outs[3] = {mx, my, mz};
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+        const long long base = warp_ls0 + (long long)j * BLOCK;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double *st = stage[j * 3 + c];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const int idx = r * 32 + lane, sl = idx / RT, tt = idx % RT;
+                if (tt < count && base + sl < nspins)
+                    outs[c][(size_t)(base + sl) * ntime + t_first + tt] = st[sl * RLD + tt];
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // One tile of n samples for this thread's SPT spins.  RECORD: write every sample (mode bit 1).
 template <int NG, int SPT, int TIER, bool SWEEP, bool STEADY, bool RECORD, bool CRZ>
 __device__ __forceinline__ void run_tile(const double *__restrict__ tile, int n, Spin (&sp)[SPT],
                                          const bool (&active)[SPT], double *const (&ox)[SPT],
-                                         double *const (&oy)[SPT], double *const (&oz)[SPT], int t0)
+                                         double *const (&oy)[SPT], double *const (&oz)[SPT], int t0,
+                                         double (*stage)[32 * RLD], long long warp_ls0, long long nspins, int ntime,
+                                         double *mx, double *my, double *mz)
 {
+    const int lane = threadIdx.x & 31;
 #pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const double *e = tile + i * SD;
@@ -217,12 +250,13 @@ __device__ __forceinline__ void run_tile(const double *__restrict__ tile, int n,
         for (int j = 0; j < SPT; ++j) spin_step<NG, TIER, SWEEP, STEADY, CRZ>(e, sp[j]);
         if (RECORD) {
 #pragma unroll
-            for (int j = 0; j < SPT; ++j)
-                if (active[j]) {  // blochC.c:381-391
-                    ox[j][t0 + i] = sp[j].mx;
-                    oy[j][t0 + i] = sp[j].my;
-                    oz[j][t0 + i] = sp[j].mz;
-                }
+            for (int j = 0; j < SPT; ++j) {   // blochC.c:381-391
+                stage[j * 3 + 0][lane * RLD + (i % RT)] = sp[j].mx;
+                stage[j * 3 + 1][lane * RLD + (i % RT)] = sp[j].my;
+                stage[j * 3 + 2][lane * RLD + (i % RT)] = sp[j].mz;
+            }
+            if ((i % RT) == RT - 1 || i == n - 1)
+                record_flush<SPT>(stage, (i % RT) + 1, t0 + i - (i % RT), warp_ls0, nspins, ntime, mx, my, mz, lane);
         }
     }
 }
@@ -233,6 +267,10 @@ __global__ void __launch_bounds__(BLOCK) bloch_kernel(const Params p)
 {
     __shared__ __align__(128) double tiles[NBUF][TT * SD];
     __shared__ __align__(8) uint64_t full[NBUF];
+    // per-warp transpose staging for the record modes (one slot otherwise so the array is never empty)
+    constexpr int NSTAGE = (MODE & 2) ? (BLOCK / 32) * SPT * 3 : 1;
+    __shared__ double stage_all[NSTAGE][(MODE & 2) ? 32 * RLD : 1];
+    double (*stage)[32 * RLD] = (MODE & 2) ? reinterpret_cast<double (*)[32 * RLD]>(&stage_all[(threadIdx.x >> 5) * SPT * 3][0]) : nullptr;
 
     const int tid = threadIdx.x;
     const int ntiles = (p.ntime + TT - 1) / TT;
@@ -324,6 +362,7 @@ __global__ void __launch_bounds__(BLOCK) bloch_kernel(const Params p)
             q.rz2 = q.rz0 * q.rz0;
         }
         tier = __reduce_max_sync(0xffffffffu, tier);  // one code path per warp
+        const long long warp_ls0 = g * group_spins + (tid & ~31);   // local spin of this warp's lane 0 (j = 0)
 
 #pragma unroll
         for (int pass = 0; pass < PASSES; ++pass) {
@@ -341,8 +380,10 @@ __global__ void __launch_bounds__(BLOCK) bloch_kernel(const Params p)
                 const double *tile = tiles[k % NBUF];
                 mbar_wait(&full[k % NBUF], (k / NBUF) & 1u);
 #define MBRF_RUN(TIER_, CRZ_)                                                                                   \
-    if (steady) run_tile<NG, SPT, TIER_, SWEEP, true, false, false>(tile, n, sp, active, ox, oy, oz, ti * TT);     \
-    else run_tile<NG, SPT, TIER_, SWEEP, false, (MODE & 2) != 0, CRZ_>(tile, n, sp, active, ox, oy, oz, ti * TT);
+    if (steady) run_tile<NG, SPT, TIER_, SWEEP, true, false, false>(tile, n, sp, active, ox, oy, oz, ti * TT, stage,    \
+                                                                    warp_ls0, p.nspins, p.ntime, p.mx, p.my, p.mz);       \
+    else run_tile<NG, SPT, TIER_, SWEEP, false, (MODE & 2) != 0, CRZ_>(tile, n, sp, active, ox, oy, oz, ti * TT, stage, \
+                                                                       warp_ls0, p.nspins, p.ntime, p.mx, p.my, p.mz);
                 if (MODE == 1 || MODE == 3) {
                     // steady-state modes are rare (no caller in the reference): one general path
                     MBRF_RUN(TIER_ANY, false)
@@ -420,10 +461,12 @@ static int dispatch_ng_spt(const Params &p, int ng, int spt, cudaStream_t stream
     } else if constexpr (MODE == 1 || MODE == 3) {
         MBRF_CASE(2, 1);
     } else {
-        if (MODE == 0 && spt == 2) {
-            if (ng == 0) MBRF_CASE(0, 2);
-            if (ng == 1) MBRF_CASE(1, 2);
-            MBRF_CASE(2, 2);
+        if constexpr (MODE == 0) {
+            if (spt == 2) {
+                if (ng == 0) MBRF_CASE(0, 2);
+                if (ng == 1) MBRF_CASE(1, 2);
+                MBRF_CASE(2, 2);
+            }
         }
         if (ng == 0) MBRF_CASE(0, 1);
         if (ng == 1) MBRF_CASE(1, 1);

@@ -69,3 +69,17 @@ for spt in (1, 2):
             t = timeit(lambda: run(ngrad))
             print(f"spt={spt} ctas/sm={bps:2d} ngrad={ngrad}: {t:.3f} ms  {ns * nt / t / 1e6:.1f} Gspin-steps/s")
 check(lib.mbrf_bloch_set_tuning(0, 0))
+
+# modes 1, 2, 3 at a smaller spin count (mode 2/3 write ntime values per spin)
+nf2 = 200
+ns2 = nf2 * npos
+out2 = [torch.empty(ns2 * nt, dtype=torch.float64, device=dev) for _ in range(3)]
+for mode in (2, 1, 3):
+    def run_m():
+        check(lib.mbrf_bloch_device(b1r.data_ptr(), b1i.data_ptr(), gx.data_ptr(), None, None, dts.data_ptr(), nt, 1e3, 1e3,
+                                    df.data_ptr(), nf2, dx.data_ptr(), None, None, npos, 0, ns2, None, None, None, 1,
+                                    out2[0].data_ptr(), out2[1].data_ptr(), out2[2].data_ptr(), mode, m.GAMMA_C13,
+                                    ws.data_ptr(), stream))
+    t = timeit(run_m, 3)
+    gb = ns2 * nt * 24 / 1e9 if mode & 2 else 0
+    print(f"mode {mode}: {ns2} spins x {nt}: {t:.3f} ms  {ns2 * nt / t / 1e6:.1f} Gspin-steps/s" + (f"  store {gb / t * 1e3:.0f} GB/s" if gb else ""))
