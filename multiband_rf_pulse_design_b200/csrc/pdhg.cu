@@ -309,6 +309,7 @@ struct Problem {
     int *active;                                // number of designs still running
     double eta, eps_pr, eps_dr, eps_gap;
     int check_every;
+    double beta_suff, beta_nec, beta_art, omega_theta;   // restart rule constants (PDLP defaults 0.2, 0.8, 0.36, 0.5)
 };
 
 enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, A_GMAX, A_ZZ, A_ZV, A_VV, NACC };
@@ -710,11 +711,11 @@ __global__ void control_kernel(Problem p, int iter_now, int max_iter)
     if (c.status != 0.0 && c.restart == 0.0) return;
     // restart rules (PDLP): sufficient decay, necessary decay + no progress, or long since last restart
     const double e = err[k];
-    const bool doit = e <= 0.2 * c.last_err || (e <= 0.8 * c.last_err && e > c.prev_err) ||
-                      c.since >= 0.36 * (double)iter_now;
+    const bool doit = e <= p.beta_suff * c.last_err || (e <= p.beta_nec * c.last_err && e > c.prev_err) ||
+                      c.since >= p.beta_art * (double)iter_now;
     c.prev_err = e;
     if (doit && c.status == 0.0) {
-        if (dz[k] > 1e-12 && dy[k] > 1e-12) c.omega = exp(0.5 * log(dy[k] / dz[k]) + 0.5 * log(c.omega));
+        if (dz[k] > 1e-12 && dy[k] > 1e-12) c.omega = exp(p.omega_theta * log(dy[k] / dz[k]) + (1.0 - p.omega_theta) * log(c.omega));
         c.tau = p.eta / c.omega;
         c.sigma = p.eta * c.omega;
         c.last_err = e;
@@ -793,6 +794,7 @@ __global__ void norm2_first_col_kernel(const double *v, int n, int Bp, double *o
 
 static inline int up(int v, int a) { return (v + a - 1) / a * a; }
 
+static double g_opt[5] = {0.9, 0.2, 0.8, 0.36, 0.5};   // eta factor, beta_suff, beta_nec, beta_art, omega_theta
 static int g_use_dmma = 1;   // 1: mma.sync m8n8k4 f64 tiles, 0: SIMT DFMA tiles (mbrf_pdhg_set_gemm)
 
 static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st)   // C[Mp x Bp] = K X
@@ -835,6 +837,15 @@ extern "C" {
 int mbrf_pdhg_set_gemm(int use_dmma)
 {
     g_use_dmma = use_dmma ? 1 : 0;
+    return MBRF_OK;
+}
+
+// algorithm constants: which = 0 eta factor (0.9), 1 sufficient-decay beta (0.2), 2 necessary-decay beta (0.8),
+// 3 artificial-restart fraction (0.36), 4 primal-weight smoothing (0.5)
+int mbrf_pdhg_set_option(int which, double value)
+{
+    if (which < 0 || which > 4 || !(value > 0.0)) return MBRF_EINVAL;
+    g_opt[which] = value;
     return MBRF_OK;
 }
 
@@ -986,7 +997,8 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         MBRF_CUDA(cudaMemsetAsync(p.G, 0, slab_doubles(Mp, Np, Bp) * 8, st));
         MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)Bp * 8, st));
     }
-    p.eta = 0.9 / sqrt(knorm2);
+    p.eta = g_opt[0] / sqrt(knorm2);
+    p.beta_suff = g_opt[1]; p.beta_nec = g_opt[2]; p.beta_art = g_opt[3]; p.omega_theta = g_opt[4];
     {
         std::vector<Ctl> hc((size_t)Bp);
         for (int b = 0; b < Bp; ++b) {

@@ -190,19 +190,8 @@ static int launch(K kernel, const Params &p, int spt, cudaStream_t stream)
     const long long group = (long long)BLOCK * spt;
     const long long ngroups = (p.npos + group - 1) / group;
     if (ngroups == 0) return MBRF_OK;
-    int occ = 0;
-    MBRF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BLOCK, 0));
-    if (occ < 1) occ = 1;
-    const int sms = sm_count();
-    int bps = occ;
-    long long best = -1;
-    for (int c = occ; c >= (occ + 1) / 2 && c >= 1; --c) {
-        const long long per_wave = (long long)sms * c;
-        const long long cost = ((ngroups + per_wave - 1) / per_wave) * c;
-        if (best < 0 || cost < best) { best = cost; bps = c; }
-    }
-    long long grid = (long long)sms * bps;
-    if (grid > ngroups) grid = ngroups;
+    // one group of BLOCK*SPT positions per CTA: the hardware block scheduler balances the SMs (see bloch.cu)
+    const long long grid = ngroups;
     kernel<<<(unsigned)grid, BLOCK, 0, stream>>>(p);
     MBRF_LAUNCH_CHECK();
     return MBRF_OK;
