@@ -185,6 +185,34 @@ def _x_to_h(x, n):
     return fmp2(r)
 
 
+def _solve_concurrently(jobs):
+    """Run independent solves (different orders n => different matrices, so they cannot share a batch) from
+    concurrent host threads: every thread owns a CUDA stream and scratch inside libmbrf, ctypes drops the GIL, and
+    the single-design kernels are small enough to overlap on the GPU.  jobs: list of zero-argument callables."""
+    if len(jobs) <= 1:
+        return [j() for j in jobs]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        return list(ex.map(lambda j: j(), jobs))
+
+
+def _speculate(state, step, depth):
+    """All probes a bisection can ask for within `depth` steps, whatever the outcomes.
+    state: hashable search state; step(state, solved) -> next state; the probe of a state is state[-1]."""
+    todo, seen, frontier = [], set(), [state]
+    for _ in range(depth):
+        nxt = []
+        for st in frontier:
+            if st is None or st[-1] is None:
+                continue
+            if st[-1] not in seen:
+                seen.add(st[-1])
+                todo.append(st[-1])
+            nxt += [step(st, True), step(st, False)]
+        frontier = nxt
+    return todo
+
+
 # --------------------------------------------------------------------------------------------
 # public mirrors
 # --------------------------------------------------------------------------------------------
@@ -277,13 +305,31 @@ def fir_ap(n, f, a, d, Peak=1e-3, min_order=0, min_tran=0, min_peak=0, dbg=0, **
         f_op = f.copy()
     if min_order > 0:
         n_top, n_bot = int(n), 2                                          # :140-141
-        while n_top - n_bot > 1:                                          # :143-162, one probe per round: orders differ -> no shared matrix
-            n_mid = int(np.ceil((n_top + n_bot) / 2))
-            h0, st0 = fir_ap_cvx(n_mid, f, a, d, lam, Peak, **solver_kw)
-            if st0 == "Failed":
-                n_bot = n_mid
+        # fir_ap.m:143-162 probes n_mid = ceil((n_top+n_bot)/2) serially.  Orders differ, so the probes cannot share
+        # a matrix; the next three levels of the bisection tree (<= 7 orders) are solved concurrently instead and
+        # the tree is then walked with exactly the reference's decisions.
+        def step(st, solved):
+            bot, top, mid = st
+            if solved:
+                top = mid
             else:
-                h, status, n_top = h0, st0, n_mid
+                bot = mid
+            return (bot, top, int(np.ceil((top + bot) / 2)) if top - bot > 1 else None)
+
+        state = (n_bot, n_top, int(np.ceil((n_top + n_bot) / 2)) if n_top - n_bot > 1 else None)
+        cache = {}
+        while state[2] is not None:
+            need = [q for q in _speculate(state, step, 3) if q not in cache]
+            res = _solve_concurrently([(lambda q=q: fir_ap_cvx(q, f, a, d, lam, Peak, **solver_kw)) for q in need])
+            cache.update(dict(zip(need, res)))
+            for _ in range(3):
+                if state[2] is None:
+                    break
+                h0, st0 = cache[state[2]]
+                if st0 != "Failed":
+                    h, status = h0, st0
+                state = step(state, st0 != "Failed")
+        n_bot, n_top = state[0], state[1]
         if min_order == 1:
             n_op = n_top                                                  # :164-166
         elif 0 < min_order < 1:
@@ -450,16 +496,31 @@ def _min_order_search(n, f, a, d, even_odd, solve, pick_longer):
     n_even_max = 2 * (n // 2)
 
     def bisect(n_top, tap_of, hbest):
-        n_bot, n_cur = 1, n_top                                           # :91-93 / :152-160
-        while n_top - n_bot > 1:
-            h, st = solve(tap_of(n_cur), hbest)
-            if st == "Solved":
-                hbest = h
-                n_top = n_cur
-                n_cur = n_bot if n_top == n_bot + 1 else int(np.ceil((n_top + n_bot) / 2))   # :131-136
+        # state (n_bot, n_top, n_cur): the reference's loop, :91-147 / :152-211, one probe per step; the next three
+        # levels of its decision tree are solved concurrently (orders differ -> separate matrices), then walked.
+        def step(st, solved):
+            bot, top, cur = st
+            if solved:
+                top = cur
+                cur = bot if top == bot + 1 else int(np.ceil((top + bot) / 2))   # :131-136
             else:
-                n_bot = n_cur
-                n_cur = int(np.ceil((n_bot + n_top) / 2))                 # :141-142
+                bot = cur
+                cur = int(np.ceil((bot + top) / 2))                              # :141-142
+            return (bot, top, cur if top - bot > 1 else None)
+
+        state = (1, n_top, n_top if n_top - 1 > 1 else None)
+        cache = {}
+        while state[2] is not None:
+            need = [q for q in _speculate(state, step, 3) if q not in cache]
+            res = _solve_concurrently([(lambda q=q: solve(tap_of(q), None)) for q in need])
+            cache.update(dict(zip(need, res)))
+            for _ in range(3):
+                if state[2] is None:
+                    break
+                h, st = cache[state[2]]
+                if st == "Solved":
+                    hbest = h
+                state = step(state, st == "Solved")
         return hbest
 
     if even_odd != 2:

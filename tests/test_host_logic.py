@@ -1,0 +1,66 @@
+"""CPU tests of host-side search logic (no GPU): the speculative, concurrent bisections must take exactly the
+decisions of the reference's serial loops (ss/fir_min_order_linprog.m:84-232, fir_ap.m:143-162)."""
+import numpy as np
+import pytest
+
+
+def _serial_min_order(n, feasible):
+    """Literal transcription of the control flow of ss/fir_min_order_linprog.m:84-232 (probe = feasible(n_tap))."""
+    hb_o = hb_e = None
+    n_odd_max, n_even_max = 2 * ((n - 1) // 2) + 1, 2 * (n // 2)
+    n_bot, n_top = 1, (n_odd_max + 1) // 2
+    n_cur = n_top
+    while n_top - n_bot > 1:
+        if feasible(2 * n_cur - 1):
+            hb_o, n_top = 2 * n_cur - 1, n_cur
+            n_cur = n_bot if n_top == n_bot + 1 else int(np.ceil((n_top + n_bot) / 2))
+        else:
+            n_bot = n_cur
+            n_cur = int(np.ceil((n_bot + n_top) / 2))
+    n_bot = 1
+    n_top = n_even_max // 2 if hb_o is None else min(n_even_max // 2, (hb_o + 1) // 2)
+    n_cur = n_top
+    while n_top - n_bot > 1:
+        if feasible(2 * n_cur):
+            hb_e, n_top = 2 * n_cur, n_cur
+            n_cur = n_bot if n_top == n_bot + 1 else int(np.ceil((n_top + n_bot) / 2))
+        else:
+            n_bot = n_cur
+            n_cur = int(np.ceil((n_bot + n_top) / 2))
+    return hb_o, hb_e
+
+
+@pytest.mark.parametrize("n,min_odd,min_even", [(40, 27, 28), (40, 19, 20), (40, 5, 40), (41, 39, 39), (64, 99, 99),
+                                                  (33, 3, 2), (512, 301, 288)])
+def test_speculative_min_order_search_equals_serial(n, min_odd, min_even):
+    from multiband_rf_pulse_design_b200 import fir
+
+    def feasible(nt):
+        return nt >= (min_odd if nt % 2 else min_even)
+
+    def solve(nt, hw):
+        return (np.zeros(nt), "Solved") if feasible(nt) else (np.zeros(0), "Failed")
+
+    hb_o, hb_e = _serial_min_order(n, feasible)
+    h, st = fir._min_order_search(n, None, None, None, 0, solve, pick_longer=False)
+    if hb_o is None and hb_e is None:
+        assert st == "Failed" and h.size == 0
+    else:
+        want = hb_e if hb_o is None else (hb_o if (hb_e is None or hb_o < hb_e) else hb_e)   # :220-228
+        assert st == "Solved" and h.size == want
+    h, st = fir._min_order_search(n, None, None, None, 0, solve, pick_longer=True)           # fir_min_order.m:222-226
+    if not (hb_o is None and hb_e is None):
+        assert h.size == (hb_o if (hb_o or 0) > (hb_e or 0) else hb_e)
+
+
+def test_speculation_lists_only_reachable_probes():
+    from multiband_rf_pulse_design_b200 import fir
+
+    def step(st, solved):
+        bot, top, mid = st
+        bot, top = (bot, mid) if solved else (mid, top)
+        return (bot, top, int(np.ceil((top + bot) / 2)) if top - bot > 1 else None)
+
+    probes = fir._speculate((2, 256, 129), step, 3)
+    assert probes[0] == 129 and set(probes) == {129, 66, 193, 34, 98, 161, 225}
+    assert fir._speculate((2, 3, None), step, 3) == []
