@@ -173,3 +173,12 @@ def test_fir_qp_cvx_config3(mbrf):
     assert abs(ex["info"][2] - ex["info"][3]) <= TOL_OBJ * ex["info"][2]
     with pytest.raises(NotImplementedError):
         mbrf.fir_qp_cvx(16, [-0.5, 0.5], [1, 1], [0.1], 2, [1.0, 1.0])
+
+
+def test_fir_ap_min_order_search(mbrf):
+    """fir_ap.m:137-176 (BASELINE config 5's search, here on a small spec): minimum order by bisection, probes of one
+    round solved concurrently; same answer as the serial bisection driven by HiGHS (Peak loose: cones inactive)."""
+    k = KNOWN["lowpass_minorder_from40"]
+    h, st, n_op, f_op = mbrf.fir_ap(k["n"], k["f"], k["a"], k["d"], k["peak"], 1, 0, 0, 0, max_iter=60000)
+    assert st == "Solved" and n_op == k["n_op"] and h.size == k["n_op"]
+    assert np.array_equal(f_op, np.array(k["f"], float))
