@@ -30,6 +30,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -225,47 +226,53 @@ dgemm_mma_kernel(const double *__restrict__ AT, int ldat, const double *__restri
 // coalesced loads, the vector kept in shared memory, warp-shuffle reduction.
 //   out[r] = sum_k A[r][k] * x[k]      A row-major [R x ld], kdim multiple of 64
 // ---------------------------------------------------------------------------
-// RPC rows per CTA of 256 threads: 8/RPC warps share a row (k split between them, partials summed through shared
-// memory).  STAGE: copy x into shared memory first (worth it when RPC rows reuse a short x).
-template <int RPC, bool STAGE>
+// out[o][b] = sum_k AT[k][o] * x[k][b]  for NB = 1, 2, 4 or 8 designs, AT k-major exactly as in the GEMM kernels.
+// A CTA owns 64 outputs; its 4 warps-pairs ("quarters") take every 4th k of a 64-row tile, so a thread issues one
+// coalesced 8-byte load of AT per 1..8 FMAs against the broadcast x tile in shared memory; the quarters are summed
+// through shared memory.  blockIdx.y splits a long reduction into slabs like the GEMM's split-K.
+template <int NB>
 __global__ void __launch_bounds__(256)
-dgemv_rows_kernel(const double *__restrict__ A, int ld, int R, int kdim, const double *__restrict__ x,
-                  double *__restrict__ out)
+thin_kernel(const double *__restrict__ AT, int ldat, const double *__restrict__ X, double *__restrict__ C, int kdim,
+            int kchunk, long long slab)
 {
-    extern __shared__ double xs[];
-    __shared__ double part[8];
-    if (STAGE) {
-        for (int k = threadIdx.x; k < kdim; k += blockDim.x) xs[k] = x[k];
+    __shared__ double xs[64 * NB];
+    __shared__ double red[4][64][NB];
+    const int tid = threadIdx.x, ol = tid & 63, q = tid >> 6;
+    const int o = blockIdx.x * 64 + ol;
+    const int k_begin = blockIdx.y * kchunk, k_end = min(kdim, k_begin + kchunk);
+    double acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.0;
+    for (int k0 = k_begin; k0 < k_end; k0 += 64) {
+        const int nk = min(64, k_end - k0);
+        for (int e = tid; e < nk * NB; e += 256) xs[e] = X[(size_t)k0 * NB + e];
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = q; kk < nk; kk += 4) {
+            const double a = AT[(size_t)(k0 + kk) * ldat + o];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = fma(a, xs[kk * NB + b], acc[b]);
+        }
         __syncthreads();
     }
-    constexpr int WPR = 8 / RPC;                       // warps per row
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * RPC + warp / WPR, sub = warp % WPR;
-    double acc = 0.0;
-    if (r < R) {
-        const double2 *row = reinterpret_cast<const double2 *>(A + (size_t)r * ld);
-        const double2 *xv = reinterpret_cast<const double2 *>(STAGE ? xs : x);
-        double acc0 = 0.0, acc1 = 0.0;
-        for (int k2 = sub * 32 + lane; k2 < kdim / 2; k2 += 32 * WPR) {
-            const double2 a = row[k2], b = xv[k2];
-            acc0 = fma(a.x, b.x, acc0);
-            acc1 = fma(a.y, b.y, acc1);
-        }
-        acc = acc0 + acc1;
 #pragma unroll
-        for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
+    for (int b = 0; b < NB; ++b) red[q][ol][b] = acc[b];
+    __syncthreads();
+    if (q == 0) {
+        double *out = C + (size_t)blockIdx.y * slab + (size_t)o * NB;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = red[0][ol][b] + red[1][ol][b] + red[2][ol][b] + red[3][ol][b];
     }
-    if (WPR == 1) {
-        if (lane == 0 && r < R) out[r] = acc;
-    } else {
-        if (lane == 0) part[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x < RPC && blockIdx.x * RPC + threadIdx.x < R) {
-            double t = 0.0;
-#pragma unroll
-            for (int q = 0; q < WPR; ++q) t += part[threadIdx.x * WPR + q];
-            out[blockIdx.x * RPC + threadIdx.x] = t;
-        }
+}
+
+template <typename... Args>
+static void launch_thin(int nb, dim3 grid, cudaStream_t st, Args... args)
+{
+    switch (nb) {
+    case 1: thin_kernel<1><<<grid, 256, 0, st>>>(args...); break;
+    case 2: thin_kernel<2><<<grid, 256, 0, st>>>(args...); break;
+    case 4: thin_kernel<4><<<grid, 256, 0, st>>>(args...); break;
+    default: thin_kernel<8><<<grid, 256, 0, st>>>(args...); break;
     }
 }
 
@@ -793,14 +800,16 @@ __global__ void norm2_first_col_kernel(const double *v, int n, int Bp, double *o
 }
 
 static inline int up(int v, int a) { return (v + a - 1) / a * a; }
+// batch widths the products support: 1, 2, 4, 8 (matrix-vector pass) or a multiple of 64 (GEMM tiles)
+static inline int batch_width(int b) { return b <= 1 ? 1 : b <= 2 ? 2 : b <= 4 ? 4 : b <= 8 ? 8 : up(b, 64); }
 
 static double g_opt[5] = {0.9, 0.2, 0.8, 0.36, 0.5};   // eta factor, beta_suff, beta_nec, beta_art, omega_theta
 static int g_use_dmma = 1;   // 1: mma.sync m8n8k4 f64 tiles, 0: SIMT DFMA tiles (mbrf_pdhg_set_gemm)
 
 static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st)   // C[Mp x Bp] = K X
 {
-    if (p.Bp == 1) {   // K z: rows of K (row-major [Mp x ldk]) against z
-        dgemv_rows_kernel<8, true><<<(p.Mp + 7) / 8, 256, (size_t)p.Np * 8, st>>>(p.K, p.ldk, p.Mp, p.Np, X, C);
+    if (p.Bp <= 8) {   // thin batch (1..8 designs): one pass over K^T, bound by streaming the matrix
+        launch_thin(p.Bp, dim3(p.Mp / 64, 1), st, p.KT, p.Mp, X, C, p.Np, p.Np, 0LL);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     }
@@ -812,8 +821,9 @@ static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st
 }
 static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st)   // G[P][Np x Bp] = K^T Y
 {
-    if (p.Bp == 1) {   // K^T y: rows of K^T (row-major [Np x Mp]) against y; P == 1, slab 0
-        dgemv_rows_kernel<1, false><<<p.Np, 256, 0, st>>>(p.KT, p.Mp, p.Np, p.Mp, Y, G);
+    if (p.Bp <= 8) {   // thin batch: one pass over K, the long reduction split into p.P slabs
+        const int kc = up((p.Mp + p.P - 1) / p.P, 64);
+        launch_thin(p.Bp, dim3(p.Np / 64, p.P), st, p.K, p.ldk, Y, G, p.Mp, kc, (long long)p.Np * p.Bp);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     }
@@ -855,13 +865,18 @@ int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp)
     if (M <= 0 || N <= 0 || B <= 0 || !Mp || !Np || !Bp) return MBRF_EINVAL;
     *Mp = up(M, 64);
     *Np = up(N, 64);
-    *Bp = B == 1 ? 1 : up(B, 64);
+    *Bp = batch_width(B);
     return MBRF_OK;
 }
 
 static int split_k(int Mp, int Np, int Bp)
 {
-    if (Bp == 1) return 1;
+    if (Bp <= 8) {   // thin path: slabs of >= 256 rows, at most 32 (every slab must own rows: ceil(Mp/P) rounded to 64)
+        int P = Mp / 256 < 32 ? Mp / 256 : 32;
+        if (P < 1) P = 1;
+        while (P > 1 && up((Mp + P - 1) / P, 64) * (P - 1) >= Mp) --P;
+        return P;
+    }
     // K^T Y has only (Np/64)*(Bp/64) output tiles: split the long reduction so that ~6 CTAs land on each SM
     const int tiles = (Np / BM) * (Bp / BN);
     int P = (6 * 148 + tiles - 1) / tiles;
@@ -874,7 +889,7 @@ static int split_k(int Mp, int Np, int Bp)
 // doubles needed for the split-K slabs at any batch width the compaction can reach
 static size_t slab_doubles(int Mp, int Np, int Bp)
 {
-    size_t mx = (size_t)Np;
+    size_t mx = (size_t)split_k(Mp, Np, 8) * Np * 8;
     for (int b = 64; b <= Bp; b += 64) {
         const size_t v = (size_t)split_k(Mp, Np, b) * Np * b;
         if (v > mx) mx = v;
@@ -915,7 +930,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
                   bk.disk_row0, bk.disk_pairs, bk.group_row0, bk.group_pairs, bk.norm_coords);
         return MBRF_EINVAL;
     }
-    if (Mp % 64 || Np % 64 || (Bp % 64 && Bp != 1) || B < 1 || B > Bp || ldk < Np || ldk % 2 ||
+    if (Mp % 64 || Np % 64 || Bp != batch_width(Bp) || B < 1 || B > Bp || ldk < Np || ldk % 2 ||
         max_iter < 1 || check_every < 1 || npairs < 0) {
         set_error("pdhg: bad padded sizes Mp=%d Np=%d Bp=%d B=%d ldk=%d", Mp, Np, Bp, B, ldk);
         return MBRF_EINVAL;
@@ -1122,7 +1137,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         for (int b = 0; b < p.B; ++b)
             if (hc[b].status == 0.0) slot.push_back(b);
         const int keep = (int)slot.size();
-        const int nBp = up(keep > 0 ? keep : 1, 64);
+        const int nBp = batch_width(keep > 0 ? keep : 1);
         if (keep == 0 || nBp >= p.Bp) return MBRF_OK;
         MBRF_CUDA(cudaMemcpyAsync(d_slot, slot.data(), (size_t)keep * 4, cudaMemcpyHostToDevice, st));
         auto regather = [&](double *arr, long long rows, double *tmp, double pad) -> int {
@@ -1166,6 +1181,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         return MBRF_OK;
     };
 
+    const bool trace = getenv("MBRF_PDHG_TRACE") != nullptr;
     int active = B, rcode = MBRF_OK;
     for (int it = 0; it < max_iter && active > 0 && rcode == MBRF_OK;) {
         if (use_graph) {
@@ -1179,8 +1195,14 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         if (rcode != MBRF_OK) break;
         if (cudaMemcpyAsync(&active, p.active, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) { set_error("pdhg: status readback failed: %s", cudaGetErrorString(cudaGetLastError())); rcode = MBRF_ECUDA; break; }
+        if (trace) {   // developer trace (MBRF_PDHG_TRACE=1): slot 0 after every check
+            Ctl t0;
+            if (cudaMemcpy(&t0, p.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost) == cudaSuccess)
+                fprintf(stderr, "pdhg it %6d st %.0f obj %.8f dual %.8f pr %.2e dr %.2e omega %.3e restart %.0f avg %.0f since %.0f lasterr %.2e\n",
+                        it, t0.status, t0.obj, t0.dual, t0.pr, t0.dr, t0.omega, t0.restart, t0.use_avg, t0.since, t0.last_err);
+        }
         // finished designs leave the batch once they would free at least one 64-design column block
-        if (active > 0 && p.Bp > 64 && up(active, 64) < p.Bp && it < max_iter) rcode = compact();
+        if (active > 0 && batch_width(active) < p.Bp && it < max_iter) rcode = compact();
     }
     if (rcode == MBRF_OK) rcode = flush_results();
     if (exec) cudaGraphExecDestroy(exec);
