@@ -26,6 +26,7 @@
 // the iterations, where fp32-accumulate tensor-core products (tcgen05 has no fp64 kind) no longer
 // contract; see DESIGN.md section 6 for the measured numbers and the split-precision plan.
 #include "common.h"
+#include "tc_gemm.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -312,6 +313,7 @@ struct Problem {
     double *G;                                  // [P x Np x Bp] split-K slabs of K^T y
     double *G2;                                 // [Np x Bp] reduced K^T (.) for metrics
     double *acc;                                // [2 cand][NACC][Bp] reduction targets
+    double *mxy, *mxz;                          // [Bp] max |y|, max |zbar| per design for the tcgen05 digit planes (or null)
     Ctl *ctl;
     int *active;                                // number of designs still running
     double eta, eps_pr, eps_dr, eps_gap;
@@ -363,15 +365,11 @@ __global__ void z_shrink_kernel(Problem p)
 }
 
 // z+ = P_X(z - tau (c + sum_p G_p)), zbar = 2 z+ - z, zs += z+.   One thread per (coordinate, design);
-// the thread of pair member i handles both members (j is skipped).
-__global__ void z_update_kernel(Problem p)
+// the thread of pair member i handles both members (j is skipped).  Returns max |zbar| written.
+__device__ __forceinline__ double z_update_elem(const Problem &p, int j, int b)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = (int)(idx % p.Bp);
-    const int j = (int)(idx / p.Bp);
-    if (j >= p.Np) return;
     const int pr = p.pair_of[j];
-    if (pr >= 0 && p.pair_j[pr] == j) return;  // second member: done by the first
+    if (pr >= 0 && p.pair_j[pr] == j) return 0.0;  // second member: done by the first
     const double tau = p.ctl[b].tau;
     const size_t stride = (size_t)p.Np * p.Bp;
     auto grad = [&](int jj) {
@@ -384,38 +382,59 @@ __global__ void z_update_kernel(Problem p)
         const double zo = p.z[o];
         double zn = zo - tau * grad(j);
         zn = fmin(fmax(zn, p.bl[o]), p.bu[o]);
+        const double zb = 2.0 * zn - zo;
         p.z[o] = zn;
-        p.zbar[o] = 2.0 * zn - zo;
+        p.zbar[o] = zb;
         p.zs[o] += zn;
-    } else {
-        const int j2 = p.pair_j[pr];
-        const size_t o2 = (size_t)j2 * p.Bp + b;
-        const double z1 = p.z[o], z2 = p.z[o2];
-        double a = z1 - tau * grad(j), c2 = z2 - tau * grad(j2);
-        const double r = hypot(a, c2), rho = p.rho[(size_t)pr * p.Bp + b];
-        if (r > rho) {
-            const double s = rho / r;
-            a *= s;
-            c2 *= s;
-        }
-        p.z[o] = a; p.z[o2] = c2;
-        p.zbar[o] = 2.0 * a - z1; p.zbar[o2] = 2.0 * c2 - z2;
-        p.zs[o] += a; p.zs[o2] += c2;
+        return fabs(zb);
     }
+    const int j2 = p.pair_j[pr];
+    const size_t o2 = (size_t)j2 * p.Bp + b;
+    const double z1 = p.z[o], z2 = p.z[o2];
+    double a = z1 - tau * grad(j), c2 = z2 - tau * grad(j2);
+    const double r = hypot(a, c2), rho = p.rho[(size_t)pr * p.Bp + b];
+    if (r > rho) {
+        const double s = rho / r;
+        a *= s;
+        c2 *= s;
+    }
+    const double zb1 = 2.0 * a - z1, zb2 = 2.0 * c2 - z2;
+    p.z[o] = a; p.z[o2] = c2;
+    p.zbar[o] = zb1; p.zbar[o2] = zb2;
+    p.zs[o] += a; p.zs[o2] += c2;
+    return fmax(fabs(zb1), fabs(zb2));
 }
-
-// v = y + sigma S;  y+ = v - sigma clip(v/sigma, lo, hi);  ys += y+
-__global__ void y_update_kernel(Problem p)
+__global__ void z_update_kernel(Problem p)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)p.Mp * p.Bp) return;
     const int b = (int)(idx % p.Bp);
-    const int row = (int)(idx / p.Bp);
-    if (row >= p.srow0 && row < p.srow0 + p.ns) return;   // simplex block: simplex_update_kernel
-    if (row >= p.grow0 && row < p.grow0 + 2 * p.ng) return;   // group block: group_update_kernel
+    const int j = (int)(idx / p.Bp);
+    if (j >= p.Np) return;
+    z_update_elem(p, j, b);
+}
+// Batches of >= 64 designs: a CTA owns 64 designs (tx) and strides the coordinates (ty, blockIdx.y), so that the per-design
+// max |zbar| the tcgen05 digit planes need costs one shared-memory reduction and one atomic per design and CTA.
+__global__ void __launch_bounds__(256) z_update_wide_kernel(Problem p)
+{
+    __shared__ double sh[4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int b = blockIdx.x * 64 + tx;
+    double m = 0.0;
+    for (int j = blockIdx.y * 4 + ty; j < p.Np; j += 4 * gridDim.y) m = fmax(m, z_update_elem(p, j, b));
+    if (!p.mxz) return;
+    sh[ty][tx] = m;
+    __syncthreads();
+    if (ty == 0) atomic_max_pos(p.mxz + b, fmax(fmax(sh[0][tx], sh[1][tx]), fmax(sh[2][tx], sh[3][tx])));
+}
+
+// v = y + sigma S;  y+ = v - sigma clip(v/sigma, lo, hi);  ys += y+.  Returns max |y+| written.
+__device__ __forceinline__ double y_update_elem(const Problem &p, int row, int b, long long idx)
+{
+    if (row >= p.srow0 && row < p.srow0 + p.ns) return 0.0;   // simplex block: simplex_update_kernel
+    if (row >= p.grow0 && row < p.grow0 + 2 * p.ng) return 0.0;   // group block: group_update_kernel
     const double sig = p.ctl[b].sigma;
     if (row >= p.drow0 && row < p.drow0 + 2 * p.nd) {     // disk pair: y+ = v - sigma * P_disk(v / sigma)
-        if ((row - p.drow0) & 1) return;                  // the first row of the pair does both
+        if ((row - p.drow0) & 1) return 0.0;              // the first row of the pair does both
         const long long i2 = idx + p.Bp;
         const double v1 = p.y[idx] + sig * p.S[idx], v2 = p.y[i2] + sig * p.S[i2];
         const double c1 = p.lo[idx], c2 = p.lo[i2], R = p.hi[idx];
@@ -429,7 +448,7 @@ __global__ void y_update_kernel(Problem p)
         }
         p.y[idx] = y1; p.y[i2] = y2;
         p.ys[idx] += y1; p.ys[i2] += y2;
-        return;
+        return fmax(fabs(y1), fabs(y2));
     }
     const double v = p.y[idx] + sig * p.S[idx];
     const double w = v / sig, lo = p.lo[idx], hi = p.hi[idx];
@@ -437,6 +456,57 @@ __global__ void y_update_kernel(Problem p)
     const double yn = w > hi ? v - sig * hi : (w < lo ? v - sig * lo : 0.0);
     p.y[idx] = yn;
     p.ys[idx] += yn;
+    return fabs(yn);
+}
+__global__ void y_update_kernel(Problem p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.Mp * p.Bp) return;
+    y_update_elem(p, (int)(idx / p.Bp), (int)(idx % p.Bp), idx);
+}
+// wide batches: see z_update_wide_kernel.  Four rows per thread and pass, all loads issued before the first store
+// (the arrays never alias, which the compiler cannot know through the Problem struct), plain interval rows inline.
+__global__ void __launch_bounds__(256) y_update_wide_kernel(Problem p)
+{
+    __shared__ double sh[4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int b = blockIdx.x * 64 + tx;
+    const int step = 4 * gridDim.y;
+    const double sig = p.ctl[b].sigma;
+    double m = 0.0;
+    for (int row = blockIdx.y * 4 + ty; row < p.Mp; row += 4 * step) {
+        double y[4], S[4], lo[4], hi[4], ys[4];
+        bool plain[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = row + u * step;
+            plain[u] = r < p.Mp && !(r >= p.srow0 && r < p.srow0 + p.ns) && !(r >= p.grow0 && r < p.grow0 + 2 * p.ng) &&
+                       !(r >= p.drow0 && r < p.drow0 + 2 * p.nd);
+            if (plain[u]) {
+                const size_t o = (size_t)r * p.Bp + b;
+                y[u] = p.y[o]; S[u] = p.S[o]; lo[u] = p.lo[o]; hi[u] = p.hi[o]; ys[u] = p.ys[o];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = row + u * step;
+            if (plain[u]) {
+                const size_t o = (size_t)r * p.Bp + b;
+                const double v = y[u] + sig * S[u];
+                const double w = v / sig;
+                const double yn = w > hi[u] ? v - sig * hi[u] : (w < lo[u] ? v - sig * lo[u] : 0.0);
+                p.y[o] = yn;
+                p.ys[o] = ys[u] + yn;
+                m = fmax(m, fabs(yn));
+            } else if (r < p.Mp) {
+                m = fmax(m, y_update_elem(p, r, b, (long long)r * p.Bp + b));
+            }
+        }
+    }
+    if (!p.mxy) return;
+    sh[ty][tx] = m;
+    __syncthreads();
+    if (ty == 0) atomic_max_pos(p.mxy + b, fmax(fmax(sh[0][tx], sh[1][tx]), fmax(sh[2][tx], sh[3][tx])));
 }
 
 // The term  w * max_{i in stop rows} (K z)_i  of the objective (fir_ap_cvx.m:163-165: obj*ripple_stop with
@@ -445,7 +515,71 @@ __global__ void y_update_kernel(Problem p)
 // never appears as a variable (it is the multiplier of the simplex constraint; its value is max_i (K z)_i).
 // Rows of the block that do not belong to a design (hi = +inf) keep y = 0.  One warp per design; Michelot's
 // fixed-point iteration  theta <- (sum_{v > theta} v - w) / #{v > theta}  (monotone, finite).
+// Blocks of up to 32*R rows (the stop band of fir_ap_cvx has ~120): one warp per design keeps its rows in registers, so
+// the Michelot passes are shuffles only instead of dependent global re-reads (the general kernel below is latency-bound).
+template <int R>
+__global__ void __launch_bounds__(256) simplex_update_reg_kernel(Problem p)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= p.Bp) return;
+    const double sig = p.ctl[b].sigma, w = p.sw[b];
+    double v[R], ys[R];
+    double sum = 0.0;
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        const int i = lane + 32 * u;
+        v[u] = -INFINITY;
+        ys[u] = 0.0;
+        if (i < p.ns) {
+            const size_t o = (size_t)(p.srow0 + i) * p.Bp + b;
+            ys[u] = p.ys[o];
+            if (p.hi[o] == 0.0) v[u] = p.y[o] + sig * p.S[o];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u)
+        if (v[u] > -INFINITY) { sum += v[u]; ++cnt; }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, k); cnt += __shfl_xor_sync(0xffffffffu, cnt, k); }
+    double theta = cnt > 0 ? (sum - w) / cnt : 0.0;
+    if (cnt > 0 && w > 0.0) {
+        int prev = cnt;
+        for (int pass = 0; pass < 64; ++pass) {
+            double s2 = 0.0;
+            int c2 = 0;
+#pragma unroll
+            for (int u = 0; u < R; ++u)
+                if (v[u] > theta) { s2 += v[u]; ++c2; }
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, k); c2 += __shfl_xor_sync(0xffffffffu, c2, k); }
+            if (c2 == 0) break;
+            theta = (s2 - w) / c2;
+            if (c2 == prev) break;
+            prev = c2;
+        }
+    }
+    double m = 0.0;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        const int i = lane + 32 * u;
+        if (i < p.ns) {
+            const size_t o = (size_t)(p.srow0 + i) * p.Bp + b;
+            const double yn = (w > 0.0 && v[u] > theta) ? v[u] - theta : 0.0;
+            p.y[o] = yn;
+            p.ys[o] = ys[u] + yn;
+            m = fmax(m, yn);
+        }
+    }
+    if (p.mxy) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+        if (lane == 0) atomic_max_pos(p.mxy + b, m);
+    }
+}
 __global__ void simplex_update_kernel(Problem p)
+
 {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -484,12 +618,19 @@ __global__ void simplex_update_kernel(Problem p)
             prev = c2;
         }
     }
+    double m = 0.0;
     for (int i = lane; i < p.ns; i += 32) {
         const size_t o = (size_t)(p.srow0 + i) * p.Bp + b;
         const double v = p.y[o];
         const double yn = (w > 0.0 && v > theta) ? v - theta : 0.0;
         p.y[o] = yn;
         p.ys[o] += yn;
+        m = fmax(m, yn);
+    }
+    if (p.mxy) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+        if (lane == 0) atomic_max_pos(p.mxy + b, m);
     }
 }
 
@@ -531,6 +672,7 @@ __global__ void group_update_kernel(Problem p)
             prev = c2;
         }
     }
+    double m = 0.0;
     for (int i = lane; i < p.ng; i += 32) {
         const size_t o = (size_t)(p.grow0 + 2 * i) * p.Bp + b;
         double v1 = p.y[o], v2 = p.y[o + p.Bp];
@@ -542,6 +684,12 @@ __global__ void group_update_kernel(Problem p)
         if (!(w > 0.0)) { v1 = 0.0; v2 = 0.0; }
         p.y[o] = v1; p.y[o + p.Bp] = v2;
         p.ys[o] += v1; p.ys[o + p.Bp] += v2;
+        m = fmax(m, fmax(fabs(v1), fabs(v2)));
+    }
+    if (p.mxy) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+        if (lane == 0) atomic_max_pos(p.mxy + b, m);
     }
 }
 
@@ -804,22 +952,98 @@ static inline int up(int v, int a) { return (v + a - 1) / a * a; }
 static inline int batch_width(int b) { return b <= 1 ? 1 : b <= 2 ? 2 : b <= 4 ? 4 : b <= 8 ? 8 : up(b, 64); }
 
 static double g_opt[5] = {0.9, 0.2, 0.8, 0.36, 0.5};   // eta factor, beta_suff, beta_nec, beta_art, omega_theta
-static int g_use_dmma = 1;   // 1: mma.sync m8n8k4 f64 tiles, 0: SIMT DFMA tiles (mbrf_pdhg_set_gemm)
+// product kernels of the iterations (mbrf_pdhg_set_gemm): 2 = tcgen05 int8 split-integer tiles (tc_gemm.cuh), 1 = FP64
+// tensor path mma.sync m8n8k4, 0 = SIMT DFMA tiles.  The convergence checks always use an fp64 kernel (1 unless 0).
+static int g_gemm_mode = 2;
+static int g_tc_digits = 6;  // digit planes / level accumulators of the split-integer product (4..6)
 
-static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st)   // C[Mp x Bp] = K X
+// digit planes, scales and tensor maps of the tcgen05 path (device memory lives in the caller's workspace)
+struct TcState {
+    bool on = false;
+    int nd = 0;
+    int8_t *pK = nullptr, *pKT = nullptr, *pX = nullptr;   // [nd][Mp][Np], [nd][Np][Mp], [nd][Bp][max(Mp,Np)]
+    double *saK = nullptr, *saKT = nullptr, *sx = nullptr, *mxy = nullptr, *mxz = nullptr;   // mx*: per-design max |iterate|
+    CUtensorMap mK, mKT, mXn, mXm;                           // X maps: reduction over Np (K zbar) / over Mp (K^T y)
+    int P = 1;                                               // split-K slabs of K^T y on this path
+};
+
+static size_t tc_bytes(int Mp, int Np, int Bp)
+{
+    if (Bp < 64) return 0;
+    const size_t mxd = (size_t)(Mp > Np ? Mp : Np);
+    return (size_t)tc::MAX_ND * (2 * (size_t)Mp * Np + (size_t)Bp * mxd) + ((size_t)Mp + Np + 3 * (size_t)Bp) * 8 + 4 * 256;
+}
+static int split_k_tc(int Mp, int Np, int Bp)
+{
+    const int tiles = ((Np + tc::TM - 1) / tc::TM) * (Bp / tc::TN);
+    int P = (2 * 148) / tiles;              // two full waves of one CTA per SM
+    if (P > Mp / 256) P = Mp / 256;
+    if (P > 32) P = 32;
+    if (P < 1) P = 1;
+    return P;
+}
+
+// mx: per-design max |X| ([Bp]); have_max: already accumulated by the kernel that produced X, otherwise computed here.
+// zero_other: the other iterate's max-accumulator, cleared for its next producer.
+template <int ND>
+static int tc_product_nd(const TcState &t, const double *X, int kdim, int Bp, const CUtensorMap &mA, const CUtensorMap &mX,
+                         const double *sa, int R, double *C, int P, long long slab, double *mx, bool have_max,
+                         double *zero_other, cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) {
+        MBRF_CUDA(cudaFuncSetAttribute(tc::tc_i8_gemm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(ND)));
+        attr = true;
+    }
+    if (!have_max) {
+        MBRF_CUDA(cudaMemsetAsync(mx, 0, (size_t)Bp * 8, st));
+        int gy = kdim / 64;
+        if (gy > 64) gy = 64;
+        tc::col_absmax_kernel<<<dim3(Bp / 64, gy), 256, 0, st>>>(X, kdim, Bp, mx);
+        MBRF_LAUNCH_CHECK();
+    }
+    tc::slice_cols_kernel<ND><<<dim3(Bp / 64, kdim / 64), 256, 0, st>>>(X, kdim, Bp, mx, t.pX, t.sx, zero_other);
+    MBRF_LAUNCH_CHECK();
+    tc::Params q;
+    q.C = C; q.slab = slab; q.ldc = Bp; q.R = R; q.kdim_total = kdim;
+    q.kchunk = up((kdim + P - 1) / P, tc::KB); q.sa = sa; q.sx = t.sx;
+    tc::tc_i8_gemm_kernel<ND><<<dim3(Bp / tc::TN, (R + tc::TM - 1) / tc::TM, P), tc::THREADS, tc::smem_bytes(ND), st>>>(mA, mX, q);
+    MBRF_LAUNCH_CHECK();
+    return MBRF_OK;
+}
+template <typename... Args>
+static int tc_product(const TcState &t, Args... args)
+{
+    switch (t.nd) {
+    case 4: return tc_product_nd<4>(t, args...);
+    case 5: return tc_product_nd<5>(t, args...);
+    default: return tc_product_nd<6>(t, args...);
+    }
+}
+template <int ND>
+static void tc_slice_rows(const double *A, int ld, int R, int kdim, int8_t *out, double *sa, cudaStream_t st)
+{
+    tc::slice_rows_kernel<ND><<<(unsigned)(((size_t)R * 32 + 255) / 256), 256, 0, st>>>(A, ld, R, kdim, out, sa);
+}
+
+// C[Mp x Bp] = K X.  tcs != null: iteration path (may run on the tcgen05 tiles); null: fp64 kernels (checks, power iteration)
+static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st, const TcState *tcs = nullptr, bool have_max = false)
 {
     if (p.Bp <= 8) {   // thin batch (1..8 designs): one pass over K^T, bound by streaming the matrix
         launch_thin(p.Bp, dim3(p.Mp / 64, 1), st, p.KT, p.Mp, X, C, p.Np, p.Np, 0LL);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     }
+    if (tcs && tcs->on)
+        return tc_product(*tcs, X, p.Np, p.Bp, tcs->mK, tcs->mXn, tcs->saK, p.Mp, C, 1, 0LL, tcs->mxz, have_max, tcs->mxy, st);
     dim3 grid(p.Bp / BN, p.Mp / BM, 1);
-    if (g_use_dmma) dgemm_mma_kernel<<<grid, 128, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
+    if (g_gemm_mode) dgemm_mma_kernel<<<grid, 128, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
     else dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.KT, p.Mp, X, p.Bp, C, p.Np, p.Np, 0);
     MBRF_LAUNCH_CHECK();
     return MBRF_OK;
 }
-static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st)   // G[P][Np x Bp] = K^T Y
+// G[p.P][Np x Bp] = K^T Y (p.P split-K slabs)
+static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st, const TcState *tcs = nullptr, bool have_max = false)
 {
     if (p.Bp <= 8) {   // thin batch: one pass over K, the long reduction split into p.P slabs
         const int kc = up((p.Mp + p.P - 1) / p.P, 64);
@@ -827,9 +1051,12 @@ static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     }
+    if (tcs && tcs->on)
+        return tc_product(*tcs, Y, p.Mp, p.Bp, tcs->mKT, tcs->mXm, tcs->saKT, p.Np, G, p.P, (long long)p.Np * p.Bp, tcs->mxy,
+                          have_max, tcs->mxz, st);
     const int kchunk = up((p.Mp + p.P - 1) / p.P, BK);
     dim3 grid(p.Bp / BN, p.Np / BM, p.P);
-    if (g_use_dmma) dgemm_mma_kernel<<<grid, 128, 0, st>>>(p.K, p.ldk, Y, p.Bp, G, p.Mp, kchunk, (long long)p.Np * p.Bp);
+    if (g_gemm_mode) dgemm_mma_kernel<<<grid, 128, 0, st>>>(p.K, p.ldk, Y, p.Bp, G, p.Mp, kchunk, (long long)p.Np * p.Bp);
     else dgemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(p.K, p.ldk, Y, p.Bp, G, p.Mp, kchunk, (long long)p.Np * p.Bp);
     MBRF_LAUNCH_CHECK();
     return MBRF_OK;
@@ -843,10 +1070,19 @@ using namespace mbrf::pdhg;
 
 extern "C" {
 
-// choose the GEMM tile kernel: 1 = FP64 tensor path (mma.sync m8n8k4), 0 = SIMT DFMA
-int mbrf_pdhg_set_gemm(int use_dmma)
+// choose the product kernels of the iterations: 2 = tcgen05 int8 split-integer tiles (default), 1 = FP64 tensor path
+// (mma.sync m8n8k4), 0 = SIMT DFMA
+int mbrf_pdhg_set_gemm(int mode)
 {
-    g_use_dmma = use_dmma ? 1 : 0;
+    if (mode < 0 || mode > 2) return MBRF_EINVAL;
+    g_gemm_mode = mode;
+    return MBRF_OK;
+}
+// digit planes of the split-integer product: 4, 5 or 6 (default 6: ~1e-12 of |row|max * |column|max per term)
+int mbrf_pdhg_set_tc_digits(int nd)
+{
+    if (nd < 4 || nd > tc::MAX_ND) return MBRF_EINVAL;
+    g_tc_digits = nd;
     return MBRF_OK;
 }
 
@@ -891,7 +1127,9 @@ static size_t slab_doubles(int Mp, int Np, int Bp)
 {
     size_t mx = (size_t)split_k(Mp, Np, 8) * Np * 8;
     for (int b = 64; b <= Bp; b += 64) {
-        const size_t v = (size_t)split_k(Mp, Np, b) * Np * b;
+        size_t v = (size_t)split_k(Mp, Np, b) * Np * b;
+        const size_t vt = (size_t)split_k_tc(Mp, Np, b) * Np * b;
+        if (vt > v) v = vt;
         if (v > mx) mx = v;
     }
     return mx;
@@ -901,7 +1139,7 @@ unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp)
 {
     const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
     size_t d = 5 * zn + 4 * yn + yn + slab_doubles(Mp, Np, Bp) + zn + 2 * NACC * (size_t)Bp + 4 * (size_t)Bp;
-    return d * 8 + (size_t)Bp * sizeof(Ctl) + 256 + (size_t)Np * 4 + 2 * (size_t)Bp * 4 + 128;
+    return d * 8 + (size_t)Bp * sizeof(Ctl) + 256 + (size_t)Np * 4 + 2 * (size_t)Bp * 4 + 128 + 512 + tc_bytes(Mp, Np, Bp);
 }
 
 /*
@@ -943,7 +1181,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     Problem p;
     p.Mp = Mp; p.Np = Np; p.Bp = Bp; p.B = B; p.npairs = npairs; p.ldk = ldk; p.K = K; p.KT = KT;
     p.c = c; p.lo = lo; p.hi = hi; p.bl = bl; p.bu = bu; p.rho = rho; p.pair_i = pair_i; p.pair_j = pair_j;
-    p.obj_upper = obj_upper; p.P = split_k(Mp, Np, Bp);
+    p.obj_upper = obj_upper; p.P = split_k(Mp, Np, Bp); p.mxy = p.mxz = nullptr;
     p.srow0 = ns > 0 ? srow0 : 0; p.ns = ns; p.sw = ns > 0 ? simplex_w : nullptr;
     p.drow0 = bk.disk_pairs > 0 ? bk.disk_row0 : 0; p.nd = bk.disk_pairs;
     p.grow0 = bk.group_pairs > 0 ? bk.group_row0 : 0; p.ng = bk.group_pairs; p.gw = bk.group_pairs > 0 ? bk.group_w : nullptr;
@@ -963,6 +1201,45 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     int *pair_of = (int *)w;
     p.pair_of = pair_of;
     int *d_slot = pair_of + Np, *d_orig = d_slot + Bp;   // compaction maps
+
+    // ---- tcgen05 path: digit planes of K and K^T (once), buffers for the iterate's planes ----
+    TcState tcs;
+    auto tc_setup_width = [&]() -> int {   // (re)build what depends on the batch width p.Bp
+        if (!tcs.on) return MBRF_OK;
+        if (p.Bp < 64) { tcs.on = false; p.mxy = p.mxz = nullptr; p.P = split_k(p.Mp, p.Np, p.Bp); return MBRF_OK; }
+        if (!tc::make_map(&tcs.mXn, tcs.pX, p.Np, p.Bp, tcs.nd, tc::TN) || !tc::make_map(&tcs.mXm, tcs.pX, p.Mp, p.Bp, tcs.nd, tc::TN)) {
+            set_error("pdhg: cuTensorMapEncodeTiled failed for the iterate planes");
+            return MBRF_ECUDA;
+        }
+        p.P = split_k_tc(p.Mp, p.Np, p.Bp);
+        p.mxy = tcs.mxy; p.mxz = tcs.mxz;
+        return MBRF_OK;
+    };
+    if (g_gemm_mode == 2 && Bp >= 64) {
+        char *t = (char *)(((uintptr_t)(d_orig + Bp) + 255) & ~(uintptr_t)255);
+        const size_t plane = (size_t)Mp * Np, mxd = (size_t)(Mp > Np ? Mp : Np);
+        tcs.nd = g_tc_digits;
+        tcs.pK = (int8_t *)t; t += tc::MAX_ND * plane;
+        tcs.pKT = (int8_t *)t; t += tc::MAX_ND * plane;
+        tcs.pX = (int8_t *)t; t += (size_t)tc::MAX_ND * Bp * mxd;
+        t = (char *)(((uintptr_t)t + 255) & ~(uintptr_t)255);
+        tcs.saK = (double *)t; t += (size_t)Mp * 8;
+        tcs.saKT = (double *)t; t += (size_t)Np * 8;
+        tcs.sx = (double *)t; t += (size_t)Bp * 8;
+        tcs.mxy = (double *)t; t += (size_t)Bp * 8;
+        tcs.mxz = (double *)t;
+        switch (tcs.nd) {
+        case 4: tc_slice_rows<4>(K, ldk, Mp, Np, tcs.pK, tcs.saK, st); tc_slice_rows<4>(KT, Mp, Np, Mp, tcs.pKT, tcs.saKT, st); break;
+        case 5: tc_slice_rows<5>(K, ldk, Mp, Np, tcs.pK, tcs.saK, st); tc_slice_rows<5>(KT, Mp, Np, Mp, tcs.pKT, tcs.saKT, st); break;
+        default: tc_slice_rows<6>(K, ldk, Mp, Np, tcs.pK, tcs.saK, st); tc_slice_rows<6>(KT, Mp, Np, Mp, tcs.pKT, tcs.saKT, st); break;
+        }
+        MBRF_LAUNCH_CHECK();
+        if (!tc::make_map(&tcs.mK, tcs.pK, Np, Mp, tcs.nd, tc::TM) || !tc::make_map(&tcs.mKT, tcs.pKT, Mp, Np, tcs.nd, tc::TM)) {
+            set_error("pdhg: cuTensorMapEncodeTiled failed for the matrix planes");
+            return MBRF_ECUDA;
+        }
+        tcs.on = true;
+    }
 
     // ---- init state ----
     MBRF_CUDA(cudaMemsetAsync(workspace, 0, (char *)pair_of - (char *)workspace, st));
@@ -1012,6 +1289,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         MBRF_CUDA(cudaMemsetAsync(p.G, 0, slab_doubles(Mp, Np, Bp) * 8, st));
         MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)Bp * 8, st));
     }
+    if (int rc = tc_setup_width()) return rc;
     p.eta = g_opt[0] / sqrt(knorm2);
     p.beta_suff = g_opt[1]; p.beta_nec = g_opt[2]; p.beta_art = g_opt[3]; p.omega_theta = g_opt[4];
     {
@@ -1035,23 +1313,32 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     unsigned gz = (unsigned)((zn + TPB - 1) / TPB), gy = (unsigned)((yn + TPB - 1) / TPB);
     dim3 gm((Bp + 63) / 64, 64);
 
-    auto iteration = [&]() -> int {
-        if (int rc = gemm_tn(p, p.y, p.G, st)) return rc;
+    // first: first iteration of a block -- y may have been replaced by a restart or a compaction since the last y-update,
+    // so its per-design max is recomputed; afterwards the update kernels keep the maxima current.
+    auto iteration = [&](bool first) -> int {
+        const bool wide = p.Bp >= 64;
+        if (int rc = gemm_tn(p, p.y, p.G, st, &tcs, !first)) return rc;
         if (p.nn > 0) {
             MBRF_CUDA(cudaMemsetAsync(p.nrm, 0, (size_t)p.Bp * 8, st));
             z_hat_kernel<<<dim3((p.Bp + 63) / 64, 16), 64, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
             z_shrink_kernel<<<gz, TPB, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
+        } else if (wide) {
+            z_update_wide_kernel<<<dim3(p.Bp / 64, 32), 256, 0, st>>>(p);
+            MBRF_LAUNCH_CHECK();
         } else {
             z_update_kernel<<<gz, TPB, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
         }
-        if (int rc = gemm_nn(p, p.zbar, p.S, st)) return rc;
-        y_update_kernel<<<gy, TPB, 0, st>>>(p);
+        if (int rc = gemm_nn(p, p.zbar, p.S, st, &tcs, p.nn == 0 && wide)) return rc;
+        if (wide) y_update_wide_kernel<<<dim3(p.Bp / 64, 128), 256, 0, st>>>(p);
+        else y_update_kernel<<<gy, TPB, 0, st>>>(p);
         MBRF_LAUNCH_CHECK();
         if (p.ns > 0) {
-            simplex_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
+            if (p.ns <= 128) simplex_update_reg_kernel<4><<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
+            else if (p.ns <= 256) simplex_update_reg_kernel<8><<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
+            else simplex_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
         }
         if (p.ng > 0) {
@@ -1064,12 +1351,14 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)p.Bp * 8, st));
         advance_kernel<<<(p.Bp + 63) / 64, 64, 0, st>>>(p);
         MBRF_LAUNCH_CHECK();
+        Problem pc = p;                      // the checks run on the fp64 kernels with their own split-K
+        pc.P = split_k(p.Mp, p.Np, p.Bp);
         for (int cand = 0; cand < 2; ++cand) {
-            if (int rc = gemm_nn(p, cand == 0 ? p.zs : p.z, p.S, st)) return rc;
+            if (int rc = gemm_nn(pc, cand == 0 ? p.zs : p.z, p.S, st)) return rc;
             row_metrics_kernel<<<gm, 64, 0, st>>>(p, cand);
             MBRF_LAUNCH_CHECK();
-            if (int rc = gemm_tn(p, cand == 0 ? p.ys : p.y, p.G, st)) return rc;
-            reduce_slabs_kernel<<<gz, TPB, 0, st>>>(p);
+            if (int rc = gemm_tn(pc, cand == 0 ? p.ys : p.y, p.G, st)) return rc;
+            reduce_slabs_kernel<<<gz, TPB, 0, st>>>(pc);
             MBRF_LAUNCH_CHECK();
             col_metrics_kernel<<<gm, 64, 0, st>>>(p, cand);
             MBRF_LAUNCH_CHECK();
@@ -1096,7 +1385,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         use_graph = true;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int rc = MBRF_OK;
-            for (int i = 0; i < check_every && rc == MBRF_OK; ++i) rc = iteration();
+            for (int i = 0; i < check_every && rc == MBRF_OK; ++i) rc = iteration(i == 0);
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             if (rc != MBRF_OK || e != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) use_graph = false;
         } else {
@@ -1174,6 +1463,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         p.B = keep;
         p.Bp = nBp;
         p.P = split_k(p.Mp, p.Np, nBp);
+        if (int rc = tc_setup_width()) return rc;
         gz = (unsigned)(((size_t)p.Np * nBp + TPB - 1) / TPB);
         gy = (unsigned)(((size_t)p.Mp * nBp + TPB - 1) / TPB);
         gm = dim3((nBp + 63) / 64, 64);
@@ -1186,9 +1476,9 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     for (int it = 0; it < max_iter && active > 0 && rcode == MBRF_OK;) {
         if (use_graph) {
             if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("pdhg: graph launch failed"); rcode = MBRF_ECUDA; break; }
-            g_launches.fetch_add((4ull + (p.ns > 0) + (p.ng > 0) + (p.nn > 0)) * check_every, std::memory_order_relaxed);
+            g_launches.fetch_add((4ull + (tcs.on ? 2 : 0) + (p.ns > 0) + (p.ng > 0) + (p.nn > 0)) * check_every, std::memory_order_relaxed);
         } else {
-            for (int i = 0; i < check_every && rcode == MBRF_OK; ++i) rcode = iteration();
+            for (int i = 0; i < check_every && rcode == MBRF_OK; ++i) rcode = iteration(i == 0);
         }
         it += check_every;
         if (rcode == MBRF_OK) rcode = check(it);

@@ -1,15 +1,24 @@
-// tcgen05 (5th-gen tensor core) GEMM tile for the PDHG products, 3xTF32 split precision.
+// tcgen05 (5th-generation tensor core) product for the batched PDHG iterations: split-integer ("Ozaki") GEMM.
 //
-//   C[R x Bp] (fp64) = AT^T * X,   AT: [kdim x R] fp32,  X: [kdim x Bp] fp32, both k-major exactly like the fp64
-//   kernels (the output index is the contiguous one), each given as a tf32-exact "hi" part and a tf32 "lo"
-//   remainder:   a*x ~= a_hi*x_hi + a_hi*x_lo + a_lo*x_hi     (the dropped a_lo*x_lo term is ~2^-22 relative)
+//   C[R x Bp] (fp64) = A * X,    A: [R x kdim] fp64 (K or K^T, fixed per solve),  X: [kdim x Bp] fp64 (the iterate)
 //
-// One CTA computes a 128 x 128 output tile: accumulators live in TMEM (128 lanes x 128 fp32 columns); operand
-// tiles of 32 k-rows arrive by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, boxes of 32 k x 32 outputs = 4 KB) into a
-// 3-stage shared-memory ring; one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8, both operands
-// MN-major), tcgen05.commit releases ring slots and finally signals the epilogue warps, which read the
-// accumulator with tcgen05.ld (32 lanes x 32 columns per instruction) and store it widened to fp64.
+// tcgen05.mma has no fp64 kind, and an fp32-accumulate product is at the level of the residuals PDHG has to drive down
+// (DESIGN.md section 6).  The int8 kind accumulates in int32 EXACTLY, so the product is rebuilt from integer digits:
+//   every row of A and every column of X is scaled by a power of two to |.| <= 1 and written as signed base-128 digits
+//       a / alpha_r = (1/64) * sum_s A_s * 128^-s ,   A_s in [-64, 64]                       (x likewise, beta_b, X_t)
+//   C_rb = alpha_r beta_b / 4096 * sum_d 128^-d * sum_{s+t=d} (A_s X_t)_rb ,   d < ND
+// The level sums  sum_{s+t=d} A_s X_t  are exact int32 GEMMs (|.| <= (d+1) * 4096 * kdim < 2^31) that share one TMEM
+// accumulator per level; dropping the levels d >= ND leaves a relative error of about (ND+1) * 2^(-7 ND) of
+// alpha_r * beta_b per term (ND = 6: 3e-12) — set by ND, not by the tensor core.
+//
+// One CTA computes a 128 x 64 output tile: ND accumulators of 64 int32 columns in TMEM; digit tiles of KB = 64 k-values
+// (all ND digit planes of A: 128 rows, and of X: 64 columns) arrive with two 3-D TMA copies per stage (64-byte swizzle)
+// in a 3-stage shared-memory ring; one elected thread issues ND(ND+1)/2 tcgen05.mma.kind::i8 (M=128, N=64, K=32, both
+// operands K-major) per 32 k-values; tcgen05.commit frees ring slots and finally signals the four epilogue warps, which
+// read the level accumulators with tcgen05.ld, combine them in fp64 (Horner in 1/128, exact) and store scaled doubles.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = epilogue (TMEM lane quarter = warp % 4).
+// Descriptor encodings were brought up with tools/microbench/tc_dbg.cu (MN-major tf32 operands return zeros on this
+// part, K-major operands are exact: hence the transposed digit planes).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -18,17 +27,19 @@
 namespace mbrf {
 namespace tc {
 
-constexpr int TM = 128, TN = 128, TBK = 32, STAGES = 3, THREADS = 192;
-constexpr int OP_BYTES = TBK * 128 * 4;            // one operand tile: 32 k-rows x 128 outputs x fp32 = 16 KB
-constexpr int STAGE_BYTES = 4 * OP_BYTES;          // A_hi, A_lo, X_hi, X_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TM = 128, TN = 64, KB = 64, STAGES = 3, THREADS = 192;
+constexpr int MAX_ND = 6;
+constexpr int stage_bytes(int nd) { return nd * (TM + TN) * KB; }
+constexpr int smem_bytes(int nd) { return STAGES * stage_bytes(nd) + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct Params {
-    double *C;          // [R x ldc] fp64, slab blockIdx.z at C + z*slab
+    double *C;                // [R x ldc] fp64, slab blockIdx.z at C + z*slab
     long long slab;
     int ldc;
-    int kdim_total, kchunk;   // reduction range of slab z: [z*kchunk, min(kdim_total, (z+1)*kchunk)), multiples of TBK
-    int passes;               // 3: split precision (hi/lo), 1: plain tf32 (tests)
+    int R;                    // valid output rows (rows >= R of a tile are not stored)
+    int kdim_total, kchunk;   // reduction range of slab z: [z*kchunk, min(kdim_total, (z+1)*kchunk)), multiples of KB
+    const double *sa;         // [R]   alpha_r / 64
+    const double *sx;         // [ldc] beta_b / 64
 };
 
 #ifdef __CUDACC__
@@ -48,36 +59,45 @@ __device__ __forceinline__ void bar_wait(uint64_t *b, unsigned parity)
         "{\n\t.reg .pred p;\n\tTCW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TCD;\n\tbra TCW;\n\tTCD:\n\t}"
         ::"r"(s32(b)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c_inner, int c_outer)
+__device__ __forceinline__ void tma_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(s32(dst)), "l"((uint64_t)map), "r"(s32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(s32(dst)), "l"((uint64_t)map), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// shared-memory matrix descriptor, MN-major, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1):
-// blocks of 32 outputs (128 B) are `lbo` bytes apart, groups of 8 k-rows are `sbo` bytes apart.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1), K-major, 64-byte swizzle: rows of 64 bytes,
+// groups of 8 rows are 512 bytes apart (stride byte offset); the leading byte offset is unused for swizzled K-major.
+__device__ __forceinline__ uint64_t smem_desc_k64(uint32_t addr)
 {
-    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(16 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+           (4ull << 61);
 }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
-
-__global__ void __launch_bounds__(THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
-               const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtensorMap mXl, const Params p)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&r)[8])
 {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+
+template <int ND>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_i8_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mX, const Params p)
+{
+    constexpr int STAGE = ND * (TM + TN) * KB;
+    constexpr int A_PLANE = TM * KB, X_PLANE = TN * KB;           // bytes of one digit plane in a stage
+    constexpr uint32_t TMEM_COLS = ND * TN <= 256 ? 256u : 512u;  // power of two >= ND accumulators of TN columns
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms need 1024-B alignment
-    uint64_t *full = (uint64_t *)(smem + STAGES * STAGE_BYTES);
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms need aligned planes
+    uint64_t *full = (uint64_t *)(smem + STAGES * STAGE);
     uint64_t *empty = full + STAGES;
     uint64_t *accf = empty + STAGES;
     uint32_t *tmem_slot = (uint32_t *)(accf + 1);
@@ -86,15 +106,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
     const int k_begin = blockIdx.z * p.kchunk;
     const int k_end = min(p.kdim_total, k_begin + p.kchunk);
-    const int nk = (k_end - k_begin) / TBK;
+    const int nk = k_end > k_begin ? (k_end - k_begin) / KB : 0;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
         bar_init(accf, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: 128 columns (power of two >= 32) for the 128 x 128 fp32 accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s32(tmem_slot)) : "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -103,79 +123,73 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ---------------- TMA producer ----------------
+        // ---------------- TMA producer: all digit planes of a k-block with one copy per operand ----------------
         for (int it = 0; it < nk; ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             bar_wait(&empty[s], ph ^ 1);
-            uint8_t *st = smem + s * STAGE_BYTES;
-            bar_expect(&full[s], p.passes == 3 ? 4 * OP_BYTES : 2 * OP_BYTES);
-            const int k0 = k_begin + it * TBK;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {   // four 32-output blocks per operand tile
-                tma_2d(&mAh, &full[s], st + 0 * OP_BYTES + b * 4096, row0 + b * 32, k0);
-                tma_2d(&mXh, &full[s], st + 2 * OP_BYTES + b * 4096, col0 + b * 32, k0);
-                if (p.passes == 3) {
-                    tma_2d(&mAl, &full[s], st + 1 * OP_BYTES + b * 4096, row0 + b * 32, k0);
-                    tma_2d(&mXl, &full[s], st + 3 * OP_BYTES + b * 4096, col0 + b * 32, k0);
-                }
-            }
+            uint8_t *st = smem + s * STAGE;
+            bar_expect(&full[s], STAGE);
+            const int k0 = k_begin + it * KB;
+            tma_3d(&mA, &full[s], st, k0, row0, 0);
+            tma_3d(&mX, &full[s], st + ND * A_PLANE, k0, col0, 0);
         }
     } else if (warp == 1 && lane == 0) {
         // ---------------- MMA issuer ----------------
-        // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both MN-major, N = 128, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
-                               ((uint32_t)(TM >> 4) << 24);
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, both K-major, N = 64, M = 128
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         for (int it = 0; it < nk; ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             bar_wait(&full[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t base = s32(smem + s * STAGE_BYTES);
+            const uint32_t base = s32(smem + s * STAGE);
 #pragma unroll
-            for (int kb = 0; kb < TBK / 8; ++kb) {   // one MMA covers K = 8 (32 bytes of tf32)
-                const uint64_t dAh = smem_desc(base + 0 * OP_BYTES + kb * 1024, 4096, 1024);
-                const uint64_t dAl = smem_desc(base + 1 * OP_BYTES + kb * 1024, 4096, 1024);
-                const uint64_t dXh = smem_desc(base + 2 * OP_BYTES + kb * 1024, 4096, 1024);
-                const uint64_t dXl = smem_desc(base + 3 * OP_BYTES + kb * 1024, 4096, 1024);
-                const uint32_t first = (it > 0 || kb > 0) ? 1u : 0u;
-                if (p.passes == 3) {   // small terms first
-                    mma_tf32(tmem, dAl, dXh, idesc, first);
-                    mma_tf32(tmem, dAh, dXl, idesc, 1u);
-                    mma_tf32(tmem, dAh, dXh, idesc, 1u);
-                } else {
-                    mma_tf32(tmem, dAh, dXh, idesc, first);
+            for (int kk = 0; kk < KB / 32; ++kk) {   // one MMA covers K = 32 int8 (32 bytes): advance inside the swizzle row
+#pragma unroll
+                for (int sa = 0; sa < ND; ++sa) {
+                    const uint64_t dA = smem_desc_k64(base + sa * A_PLANE + kk * 32);
+#pragma unroll
+                    for (int sx = 0; sx < ND - sa; ++sx) {
+                        const uint64_t dX = smem_desc_k64(base + ND * A_PLANE + sx * X_PLANE + kk * 32);
+                        // level sa+sx; its first product of the tile (it = 0, kk = 0, sa = 0) overwrites the accumulator
+                        mma_i8(tmem + (uint32_t)((sa + sx) * TN), dA, dX, idesc, (it > 0 || kk > 0 || sa > 0) ? 1u : 0u);
+                    }
                 }
             }
             mma_commit(&empty[s]);          // slot free once these MMAs have read it
         }
-        mma_commit(accf);                   // accumulator complete
+        mma_commit(accf);                   // accumulators complete
     } else if (warp >= 2) {
         // ---------------- epilogue: TMEM -> registers -> fp64 global ----------------
         bar_wait(accf, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
         const int row = row0 + q * 32 + lane;
+        const bool live = row < p.R;
+        const double ra = live ? p.sa[row] : 0.0;
         double *out = p.C + (size_t)blockIdx.z * p.slab + (size_t)row * p.ldc + col0;
-#pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-            uint32_t r[32];
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 8) {
+            int acc[ND][8];
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (nk > 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2)
-                    *reinterpret_cast<double2 *>(out + c0 + j) =
-                        make_double2((double)__uint_as_float(r[j]), (double)__uint_as_float(r[j + 1]));
-            } else {
+                for (int d = 0; d < ND; ++d) tmem_ld8(taddr + (uint32_t)(d * TN), acc[d]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            double v[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2 *>(out + c0 + j) = make_double2(0.0, 0.0);
+            for (int j = 0; j < 8; ++j) {
+                double t = 0.0;
+                if (nk > 0) {
+                    t = (double)acc[ND - 1][j];
+#pragma unroll
+                    for (int d = ND - 2; d >= 0; --d) t = fma(t, 0.0078125, (double)acc[d][j]);
+                }
+                v[j] = t * ra * __ldg(p.sx + col0 + c0 + j);
+            }
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2 *>(out + c0 + j) = make_double2(v[j], v[j + 1]);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -183,7 +197,114 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// digit planes
+// ---------------------------------------------------------------------------
+// signed base-128 digits of v = x / scale * 64 (|v| <= 64): d_0 = rint(v), v <- (v - d_0) * 128, ...  (all steps exact)
+template <int ND>
+__device__ __forceinline__ void digits(double v, int8_t (&d)[ND])
+{
+#pragma unroll
+    for (int s = 0; s < ND; ++s) {
+        const double r = rint(v);
+        d[s] = (int8_t)(int)r;
+        v = (v - r) * 128.0;
+    }
+}
+// power of two >= max|x| (1 for a zero vector), returned as the factor 64 / scale applied before the digits
+__device__ __forceinline__ double pow2_scale(double mx, double *scale_over_64)
+{
+    int e = 0;
+    if (mx > 0.0 && mx < 1e300) frexp(mx, &e);      // mx = f * 2^e, f in [0.5, 1)
+    *scale_over_64 = ldexp(1.0, e - 6);
+    return ldexp(1.0, 6 - e);
+}
+
+// Rows of a fixed fp64 matrix A [R x ld] (kdim live columns) -> planes [ND][R][kdim] int8 + sa[r].  One warp per row.
+template <int ND>
+__global__ void slice_rows_kernel(const double *__restrict__ A, int ld, int R, int kdim, int8_t *__restrict__ out,
+                                  double *__restrict__ sa)
+{
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const double *a = A + (size_t)r * ld;
+    double mx = 0.0;
+    for (int k = lane; k < kdim; k += 32) mx = fmax(mx, fabs(a[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double so64;
+    const double f = pow2_scale(mx, &so64);
+    if (lane == 0) sa[r] = so64;
+    const size_t plane = (size_t)R * kdim;
+    for (int k = lane * 4; k < kdim; k += 128) {     // kdim is a multiple of 64: char4 stores
+        int8_t d[4][ND];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) digits<ND>(a[k + j] * f, d[j]);
+#pragma unroll
+        for (int s = 0; s < ND; ++s)
+            *reinterpret_cast<char4 *>(out + s * plane + (size_t)r * kdim + k) = make_char4(d[0][s], d[1][s], d[2][s], d[3][s]);
+    }
+}
+
+// per-design max |x| of an iterate X [kdim x Bp] (design index fastest); mx must be zeroed before
+__global__ void col_absmax_kernel(const double *__restrict__ X, int kdim, int Bp, double *__restrict__ mx)
+{
+    __shared__ double sh[4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int b = blockIdx.x * 64 + tx;
+    double m = 0.0;
+    for (int k = blockIdx.y * 4 + ty; k < kdim; k += 4 * gridDim.y) m = fmax(m, fabs(X[(size_t)k * Bp + b]));
+    sh[ty][tx] = m;
+    __syncthreads();
+    if (ty == 0) {
+        m = fmax(fmax(sh[0][tx], sh[1][tx]), fmax(sh[2][tx], sh[3][tx]));
+        if (m > 0.0) atomicMax(reinterpret_cast<unsigned long long *>(mx + b), (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+// Iterate X [kdim x Bp] -> planes [ND][Bp][kdim] int8 (transposed: k fastest) + sx[b].  A CTA of 256 threads
+// transposes a 64 (k) x 64 (designs) tile through shared memory: coalesced 512-byte reads; each thread packs the
+// digits of 4 consecutive k into one 32-bit word per plane (row pitch 17 words: conflict-free), 64-byte row segments out.
+// zero_other (optional, [Bp]): the max-accumulator of the OTHER iterate is cleared here for its next producer.
+template <int ND>
+__global__ void __launch_bounds__(256) slice_cols_kernel(const double *__restrict__ X, int kdim, int Bp,
+                                                         const double *__restrict__ mx, int8_t *__restrict__ out,
+                                                         double *__restrict__ sx, double *__restrict__ zero_other)
+{
+    __shared__ uint32_t tile[ND][64][17];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int b0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    double so64;
+    const double f = pow2_scale(mx[b0 + tx], &so64);
+    if (blockIdx.y == 0 && ty == 0) {
+        sx[b0 + tx] = so64;
+        if (zero_other) zero_other[b0 + tx] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int q = ty + 4 * j;                         // quad of k: k0 + 4q .. k0 + 4q + 3
+        const double *src = X + (size_t)(k0 + 4 * q) * Bp + b0 + tx;
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = src[(size_t)i * Bp] * f;
+        int8_t d[4][ND];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) digits<ND>(v[i], d[i]);
+#pragma unroll
+        for (int s = 0; s < ND; ++s)
+            tile[s][tx][q] = (uint32_t)(uint8_t)d[0][s] | ((uint32_t)(uint8_t)d[1][s] << 8) | ((uint32_t)(uint8_t)d[2][s] << 16) |
+                             ((uint32_t)(uint8_t)d[3][s] << 24);
+    }
+    __syncthreads();
+    const size_t plane = (size_t)Bp * kdim;
+    for (int c = threadIdx.x; c < ND * 64 * 4; c += 256) {     // 16-byte chunks: (plane, design, quarter of the 64 k)
+        const int s = c / 256, bb = (c >> 2) & 63, qd = c & 3;
+        const uint32_t *t = &tile[s][bb][qd * 4];
+        *reinterpret_cast<uint4 *>(out + s * plane + (size_t)(b0 + bb) * kdim + k0 + qd * 16) = make_uint4(t[0], t[1], t[2], t[3]);
     }
 }
 #endif  // __CUDACC__
@@ -206,17 +327,17 @@ inline EncodeTiledFn encode_fn()
     return fn;
 }
 
-// fp32 matrix [rows(k) x cols(outputs)] with leading dimension ld (elements): boxes of 32 k-rows x 32 outputs, 128B swizzle
-inline bool make_map(CUtensorMap *map, const float *base, int rows, int cols, int ld)
+// digit planes [nd][rows][kdim] int8 (k fastest): boxes of KB k-values x box_rows rows x nd planes, 64-byte swizzle
+inline bool make_map(CUtensorMap *map, const int8_t *base, int kdim, int rows, int nd, int box_rows)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {32, (cuuint32_t)TBK};
-    cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)rows, (cuuint64_t)nd};
+    cuuint64_t strides[2] = {(cuuint64_t)kdim, (cuuint64_t)kdim * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)box_rows, (cuuint32_t)nd};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tc

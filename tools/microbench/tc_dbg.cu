@@ -80,8 +80,96 @@ __global__ void __launch_bounds__(128, 1) dbg_kernel(const float *A, const float
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
 }
 
+
+// ---- int8: K-major, 128B swizzle rows of 128 k-values; NK MMAs of K=32 advance the descriptor start address by 32 B ----
+template <int N>
+__global__ void __launch_bounds__(128, 1) dbg_i8(const int8_t *A, const int8_t *B, int *D, int nk)
+{
+    extern __shared__ uint8_t raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem, *sB = smem + 16384;
+    uint64_t *bar = (uint64_t *)(smem + 32768);
+    uint32_t *slot = (uint32_t *)(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 128 * 128; i += 128) {
+        const int mn = i >> 7, k = i & 127;
+        uint32_t off = (mn >> 3) * 1024 + (mn & 7) * 128 + k;
+        off ^= ((off >> 7) & 7) << 4;
+        sA[off] = (uint8_t)A[i];
+        if (mn < N) sB[off] = (uint8_t)B[i];
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s32(slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    if (tid == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int kb = 0; kb < nk; ++kb) {
+            const uint64_t da = mk_desc(s32(sA) + kb * 32, 16, 1024, 2), db = mk_desc(s32(sB) + kb * 32, 16, 1024, 2);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc),
+                         "r"(kb > 0 ? 1u : 0u)
+                         : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+    }
+    asm volatile("{\n\t.reg .pred p;\n\tW8:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra E8;\n\tbra W8;\n\tE8:\n\t}" ::"r"(s32(bar))
+                 : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t r[8];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 8; ++j) D[(warp * 32 + lane) * N + c0 + j] = (int)r[j];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+}
+
+template <int N>
+static int run_i8(int nk)
+{
+    std::vector<int8_t> A(128 * 128), B(128 * 128);
+    std::vector<int> D(128 * N);
+    for (auto &v : A) v = (int8_t)((rand() % 129) - 64);
+    for (auto &v : B) v = (int8_t)((rand() % 129) - 64);
+    int8_t *dA, *dB; int *dD;
+    cudaMalloc(&dA, 16384); cudaMalloc(&dB, 16384); cudaMalloc(&dD, 128 * N * 4);
+    cudaMemcpy(dA, A.data(), 16384, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B.data(), 16384, cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0xff, 128 * N * 4);
+    cudaFuncSetAttribute(dbg_i8<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+    dbg_i8<N><<<1, 128, 40000>>>(dA, dB, dD, nk);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("i8 N %d nk %d: %s\n", N, nk, cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(D.data(), dD, 128 * N * 4, cudaMemcpyDeviceToHost);
+    long long bad = 0;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            int s = 0;
+            for (int k = 0; k < nk * 32; ++k) s += (int)A[m * 128 + k] * (int)B[n * 128 + k];
+            bad += s != D[m * N + n];
+        }
+    printf("i8 N %d nk %d: mismatches %lld of %d  D[0..2]=%d %d %d\n", N, nk, bad, 128 * N, D[0], D[1], D[2]);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    run_i8<128>(1); run_i8<128>(4); run_i8<64>(4); run_i8<32>(2);
     std::vector<float> A(1024), B(1024), D(16384);
     srand(3);
     for (auto &v : A) v = (float)((rand() % 17) - 8) / 8.f;

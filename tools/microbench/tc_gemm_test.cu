@@ -1,5 +1,7 @@
-// Standalone correctness/speed test of the tcgen05 3xTF32 GEMM tile (csrc/tc_gemm.cuh).
+// Standalone correctness/speed test of the tcgen05 split-integer GEMM (csrc/tc_gemm.cuh): fp64 operands -> digit
+// planes -> int8 tensor-core level products -> fp64 result, compared with a long-double reference.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tc_gemm_test tc_gemm_test.cu
+// usage: tc_gemm_test kdim R Bp [P split-K slabs]
 #include "../../multiband_rf_pulse_design_b200/csrc/tc_gemm.cuh"
 #include <cmath>
 #include <cstdio>
@@ -7,57 +9,85 @@
 #include <vector>
 using namespace mbrf::tc;
 
-static float tf32_round(float x)
+template <int ND>
+static int run(int kdim, int R, int Bp, int P)
 {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    u = (u + 0x1000u) & 0xFFFFE000u;
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
+    std::vector<double> A((size_t)R * kdim), X((size_t)kdim * Bp);
+    srand(1);
+    for (int r = 0; r < R; ++r) {
+        const double amp = ldexp(1.0, (r % 7) - 3);   // rows of different magnitude
+        for (int k = 0; k < kdim; ++k) A[(size_t)r * kdim + k] = amp * cos(0.001 * (r + 1) * (k + 1));
+    }
+    for (int k = 0; k < kdim; ++k)
+        for (int b = 0; b < Bp; ++b) {
+            const double u = rand() / (double)RAND_MAX - 0.5;
+            X[(size_t)k * Bp + b] = (b % 5 == 0 && k % 3) ? 0.0 : u * ldexp(1.0, (b % 11) - 5) * ((k % 17 == 0) ? 1e-6 : 1.0);
+        }
+    double *dA, *dX, *dC, *dsa, *dsx, *dmx;
+    int8_t *pA, *pX;
+    cudaMalloc(&dA, A.size() * 8); cudaMalloc(&dX, X.size() * 8); cudaMalloc(&dC, (size_t)P * R * Bp * 8);
+    cudaMalloc(&dsa, R * 8); cudaMalloc(&dsx, Bp * 8); cudaMalloc(&dmx, Bp * 8);
+    cudaMalloc(&pA, (size_t)ND * R * kdim); cudaMalloc(&pX, (size_t)ND * Bp * kdim);
+    cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dX, X.data(), X.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemset(dC, 0xff, (size_t)P * R * Bp * 8);
+    slice_rows_kernel<ND><<<(R * 32 + 255) / 256, 256>>>(dA, kdim, R, kdim, pA, dsa);
+    CUtensorMap mA, mX;
+    if (!make_map(&mA, pA, kdim, R, ND, TM) || !make_map(&mX, pX, kdim, Bp, ND, TN)) { printf("tensor map failed\n"); return 1; }
+    cudaFuncSetAttribute(tc_i8_gemm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ND));
+    Params p;
+    p.C = dC; p.slab = (long long)R * Bp; p.ldc = Bp; p.R = R; p.kdim_total = kdim;
+    p.kchunk = ((kdim + P - 1) / P + KB - 1) / KB * KB; p.sa = dsa; p.sx = dsx;
+    dim3 grid(Bp / TN, (R + TM - 1) / TM, P);
+    auto product = [&]() {
+        cudaMemsetAsync(dmx, 0, Bp * 8);
+        col_absmax_kernel<<<dim3(Bp / 64, 16), 256>>>(dX, kdim, Bp, dmx);
+        slice_cols_kernel<ND><<<dim3(Bp / 64, kdim / 64), 256>>>(dX, kdim, Bp, dmx, pX, dsx, nullptr);
+        tc_i8_gemm_kernel<ND><<<grid, THREADS, smem_bytes(ND)>>>(mA, mX, p);
+    };
+    product();
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { printf("ND %d launch: %s\n", ND, cudaGetErrorString(err)); return 2; }
+    cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    cudaEventRecord(e0);
+    for (int i = 0; i < 20; ++i) product();
+    cudaEventRecord(e1);
+    for (int i = 0; i < 20; ++i) tc_i8_gemm_kernel<ND><<<grid, THREADS, smem_bytes(ND)>>>(mA, mX, p);
+    cudaEventRecord(e2); cudaEventSynchronize(e2);
+    float ms_all, ms_mm; cudaEventElapsedTime(&ms_all, e0, e1); cudaEventElapsedTime(&ms_mm, e1, e2);
+    ms_all /= 20; ms_mm /= 20;
+    std::vector<double> C((size_t)P * R * Bp);
+    cudaMemcpy(C.data(), dC, C.size() * 8, cudaMemcpyDeviceToHost);
+    double maxrel = 0, maxabs = 0;
+    for (int r = 0; r < R; r += 5)
+        for (int b = 0; b < Bp; b += 3) {
+            long double s = 0, sabs = 0;
+            double amax = 0, xmax = 0;
+            for (int k = 0; k < kdim; ++k) {
+                const double a = A[(size_t)r * kdim + k], x = X[(size_t)k * Bp + b];
+                s += (long double)a * x; sabs += fabsl((long double)a * x);
+                amax = fmax(amax, fabs(a)); xmax = fmax(xmax, fabs(x));
+            }
+            double c = 0;
+            for (int z = 0; z < P; ++z) c += C[(size_t)z * R * Bp + (size_t)r * Bp + b];
+            const double e = fabs((double)(s - c));
+            maxabs = fmax(maxabs, e);
+            if (amax * xmax > 0) maxrel = fmax(maxrel, e / (amax * xmax * sqrt((double)kdim)));
+            if (!(e == e)) { printf("NaN at %d %d\n", r, b); return 3; }
+        }
+    const double flops = 2.0 * kdim * R * Bp;
+    printf("ND %d kdim %d R %d Bp %d P %d: max abs err %.3e, err/(amax*xmax*sqrt(k)) %.3e | product %.3f ms (gemm %.3f ms = %.1f TFLOP/s fp64-equivalent, %.0f TOP/s int8)\n",
+           ND, kdim, R, Bp, P, maxabs, maxrel, ms_all, ms_mm, flops / ms_mm / 1e9, flops * (ND * (ND + 1) / 2) / ms_mm / 1e9);
+    cudaFree(dA); cudaFree(dX); cudaFree(dC); cudaFree(dsa); cudaFree(dsx); cudaFree(dmx); cudaFree(pA); cudaFree(pX);
+    return 0;
 }
 
 int main(int argc, char **argv)
 {
     const int kdim = argc > 1 ? atoi(argv[1]) : 512, R = argc > 2 ? atoi(argv[2]) : 256, Bp = argc > 3 ? atoi(argv[3]) : 128;
-    const int passes = argc > 4 ? atoi(argv[4]) : 3;
-    std::vector<double> A((size_t)kdim * R), X((size_t)kdim * Bp);
-    std::vector<float> Ah(A.size()), Al(A.size()), Xh(X.size()), Xl(X.size());
-    srand(1);
-    for (size_t i = 0; i < A.size(); ++i) { A[i] = (rand() / (double)RAND_MAX - 0.5); Ah[i] = tf32_round((float)A[i]); Al[i] = tf32_round((float)(A[i] - Ah[i])); }
-    for (size_t i = 0; i < X.size(); ++i) { X[i] = (rand() / (double)RAND_MAX - 0.5); Xh[i] = tf32_round((float)X[i]); Xl[i] = tf32_round((float)(X[i] - Xh[i])); }
-    float *dAh, *dAl, *dXh, *dXl;
-    double *dC;
-    cudaMalloc(&dAh, A.size() * 4); cudaMalloc(&dAl, A.size() * 4); cudaMalloc(&dXh, X.size() * 4); cudaMalloc(&dXl, X.size() * 4);
-    cudaMalloc(&dC, (size_t)R * Bp * 8);
-    cudaMemcpy(dAh, Ah.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dAl, Al.data(), A.size() * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(dXh, Xh.data(), X.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dXl, Xl.data(), X.size() * 4, cudaMemcpyHostToDevice);
-    cudaMemset(dC, 0xff, (size_t)R * Bp * 8);
-    CUtensorMap mAh, mAl, mXh, mXl;
-    if (!make_map(&mAh, dAh, kdim, R, R) || !make_map(&mAl, dAl, kdim, R, R) || !make_map(&mXh, dXh, kdim, Bp, Bp) ||
-        !make_map(&mXl, dXl, kdim, Bp, Bp)) { printf("tensor map failed\n"); return 1; }
-    cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    Params p; p.C = dC; p.slab = 0; p.ldc = Bp; p.kdim_total = kdim; p.kchunk = kdim; p.passes = passes;
-    dim3 grid(Bp / TN, R / TM, 1);
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES>>>(mAh, mAl, mXh, mXl, p);
-    cudaError_t err = cudaDeviceSynchronize();
-    printf("launch: %s\n", cudaGetErrorString(err));
-    if (err != cudaSuccess) return 2;
-    cudaEventRecord(e0);
-    for (int i = 0; i < 10; ++i) tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES>>>(mAh, mAl, mXh, mXl, p);
-    cudaEventRecord(e1); cudaEventSynchronize(e1);
-    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 10;
-    std::vector<double> C((size_t)R * Bp);
-    cudaMemcpy(C.data(), dC, C.size() * 8, cudaMemcpyDeviceToHost);
-    double maxerr = 0, maxref = 0;
-    for (int r = 0; r < R; r += 7)
-        for (int b = 0; b < Bp; b += 5) {
-            double s = 0;
-            for (int k = 0; k < kdim; ++k) s += (passes == 3 ? A[(size_t)k * R + r] * X[(size_t)k * Bp + b] : (double)Ah[(size_t)k * R + r] * Xh[(size_t)k * Bp + b]);
-            maxerr = fmax(maxerr, fabs(s - C[(size_t)r * Bp + b])); maxref = fmax(maxref, fabs(s));
-        }
-    printf("kdim %d R %d Bp %d passes %d: max err %.3e (max |ref| %.3f)  %.3f ms  %.1f TFLOP/s effective\n", kdim, R, Bp, passes, maxerr,
-           maxref, ms, 2.0 * kdim * R * Bp / ms / 1e9);
-    return maxerr < 1e-4 * (passes == 3 ? 0.02 : 1.0) * fmax(maxref, 1.0) + 1e-4 ? 0 : 3;
+    const int P = argc > 4 ? atoi(argv[4]) : 1;
+    int rc = run<4>(kdim, R, Bp, P);
+    if (!rc) rc = run<5>(kdim, R, Bp, P);
+    if (!rc) rc = run<6>(kdim, R, Bp, P);
+    return rc;
 }
