@@ -955,7 +955,7 @@ static double g_opt[5] = {0.9, 0.2, 0.8, 0.36, 0.5};   // eta factor, beta_suff,
 // product kernels of the iterations (mbrf_pdhg_set_gemm): 2 = tcgen05 int8 split-integer tiles (tc_gemm.cuh), 1 = FP64
 // tensor path mma.sync m8n8k4, 0 = SIMT DFMA tiles.  The convergence checks always use an fp64 kernel (1 unless 0).
 static int g_gemm_mode = 2;
-static int g_tc_digits = 6;  // digit planes / level accumulators of the split-integer product (4..6)
+static int g_tc_digits = 5;  // digit planes / level accumulators of the split-integer product (4..6)
 
 // digit planes, scales and tensor maps of the tcgen05 path (device memory lives in the caller's workspace)
 struct TcState {
@@ -973,13 +973,23 @@ static size_t tc_bytes(int Mp, int Np, int Bp)
     const size_t mxd = (size_t)(Mp > Np ? Mp : Np);
     return (size_t)tc::MAX_ND * (2 * (size_t)Mp * Np + (size_t)Bp * mxd) + ((size_t)Mp + Np + 3 * (size_t)Bp) * 8 + 4 * 256;
 }
+static int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    }
+    return n;
+}
 static int split_k_tc(int Mp, int Np, int Bp)
 {
-    const int tiles = ((Np + tc::TM - 1) / tc::TM) * (Bp / tc::TN);
+    const int tiles = (Np / tc::TN) * ((Bp + tc::TM - 1) / tc::TM);
     int P = (2 * 148) / tiles;              // two full waves of one CTA per SM
     if (P > Mp / 256) P = Mp / 256;
     if (P > 32) P = 32;
     if (P < 1) P = 1;
+    while (P < 32 && (double)up((Mp + P - 1) / P, tc::KB) * tc::MAX_ND * 16384.0 >= 2147483648.0) ++P;   // int32 level sums
     return P;
 }
 
@@ -1006,8 +1016,10 @@ static int tc_product_nd(const TcState &t, const double *X, int kdim, int Bp, co
     MBRF_LAUNCH_CHECK();
     tc::Params q;
     q.C = C; q.slab = slab; q.ldc = Bp; q.R = R; q.kdim_total = kdim;
-    q.kchunk = up((kdim + P - 1) / P, tc::KB); q.sa = sa; q.sx = t.sx;
-    tc::tc_i8_gemm_kernel<ND><<<dim3(Bp / tc::TN, (R + tc::TM - 1) / tc::TM, P), tc::THREADS, tc::smem_bytes(ND), st>>>(mA, mX, q);
+    q.kchunk = up((kdim + P - 1) / P, tc::KB); q.sa = sa; q.sx = t.sx; q.nslab = P;
+    const int ntiles = (R / tc::TN) * ((Bp + tc::TM - 1) / tc::TM) * P;
+    const int nsm = sm_count();
+    tc::tc_i8_gemm_kernel<ND><<<ntiles < nsm ? ntiles : nsm, tc::THREADS, tc::smem_bytes(ND), st>>>(mA, mX, q);
     MBRF_LAUNCH_CHECK();
     return MBRF_OK;
 }
@@ -1078,7 +1090,7 @@ int mbrf_pdhg_set_gemm(int mode)
     g_gemm_mode = mode;
     return MBRF_OK;
 }
-// digit planes of the split-integer product: 4, 5 or 6 (default 6: ~1e-12 of |row|max * |column|max per term)
+// digit planes of the split-integer product: 4, 5 (default: ~1e-11 of |row|max * |column|max per term) or 6 (~1e-13)
 int mbrf_pdhg_set_tc_digits(int nd)
 {
     if (nd < 4 || nd > tc::MAX_ND) return MBRF_EINVAL;
@@ -1207,7 +1219,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     auto tc_setup_width = [&]() -> int {   // (re)build what depends on the batch width p.Bp
         if (!tcs.on) return MBRF_OK;
         if (p.Bp < 64) { tcs.on = false; p.mxy = p.mxz = nullptr; p.P = split_k(p.Mp, p.Np, p.Bp); return MBRF_OK; }
-        if (!tc::make_map(&tcs.mXn, tcs.pX, p.Np, p.Bp, tcs.nd, tc::TN) || !tc::make_map(&tcs.mXm, tcs.pX, p.Mp, p.Bp, tcs.nd, tc::TN)) {
+        if (!tc::make_map(&tcs.mXn, tcs.pX, p.Np, p.Bp, tcs.nd, tc::TM) || !tc::make_map(&tcs.mXm, tcs.pX, p.Mp, p.Bp, tcs.nd, tc::TM)) {
             set_error("pdhg: cuTensorMapEncodeTiled failed for the iterate planes");
             return MBRF_ECUDA;
         }
@@ -1234,7 +1246,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         default: tc_slice_rows<6>(K, ldk, Mp, Np, tcs.pK, tcs.saK, st); tc_slice_rows<6>(KT, Mp, Np, Mp, tcs.pKT, tcs.saKT, st); break;
         }
         MBRF_LAUNCH_CHECK();
-        if (!tc::make_map(&tcs.mK, tcs.pK, Np, Mp, tcs.nd, tc::TM) || !tc::make_map(&tcs.mKT, tcs.pKT, Mp, Np, tcs.nd, tc::TM)) {
+        if (!tc::make_map(&tcs.mK, tcs.pK, Np, Mp, tcs.nd, tc::TN) || !tc::make_map(&tcs.mKT, tcs.pKT, Mp, Np, tcs.nd, tc::TN)) {
             set_error("pdhg: cuTensorMapEncodeTiled failed for the matrix planes");
             return MBRF_ECUDA;
         }

@@ -4,19 +4,21 @@
 //
 // tcgen05.mma has no fp64 kind, and an fp32-accumulate product is at the level of the residuals PDHG has to drive down
 // (DESIGN.md section 6).  The int8 kind accumulates in int32 EXACTLY, so the product is rebuilt from integer digits:
-//   every row of A and every column of X is scaled by a power of two to |.| <= 1 and written as signed base-128 digits
-//       a / alpha_r = (1/64) * sum_s A_s * 128^-s ,   A_s in [-64, 64]                       (x likewise, beta_b, X_t)
-//   C_rb = alpha_r beta_b / 4096 * sum_d 128^-d * sum_{s+t=d} (A_s X_t)_rb ,   d < ND
-// The level sums  sum_{s+t=d} A_s X_t  are exact int32 GEMMs (|.| <= (d+1) * 4096 * kdim < 2^31) that share one TMEM
-// accumulator per level; dropping the levels d >= ND leaves a relative error of about (ND+1) * 2^(-7 ND) of
-// alpha_r * beta_b per term (ND = 6: 3e-12) — set by ND, not by the tensor core.
+//   every row of A and every column of X is scaled by a power of two to |.| <= 1 and written as signed base-256 digits
+//       a / alpha_r = (1/64) * sum_s A_s * 256^-s ,   A_s in [-128, 127]                     (x likewise, beta_b, X_t)
+//   C_rb = alpha_r beta_b / 4096 * sum_d 256^-d * sum_{s+t=d} (A_s X_t)_rb ,   d < ND
+// The level sums  sum_{s+t=d} A_s X_t  are exact int32 GEMMs (|.| <= (d+1) * 2^14 * kdim < 2^31 for kdim < 2^17 / ND)
+// that share one TMEM accumulator per level; dropping the levels d >= ND leaves an error of about 2^(-8 ND + 3) of
+// alpha_r * beta_b per term (ND = 5: measured 1e-11, ND = 6: 1e-13) — set by ND, not by the tensor core.
 //
-// One CTA computes a 128 x 64 output tile: ND accumulators of 64 int32 columns in TMEM; digit tiles of KB = 64 k-values
-// (all ND digit planes of A: 128 rows, and of X: 64 columns) arrive with two 3-D TMA copies per stage (64-byte swizzle)
+// One tile is 128 designs (the MMA's M side: TMEM lanes, so that a warp stores 256 contiguous bytes of a C row) x 64
+// matrix rows: ND accumulators of 64 int32 columns in TMEM; digit tiles of KB = 64 k-values (all ND digit planes of X:
+// 128 designs, and of A: 64 rows) arrive with two 3-D TMA copies per stage (64-byte swizzle)
 // in a 3-stage shared-memory ring; one elected thread issues ND(ND+1)/2 tcgen05.mma.kind::i8 (M=128, N=64, K=32, both
-// operands K-major) per 32 k-values; tcgen05.commit frees ring slots and finally signals the four epilogue warps, which
-// read the level accumulators with tcgen05.ld, combine them in fp64 (Horner in 1/128, exact) and store scaled doubles.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = epilogue (TMEM lane quarter = warp % 4).
+// operands K-major) per 32 k-values; tcgen05.commit frees ring slots and finally signals the sixteen epilogue warps, which
+// read the level accumulators with tcgen05.ld, combine them (Horner in 1/256 in fp64: exact) and
+// store scaled doubles.  The kernel is persistent (one CTA per SM walks the tiles).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..17 = epilogue (TMEM lane quarter = warp % 4).
 // Descriptor encodings were brought up with tools/microbench/tc_dbg.cu (MN-major tf32 operands return zeros on this
 // part, K-major operands are exact: hence the transposed digit planes).
 #pragma once
@@ -27,17 +29,20 @@
 namespace mbrf {
 namespace tc {
 
-constexpr int TM = 128, TN = 64, KB = 64, STAGES = 3, THREADS = 192;
+constexpr int TM = 128, TN = 64, KB = 64, STAGES = 3;
+constexpr int EPI_WARPS = 16, EPI_COLS = TN / (EPI_WARPS / 4);   // epilogue: 4 warps per TMEM lane quarter, 16 columns each
+constexpr int THREADS = 64 + 32 * EPI_WARPS;                       // warps: TMA, MMA, epilogue
 constexpr int MAX_ND = 6;
 constexpr int stage_bytes(int nd) { return nd * (TM + TN) * KB; }
 constexpr int smem_bytes(int nd) { return STAGES * stage_bytes(nd) + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct Params {
-    double *C;                // [R x ldc] fp64, slab blockIdx.z at C + z*slab
+    double *C;                // [R x ldc] fp64, slab z at C + z*slab
     long long slab;
     int ldc;
-    int R;                    // valid output rows (rows >= R of a tile are not stored)
+    int R;                    // output rows (multiple of TN); designs >= ldc of a tile are not stored
     int kdim_total, kchunk;   // reduction range of slab z: [z*kchunk, min(kdim_total, (z+1)*kchunk)), multiples of KB
+    int nslab;                // split-K slabs
     const double *sa;         // [R]   alpha_r / 64
     const double *sx;         // [ldc] beta_b / 64
 };
@@ -45,6 +50,14 @@ struct Params {
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp; the compiler then knows the region is single-lane and feeds the uniform-register operands
+// of UTMALDG / UTCIMMA without a per-instruction lane loop (with `lane == 0` every MMA sat in an ELECT/R2UR/BRA loop)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bar_init(uint64_t *b, unsigned n)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n) : "memory");
@@ -88,29 +101,62 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&r)[8])
                  : "r"(taddr));
 }
 
+// A_TMEM: every A digit plane of a k-block is copied once into TMEM (tcgen05.cp) and the ND - s products that use plane s
+// read it from there: shared-memory operand traffic per 32 k-values drops from ND(ND+1)/2 * 6 KB to ND * 4 KB +
+// ND(ND+1)/2 * 2 KB, which moves the tile from shared-memory-bound to tensor-pipe-bound (measured).
+__device__ __forceinline__ void bar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// exact int32 -> double without the (slow) I2F.F64: flip the sign bit into the low mantissa word of 2^52, subtract 2^52 + 2^31
+__device__ __forceinline__ double i2d(int a)
+{
+    return __hiloint2double(0x43300000, a ^ (int)0x80000000) - 4503601774854144.0;
+}
+
+#ifdef TC_TIMING   // developer instrumentation (tools/microbench/tc_gemm_test.cu): clock stamps of every CTA's first tile
+__device__ long long *tc_timing;
+#define TC_STAMP(i) do { if (tc_timing && tile == (int)blockIdx.x) tc_timing[(size_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#endif
+
+// Persistent: gridDim.x CTAs (one per SM) walk the tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...;  tile t is
+// (matrix-row tile t % tiles_x, design tile (t / tiles_x) % tiles_y, split-K slab t / (tiles_x * tiles_y)).  The shared-memory
+// ring runs on across tiles (the producer prefetches the next tile during the epilogue); the epilogue warps pull the whole
+// accumulator into registers (ND x 16 ints per thread), hand TMEM back to the MMA warp (tmem_empty) and only then
+// convert and store, so conversion and stores of tile t overlap the MMAs of tile t + 1.
 template <int ND>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_i8_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mX, const Params p)
 {
     constexpr int STAGE = ND * (TM + TN) * KB;
-    constexpr int A_PLANE = TM * KB, X_PLANE = TN * KB;           // bytes of one digit plane in a stage
+    constexpr int X_PLANE = TM * KB, A_PLANE = TN * KB;           // bytes of one digit plane in a stage (designs are the M side)
     constexpr uint32_t TMEM_COLS = ND * TN <= 256 ? 256u : 512u;  // power of two >= ND accumulators of TN columns
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms need aligned planes
     uint64_t *full = (uint64_t *)(smem + STAGES * STAGE);
     uint64_t *empty = full + STAGES;
-    uint64_t *accf = empty + STAGES;
-    uint32_t *tmem_slot = (uint32_t *)(accf + 1);
+    uint64_t *tmem_full = empty + STAGES;
+    uint64_t *tmem_empty = tmem_full + 1;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 1);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
-    const int k_begin = blockIdx.z * p.kchunk;
-    const int k_end = min(p.kdim_total, k_begin + p.kchunk);
-    const int nk = k_end > k_begin ? (k_end - k_begin) / KB : 0;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    const int tiles_x = p.R / TN, tiles_y = (p.ldc + TM - 1) / TM;   // matrix-row tiles (fastest), design tiles
+    const int ntiles = tiles_x * tiles_y * p.nslab;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
-        bar_init(accf, 1);
+        bar_init(tmem_full, 1);
+        bar_init(tmem_empty, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -122,77 +168,102 @@ tc_i8_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         // ---------------- TMA producer: all digit planes of a k-block with one copy per operand ----------------
-        for (int it = 0; it < nk; ++it) {
-            const int s = it % STAGES, ph = (it / STAGES) & 1;
-            bar_wait(&empty[s], ph ^ 1);
-            uint8_t *st = smem + s * STAGE;
-            bar_expect(&full[s], STAGE);
-            const int k0 = k_begin + it * KB;
-            tma_3d(&mA, &full[s], st, k0, row0, 0);
-            tma_3d(&mX, &full[s], st + ND * A_PLANE, k0, col0, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int r0 = (tile % tiles_x) * TN, b0 = ((tile / tiles_x) % tiles_y) * TM, z = tile / (tiles_x * tiles_y);
+            const int k_begin = z * p.kchunk, k_end = min(p.kdim_total, k_begin + p.kchunk);
+            for (int k0 = k_begin; k0 < k_end; k0 += KB, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                bar_wait(&empty[s], ph ^ 1);
+                uint8_t *st = smem + s * STAGE;
+                bar_expect(&full[s], STAGE);
+                tma_3d(&mX, &full[s], st, k0, b0, 0);                    // 128 designs x KB x ND planes  (MMA operand A)
+                tma_3d(&mA, &full[s], st + ND * X_PLANE, k0, r0, 0);     // 64 matrix rows x KB x ND planes (MMA operand B)
+            }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         // ---------------- MMA issuer ----------------
         // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, both K-major, N = 64, M = 128
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-        for (int it = 0; it < nk; ++it) {
-            const int s = it % STAGES, ph = (it / STAGES) & 1;
-            bar_wait(&full[s], ph);
+        int it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+            const int z = tile / (tiles_x * tiles_y);
+            const int k_begin = z * p.kchunk, k_end = min(p.kdim_total, k_begin + p.kchunk);
+            const int nk = k_end > k_begin ? (k_end - k_begin) / KB : 0;
+            bar_wait(tmem_empty, (tl & 1) ^ 1);          // the epilogue has pulled the previous tile out of TMEM
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t base = s32(smem + s * STAGE);
+            TC_STAMP(1);
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                bar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (kb == 0) TC_STAMP(2);
+                const uint32_t base = s32(smem + s * STAGE);
 #pragma unroll
-            for (int kk = 0; kk < KB / 32; ++kk) {   // one MMA covers K = 32 int8 (32 bytes): advance inside the swizzle row
+                for (int kk = 0; kk < KB / 32; ++kk) {   // one MMA covers K = 32 int8 (32 bytes): advance inside the swizzle row
 #pragma unroll
-                for (int sa = 0; sa < ND; ++sa) {
-                    const uint64_t dA = smem_desc_k64(base + sa * A_PLANE + kk * 32);
+                    for (int sx = 0; sx < ND; ++sx) {
+                        const uint64_t dX = smem_desc_k64(base + sx * X_PLANE + kk * 32);
 #pragma unroll
-                    for (int sx = 0; sx < ND - sa; ++sx) {
-                        const uint64_t dX = smem_desc_k64(base + ND * A_PLANE + sx * X_PLANE + kk * 32);
-                        // level sa+sx; its first product of the tile (it = 0, kk = 0, sa = 0) overwrites the accumulator
-                        mma_i8(tmem + (uint32_t)((sa + sx) * TN), dA, dX, idesc, (it > 0 || kk > 0 || sa > 0) ? 1u : 0u);
+                        for (int sa = 0; sa < ND - sx; ++sa) {
+                            const uint64_t dA = smem_desc_k64(base + ND * X_PLANE + sa * A_PLANE + kk * 32);
+                            // level sa+sx; its first product of the tile (kb = 0, kk = 0, sx = 0) overwrites the accumulator
+                            mma_i8(tmem + (uint32_t)((sa + sx) * TN), dX, dA, idesc, (kb > 0 || kk > 0 || sx > 0) ? 1u : 0u);
+                        }
                     }
                 }
+                mma_commit(&empty[s]);          // slot free once these MMAs have read it
             }
-            mma_commit(&empty[s]);          // slot free once these MMAs have read it
+            mma_commit(tmem_full);              // accumulators complete (arrives immediately for an empty slab)
+            TC_STAMP(3);
         }
-        mma_commit(accf);                   // accumulators complete
     } else if (warp >= 2) {
-        // ---------------- epilogue: TMEM -> registers -> fp64 global ----------------
-        bar_wait(accf, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---------------- epilogue: TMEM -> registers (release TMEM) -> fp64 global ----------------
+        // four warps per TMEM lane quarter (warp % 4), each takes EPI_COLS = 16 of the tile's columns
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
-        const int row = row0 + q * 32 + lane;
-        const bool live = row < p.R;
-        const double ra = live ? p.sa[row] : 0.0;
-        double *out = p.C + (size_t)blockIdx.z * p.slab + (size_t)row * p.ldc + col0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 8) {
-            int acc[ND][8];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            if (nk > 0) {
+        const int part = (warp - 2) >> 2;             // columns [part*16, part*16 + 16)
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+            const int r0 = (tile % tiles_x) * TN + part * EPI_COLS, b0 = ((tile / tiles_x) % tiles_y) * TM, z = tile / (tiles_x * tiles_y);
+            const int k_begin = z * p.kchunk;
+            const bool any = k_begin < p.kdim_total;
+            const int b = b0 + q * 32 + lane;              // TMEM lane = design: a warp stores 256 contiguous bytes per matrix row
+            const bool live = b < p.ldc;
+            const double xs = live ? p.sx[b] : 0.0;
+            const double my_sa = p.sa[r0 + (lane & (EPI_COLS - 1))];
+            double *out = p.C + (size_t)z * p.slab + (size_t)r0 * p.ldc + b;
+            bar_wait(tmem_full, tl & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 64) TC_STAMP(4);
+            int acc[ND][EPI_COLS];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * EPI_COLS);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) tmem_ld8(taddr + (uint32_t)(d * TN), acc[d]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int d = 0; d < ND; ++d) tmem_ld16(taddr + (uint32_t)(d * TN), acc[d]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(tmem_empty);
+            if (tid == 64) TC_STAMP(5);
+            // sum_d acc_d 256^-d by Horner in fp64 (every step exact: < 2^53 significant bits)
+            // branch-free and level-major, so that the 16 independent Horner chains of a thread interleave (the FP64 pipe has
+            // a long latency: one chain after the other cost 4200 cycles per tile, measured)
+            double t[EPI_COLS];
+#pragma unroll
+            for (int j = 0; j < EPI_COLS; ++j) t[j] = i2d(acc[ND - 1][j]);
+#pragma unroll
+            for (int d = ND - 2; d >= 0; --d)
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) t[j] = fma(t[j], 0.00390625, i2d(acc[d][j]));
+            const double xs_any = any ? xs : 0.0;      // an empty split-K slab stores zeros
+#pragma unroll
+            for (int j = 0; j < EPI_COLS; ++j) {
+                const double v = t[j] * (xs_any * __shfl_sync(0xffffffffu, my_sa, j));
+                if (live) out[(size_t)j * p.ldc] = v;
             }
-            double v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                double t = 0.0;
-                if (nk > 0) {
-                    t = (double)acc[ND - 1][j];
-#pragma unroll
-                    for (int d = ND - 2; d >= 0; --d) t = fma(t, 0.0078125, (double)acc[d][j]);
-                }
-                v[j] = t * ra * __ldg(p.sx + col0 + c0 + j);
-            }
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2 *>(out + c0 + j) = make_double2(v[j], v[j + 1]);
-            }
+            if (tid == 64) TC_STAMP(6);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
     if (warp == 1) {
@@ -204,24 +275,29 @@ tc_i8_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant_
 // ---------------------------------------------------------------------------
 // digit planes
 // ---------------------------------------------------------------------------
-// signed base-128 digits of v = x / scale * 64 (|v| <= 64): d_0 = rint(v), v <- (v - d_0) * 128, ...  (all steps exact)
+// signed base-256 digits of the fixed-point number W = rint(x / scale * 2^(8 ND - 2)), |x| <= scale: taken from the least
+// significant end, d = ((W + 128) mod 256) - 128 in [-128, 127], W <- (W - d) / 256 (exact); the top digit is then within
+// [-65, 65].  x = scale / 64 * sum_s d_s * 256^-s up to the rounding of W (2^-(8 ND - 1) of scale).
 template <int ND>
-__device__ __forceinline__ void digits(double v, int8_t (&d)[ND])
+__device__ __forceinline__ void digits(double xf, int8_t (&d)[ND])   // xf = x * 2^(8 ND - 2) / scale
 {
+    long long W = __double2ll_rn(xf);
 #pragma unroll
-    for (int s = 0; s < ND; ++s) {
-        const double r = rint(v);
-        d[s] = (int8_t)(int)r;
-        v = (v - r) * 128.0;
+    for (int s = ND - 1; s > 0; --s) {
+        const int dd = (int)((W + 128) & 255) - 128;
+        d[s] = (int8_t)dd;
+        W = (W - dd) >> 8;
     }
+    d[0] = (int8_t)W;
 }
-// power of two >= max|x| (1 for a zero vector), returned as the factor 64 / scale applied before the digits
+// power of two >= max|x| (1 for a zero vector): returns the factor 2^(8 ND - 2) / scale applied before the digits
+template <int ND>
 __device__ __forceinline__ double pow2_scale(double mx, double *scale_over_64)
 {
     int e = 0;
     if (mx > 0.0 && mx < 1e300) frexp(mx, &e);      // mx = f * 2^e, f in [0.5, 1)
     *scale_over_64 = ldexp(1.0, e - 6);
-    return ldexp(1.0, 6 - e);
+    return ldexp(1.0, 8 * ND - 2 - e);
 }
 
 // Rows of a fixed fp64 matrix A [R x ld] (kdim live columns) -> planes [ND][R][kdim] int8 + sa[r].  One warp per row.
@@ -237,7 +313,7 @@ __global__ void slice_rows_kernel(const double *__restrict__ A, int ld, int R, i
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     double so64;
-    const double f = pow2_scale(mx, &so64);
+    const double f = pow2_scale<ND>(mx, &so64);
     if (lane == 0) sa[r] = so64;
     const size_t plane = (size_t)R * kdim;
     for (int k = lane * 4; k < kdim; k += 128) {     // kdim is a multiple of 64: char4 stores
@@ -279,7 +355,7 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double *__restric
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int b0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
     double so64;
-    const double f = pow2_scale(mx[b0 + tx], &so64);
+    const double f = pow2_scale<ND>(mx[b0 + tx], &so64);
     if (blockIdx.y == 0 && ty == 0) {
         sx[b0 + tx] = so64;
         if (zero_other) zero_other[b0 + tx] = 0.0;

@@ -66,11 +66,16 @@ def _bands(w, f, a, d):
     return idx_band, np.nonzero(mask)[0], U, L
 
 
-def assemble_fir_ap(n, f, a, d, obj, peak, oversamp=15):
-    """One design -> (w rows, lo, hi, stop mask, objective weight, radii) in the reference's row order."""
-    f = np.asarray(f, float).ravel() * np.pi                              # :44
-    a = np.asarray(a, float).ravel()
-    d = np.asarray(d, float).ravel()
+_AP_ROWS_CACHE: dict = {}
+
+
+def _ap_rows(n, f, a, d, oversamp):
+    """Grid rows and bounds of one band specification (everything in assemble_fir_ap that does not depend on obj / Peak).
+    Cached: the designs of a trade-off sweep share it, and identical array objects let the batch code fill in blocks."""
+    key = (n, f.tobytes(), a.tobytes(), d.tobytes(), oversamp)
+    hit = _AP_ROWS_CACHE.get(key)
+    if hit is not None:
+        return hit
     m = 2 * n * oversamp                                                  # :45-46
     base = np.linspace(-np.pi, np.pi, m)
     w = np.sort(np.concatenate([base, f]))                                # :47-48
@@ -87,6 +92,20 @@ def assemble_fir_ap(n, f, a, d, obj, peak, oversamp=15):
     L_b = L_b ** 2
     L_b[L_b < 1e-20] = 1e-20                                              # :115-116 (epsilon^2)
     stop = np.sqrt(U_b) < np.sqrt(U_b).min() + 1e-2                       # :125
+    for v in (w, L_b, U_b, stop):
+        v.setflags(write=False)
+    if len(_AP_ROWS_CACHE) > 64:
+        _AP_ROWS_CACHE.clear()
+    _AP_ROWS_CACHE[key] = (w, L_b, U_b, stop)
+    return _AP_ROWS_CACHE[key]
+
+
+def assemble_fir_ap(n, f, a, d, obj, peak, oversamp=15):
+    """One design -> (w rows, lo, hi, stop mask, objective weight, radii) in the reference's row order."""
+    f = np.asarray(f, float).ravel() * np.pi                              # :44
+    a = np.asarray(a, float).ravel()
+    d = np.asarray(d, float).ravel()
+    w, L_b, U_b, stop = _ap_rows(int(n), f, a, d, int(oversamp))
     radius = (n - np.arange(1, n + 1) + 1) * float(peak)                  # :166-168
     return dict(n=n, w=w, lo=L_b, hi=U_b, stop=stop, obj=float(obj), radius=radius)
 
@@ -102,9 +121,20 @@ def _solve_batch_ap(n, designs, max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_
     Returns x [B, 2n-1], ripple_stop [B], info [B, 8].
     """
     B = len(designs)
-    allw = np.unique(np.concatenate([p["w"] for p in designs]))
+    # designs of a sweep mostly share their grid (only band-edge samples differ): deduplicate before the union
+    keys = [id(p["w"]) for p in designs]           # assemble_fir_ap hands out cached (shared) arrays per band specification
+    distinct = {}
+    for k, p in zip(keys, designs):
+        distinct.setdefault(k, p["w"])
+    allw = np.unique(np.concatenate(list(distinct.values())))
     M1 = allw.size
-    pos = [np.searchsorted(allw, p["w"]) for p in designs]
+    pos_of = {}
+    for k, w in distinct.items():
+        ix = np.searchsorted(allw, w)
+        sx = np.sort(ix)
+        pos_of[k] = (ix, bool((sx[1:] == sx[:-1]).any()))
+    pos = [pos_of[k][0] for k in keys]
+    has_dup = [pos_of[k][1] for k in keys]
     stop_any = np.zeros(M1, bool)
     for p, ix in zip(designs, pos):
         stop_any[ix[p["stop"]]] = True
@@ -115,26 +145,45 @@ def _solve_batch_ap(n, designs, max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_
     nx = 2 * n - 1
     N = nx
     w_row = np.concatenate([allw, allw[srows]])
-    lo = np.full((M, B), -np.inf)
-    hi = np.full((M, B), np.inf)
+    # per-design arrays are filled design-major (contiguous rows) and transposed once at the end: [dim x B] is what the
+    # C ABI takes, but column-strided writes and ufunc.at made this loop the largest host cost of a 512-design batch
+    loT = np.empty((B, M))
+    hiT = np.empty((B, M))
     c = np.zeros((N, B))
     bl = np.full((N, B), -np.inf)
     bu = np.full((N, B), np.inf)
     rho = np.zeros((n - 1, B))
     upper = np.zeros(B)
     sw = np.zeros(B)
-    for b, (p, ix) in enumerate(zip(designs, pos)):
+    groups = {}                                     # designs sharing rows and bounds are filled as one block
+    for b, p in enumerate(designs):
+        groups.setdefault((keys[b], id(p["lo"]), id(p["hi"]), id(p["stop"])), []).append(b)
+    for members in groups.values():
+        p, ix = designs[members[0]], pos[members[0]]
+        row_lo = np.full(M, -np.inf)
+        row_hi = np.full(M, np.inf)
         # a grid point may occur twice in a design (band edge coinciding with a base sample): keep the tighter
-        np.maximum.at(lo[:, b], ix, p["lo"])
-        np.minimum.at(hi[:, b], ix, p["hi"])
+        if not has_dup[members[0]]:
+            row_lo[ix] = p["lo"]
+            row_hi[ix] = p["hi"]
+        else:
+            np.maximum.at(row_lo, ix, p["lo"])
+            np.minimum.at(row_hi, ix, p["hi"])
         # `A_U(idx_stop,:)*x <= ripple_stop` with `obj*ripple_stop` in the objective (:163-165)
         #   ==  obj * max_{i in idx_stop} (A x)_i : the duplicate rows form the solver's simplex block
-        hi[M1 + srank[ix[p["stop"]]], b] = 0.0                            # membership flag of the block
-        sw[b] = p["obj"]
-        c[0, b] = 1.0                                                     # minimise x(1) + ..., :163
-        bl[0, b], bu[0, b] = -p["radius"][0], p["radius"][0]              # |x1| <= n Peak, :167 (i = 1)
-        rho[:, b] = p["radius"][1:]
-        upper[b] = p["radius"][0] + p["obj"] * p["hi"][p["stop"]].max()   # no feasible point has a larger objective
+        row_hi[M1 + srank[ix[p["stop"]]]] = 0.0                           # membership flag of the block
+        loT[members] = row_lo
+        hiT[members] = row_hi
+        stop_hi_max = p["hi"][p["stop"]].max()
+        for b in members:
+            q = designs[b]
+            sw[b] = q["obj"]
+            bl[0, b], bu[0, b] = -q["radius"][0], q["radius"][0]          # |x1| <= n Peak, :167 (i = 1)
+            rho[:, b] = q["radius"][1:]
+            upper[b] = q["radius"][0] + q["obj"] * stop_hi_max            # no feasible point has a larger objective
+    c[0, :] = 1.0                                                         # minimise x(1) + ..., :163
+    lo = np.ascontiguousarray(loT.T)
+    hi = np.ascontiguousarray(hiT.T)
     col_type = np.concatenate([[0], np.full(n - 1, 1), np.full(n - 1, 2)]).astype(np.int32)
     k = np.arange(1, n, dtype=float)
     col_kappa = np.concatenate([[0.0], k, k])

@@ -167,8 +167,115 @@ static int run_i8(int nk)
     return 0;
 }
 
+// ---- A operand staged in TMEM: tcgen05.cp 128x256b (smem -> tmem) of a 64-byte-swizzled K-major tile, then
+//      tcgen05.mma with [a_tmem].  Dumps the TMEM copy of A as well. ----
+__device__ __forceinline__ uint64_t mk_desc64(uint32_t addr)
+{
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__global__ void __launch_bounds__(128, 1) dbg_i8_ts(const int8_t *A, const int8_t *B, int *D, uint32_t *Adump, int variant)
+{
+    extern __shared__ uint8_t raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem, *sB = smem + 8192;
+    uint64_t *bar = (uint64_t *)(smem + 16384);
+    uint32_t *slot = (uint32_t *)(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 128 * 64; i += 128) {          // element (mn, k), k < 64
+        const int mn = i >> 6, k = i & 63;
+        uint32_t off = (mn >> 3) * 512 + (mn & 7) * 64 + k;
+        off ^= ((off >> 7) & 3) << 4;
+        sA[off] = (uint8_t)A[mn * 128 + k];
+        if (mn < 64) sB[off] = (uint8_t)B[mn * 128 + k];
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s32(slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    const uint32_t tA = tmem + 64;                         // A staging: 16 columns (2 k-steps of 8 columns)
+    if (tid == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t da = mk_desc64(s32(sA) + kb * 32);
+            if (variant == 0)
+                asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tA + kb * 8), "l"(da) : "memory");
+        }
+        for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t db = mk_desc64(s32(sB) + kb * 32);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem), "r"(tA + kb * 8), "l"(db), "r"(idesc),
+                         "r"(kb > 0 ? 1u : 0u)
+                         : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+    }
+    asm volatile("{\n\t.reg .pred p;\n\tWT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra ET;\n\tbra WT;\n\tET:\n\t}" ::"r"(s32(bar))
+                 : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < 80; c0 += 8) {
+        uint32_t r[8];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 8; ++j) {
+            if (c0 < 64) D[(warp * 32 + lane) * 64 + c0 + j] = (int)r[j];
+            else Adump[(warp * 32 + lane) * 16 + (c0 - 64) + j] = r[j];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+}
+static int run_ts(int variant)
+{
+    std::vector<int8_t> A(128 * 128), B(128 * 128);
+    std::vector<int> D(128 * 64);
+    std::vector<uint32_t> Ad(128 * 16);
+    for (auto &v : A) v = (int8_t)((rand() % 255) - 127);
+    for (auto &v : B) v = (int8_t)((rand() % 255) - 127);
+    int8_t *dA, *dB; int *dD; uint32_t *dAd;
+    cudaMalloc(&dA, 16384); cudaMalloc(&dB, 16384); cudaMalloc(&dD, 128 * 64 * 4); cudaMalloc(&dAd, 128 * 16 * 4);
+    cudaMemcpy(dA, A.data(), 16384, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B.data(), 16384, cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0xff, 128 * 64 * 4); cudaMemset(dAd, 0xff, 128 * 16 * 4);
+    cudaFuncSetAttribute(dbg_i8_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, 20000);
+    dbg_i8_ts<<<1, 128, 20000>>>(dA, dB, dD, dAd, variant);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("ts variant %d: %s\n", variant, cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(D.data(), dD, 128 * 64 * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(Ad.data(), dAd, 128 * 16 * 4, cudaMemcpyDeviceToHost);
+    long long bad = 0, badA = 0;
+    for (int m = 0; m < 128; ++m) {
+        for (int n = 0; n < 64; ++n) {
+            int s = 0;
+            for (int k = 0; k < 64; ++k) s += (int)A[m * 128 + k] * (int)B[n * 128 + k];
+            bad += s != D[m * 64 + n];
+        }
+        for (int c = 0; c < 16; ++c) {
+            uint32_t w = 0;
+            for (int j = 0; j < 4; ++j) w |= (uint32_t)(uint8_t)A[m * 128 + 4 * c + j] << (8 * j);
+            badA += w != Ad[m * 16 + c];
+        }
+    }
+    printf("A-in-TMEM variant %d: D mismatches %lld of 8192, A-copy mismatches %lld of 2048; row0 A words tmem %08x %08x expect %02x%02x%02x%02x\n", variant, bad, badA,
+           Ad[0], Ad[1], (uint8_t)A[3], (uint8_t)A[2], (uint8_t)A[1], (uint8_t)A[0]);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    run_ts(0);
     run_i8<128>(1); run_i8<128>(4); run_i8<64>(4); run_i8<32>(2);
     std::vector<float> A(1024), B(1024), D(16384);
     srand(3);

@@ -2,6 +2,7 @@
 // planes -> int8 tensor-core level products -> fp64 result, compared with a long-double reference.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tc_gemm_test tc_gemm_test.cu
 // usage: tc_gemm_test kdim R Bp [P split-K slabs]
+#define TC_TIMING
 #include "../../multiband_rf_pulse_design_b200/csrc/tc_gemm.cuh"
 #include <cmath>
 #include <cstdio>
@@ -33,12 +34,16 @@ static int run(int kdim, int R, int Bp, int P)
     cudaMemset(dC, 0xff, (size_t)P * R * Bp * 8);
     slice_rows_kernel<ND><<<(R * 32 + 255) / 256, 256>>>(dA, kdim, R, kdim, pA, dsa);
     CUtensorMap mA, mX;
-    if (!make_map(&mA, pA, kdim, R, ND, TM) || !make_map(&mX, pX, kdim, Bp, ND, TN)) { printf("tensor map failed\n"); return 1; }
+    if (!make_map(&mA, pA, kdim, R, ND, TN) || !make_map(&mX, pX, kdim, Bp, ND, TM)) { printf("tensor map failed\n"); return 1; }
     cudaFuncSetAttribute(tc_i8_gemm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ND));
     Params p;
     p.C = dC; p.slab = (long long)R * Bp; p.ldc = Bp; p.R = R; p.kdim_total = kdim;
     p.kchunk = ((kdim + P - 1) / P + KB - 1) / KB * KB; p.sa = dsa; p.sx = dsx;
-    dim3 grid(Bp / TN, (R + TM - 1) / TM, P);
+    p.nslab = P;
+    const int ntiles = (R / TN) * ((Bp + TM - 1) / TM) * P;
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    dim3 grid(ntiles < nsm ? ntiles : nsm, 1, 1);
     auto product = [&]() {
         cudaMemsetAsync(dmx, 0, Bp * 8);
         col_absmax_kernel<<<dim3(Bp / 64, 16), 256>>>(dX, kdim, Bp, dmx);
@@ -75,6 +80,25 @@ static int run(int kdim, int R, int Bp, int P)
             if (amax * xmax > 0) maxrel = fmax(maxrel, e / (amax * xmax * sqrt((double)kdim)));
             if (!(e == e)) { printf("NaN at %d %d\n", r, b); return 3; }
         }
+    {   // phase timeline of a few CTAs (clock64 deltas in cycles; stamps: 0 start, 1 setup done, 2 first stage landed, 3 MMAs issued,
+        // 4 accumulators complete, 5 TMEM drained, 6 tile stored) -- first tile of every CTA
+        const size_t nct = (size_t)grid.x;
+        long long *dt;
+        cudaMalloc(&dt, nct * 64); cudaMemset(dt, 0, nct * 64);
+        cudaMemcpyToSymbol(mbrf::tc::tc_timing, &dt, sizeof dt);
+        tc_i8_gemm_kernel<ND><<<grid, THREADS, smem_bytes(ND)>>>(mA, mX, p);
+        cudaDeviceSynchronize();
+        std::vector<long long> ht(nct * 8);
+        cudaMemcpy(ht.data(), dt, nct * 64, cudaMemcpyDeviceToHost);
+        long long *nul = nullptr;
+        cudaMemcpyToSymbol(mbrf::tc::tc_timing, &nul, sizeof nul);
+        double avg[7] = {0};
+        for (size_t c = 0; c < nct; ++c)
+            for (int i = 2; i < 7; ++i) avg[i] += (double)(ht[c * 8 + i] - ht[c * 8 + i - 1]) / nct;
+        printf("   first tile, mean cycles over %zu CTAs: first stage %.0f | issue %.0f | drain %.0f | TMEM->regs %.0f | convert+store %.0f\n", nct,
+               avg[2], avg[3], avg[4], avg[5], avg[6]);
+        cudaFree(dt);
+    }
     const double flops = 2.0 * kdim * R * Bp;
     printf("ND %d kdim %d R %d Bp %d P %d: max abs err %.3e, err/(amax*xmax*sqrt(k)) %.3e | product %.3f ms (gemm %.3f ms = %.1f TFLOP/s fp64-equivalent, %.0f TOP/s int8)\n",
            ND, kdim, R, Bp, P, maxabs, maxrel, ms_all, ms_mm, flops / ms_mm / 1e9, flops * (ND * (ND + 1) / 2) / ms_mm / 1e9);
@@ -86,8 +110,8 @@ int main(int argc, char **argv)
 {
     const int kdim = argc > 1 ? atoi(argv[1]) : 512, R = argc > 2 ? atoi(argv[2]) : 256, Bp = argc > 3 ? atoi(argv[3]) : 128;
     const int P = argc > 4 ? atoi(argv[4]) : 1;
-    int rc = run<4>(kdim, R, Bp, P);
-    if (!rc) rc = run<5>(kdim, R, Bp, P);
+    int rc = run<5>(kdim, R, Bp, P);
     if (!rc) rc = run<6>(kdim, R, Bp, P);
+    if (!rc) rc = run<4>(kdim, R, Bp, P);
     return rc;
 }
