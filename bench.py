@@ -235,6 +235,9 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
         single = {"workload": "cfg3: fir_qp_cvx min-energy multiband FIR, N=256, dual-band H-1 spec, k=120, obj=1, single design",
                   "status": st3, "seconds": time.perf_counter() - t1, "iterations": float(ex3["info"][1]),
                   "objective": float(ex3["info"][2]), "max_violation": float(ex3["info"][4])}
+    roof = None
+    if rank == 0:
+        roof = solver_roofline(lib, per_gpu)
     info = r["info"]
     solved = int((info[:, 0] == 1).sum())
     iters = float(info[:, 1].max()) if info.size else 0.0
@@ -247,11 +250,60 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
             "designs": total, "designs_per_gpu": per_gpu, "solved_on_rank0": solved, "local_designs_rank0": int(info.shape[0]),
             "seconds": sec, "iterations_max": iters, "gpu_launches": int(launches),
             "workload": "cfg4 slice: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, obj x Peak trade-off grid",
-            "single_design": single,
+            "single_design": single, "roofline": roof,
             "tolerances": {"eps_pr": fir.EPS_PR, "eps_gap_rel": fir.EPS_GAP, "eps_dr": fir.EPS_DR},
             "gemm_tflops_useful": flops / sec / 1e12, "iterations_mean": float(info[:, 1].mean()) if info.size else 0.0,
-            "note": "fp64 restarted PDHG; products on the FP64 tensor path (mma.sync m8n8k4); whole call timed on the host "
-                    "(assembly + PCIe + solve); gemm_tflops_useful = 4*Mp*Np*sum_b(iterations_b) / wall time (rank 0's designs x world)"}
+            "note": "fp64 restarted PDHG; the two products of every iteration run on tcgen05 int8 tiles (split-integer, 5 base-256 "
+                    "digit planes, exact int32 level sums in TMEM, ~1e-11 relative), convergence checks on fp64 mma.sync tiles; whole "
+                    "call timed on the host (assembly + PCIe + solve); gemm_tflops_useful = fp64-equivalent 4*Mp*Np*sum_b(iterations_b) "
+                    "/ wall time (rank 0's designs x world)"}
+
+
+def solver_roofline(lib, per_gpu, nd=5):
+    """Roofline of the solver's dominant kernel, tc::tc_i8_gemm_kernel<5>: the two products of one PDHG iteration at the
+    bench shape (K: 7808 x 512, `per_gpu` designs), each timed alone with CUDA events inside libmbrf
+    (mbrf_tc_product_device).  Tensor bound: int8 operations 2*R*k*B per digit-plane product, nd(nd+1)/2 = 15 products."""
+    import torch
+    from multiband_rf_pulse_design_b200._lib import check
+    Mp, Np, Bp = C.c_int(), C.c_int(), C.c_int()
+    lib.mbrf_pdhg_padded_sizes(7686 + 118, 511, per_gpu, C.byref(Mp), C.byref(Np), C.byref(Bp))
+    Mp, Np, Bp = Mp.value, Np.value, Bp.value
+    if Bp < 64:
+        return None
+    g = torch.Generator(device="cuda").manual_seed(0)
+    K = torch.rand((Mp, Np), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    KT = K.t().contiguous()
+    z = torch.rand((Np, Bp), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    y = torch.rand((Mp, Bp), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    tiles = (Np // 64) * ((Bp + 127) // 128)
+    P = max(1, min(32, Mp // 256, (2 * 148) // tiles))          # same split as pdhg.cu:split_k_tc
+    out = torch.empty((max(P, 1), max(Mp, Np), Bp), dtype=torch.float64, device="cuda")
+    ms = {}
+    for name, (A, X, R, kd, ns) in {"K*zbar": (K, z, Mp, Np, 1), "K^T*y": (KT, y, Np, Mp, P)}.items():
+        a, b = C.c_float(), C.c_float()
+        check(lib.mbrf_tc_product_device(A.data_ptr(), R, kd, X.data_ptr(), Bp, nd, ns, out.data_ptr(), 20,
+                                         C.cast(C.byref(a), C.c_void_p), C.cast(C.byref(b), C.c_void_p), None))
+        ms[name] = (a.value, b.value)
+    torch.cuda.synchronize()
+    ops = 2.0 * Mp * Np * Bp * (nd * (nd + 1) // 2)              # int8 multiply-adds x2, per product
+    t = ms["K*zbar"][0] + ms["K^T*y"][0]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    if "bf16_tflops" in peaks:
+        peak, src = 2.0 * float(peaks["bf16_tflops"]), "2 x MEASURED_PEAKS.json bf16_tflops (int8 issues at twice the bf16 rate; no int8 figure is recorded)"
+    else:
+        peak, src = 4500.0, "fallback: nominal dense int8 4.5 POP/s (B200_PROFILING.md: 2 x bf16 2.25 PFLOP/s)"
+    ach = 2 * ops / (t * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "mbrf::tc::tc_i8_gemm_kernel<%d>" % nd, "achieved": ach, "peak": peak, "unit": "TOP/s (int8)",
+            "frac": ach / peak, "traffic": None, "peak_source": src,
+            "fp64_equivalent_tflops": 2 * 2.0 * Mp * Np * Bp / (t * 1e-3) / 1e12,
+            "kernel_ms": {k: v[0] for k, v in ms.items()}, "with_digit_planes_ms": {k: v[1] for k, v in ms.items()},
+            "shape": {"Mp": Mp, "Np": Np, "Bp": Bp, "digit_planes": nd, "split_k": P},
+            "note": "algorithmic work = 2*Mp*Np*Bp int8 MACs x2 per digit-plane product x 15 products x 2 GEMMs per iteration; the "
+                    "fp64 tensor path this replaced (mma.sync m8n8k4) ran the same two products in 0.139 + 0.148 ms"}
 
 
 # ----------------------------------------------------------------------------

@@ -237,6 +237,11 @@ int mbrf_pdhg_set_gemm(int mode);       /* product kernels of the iterations: 2 
                                            1 FP64 tensor tiles mma.sync.m8n8k4, 0 SIMT DFMA tiles; checks always run in fp64 */
 int mbrf_pdhg_set_tc_digits(int nd);    /* base-256 digit planes of the split-integer product: 4, 5 (default) or 6 */
 unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
+/* The tcgen05 split-integer product alone, device pointers: C[nslab][R x Bp] = A[R x kdim] * X[kdim x Bp] over nslab ranges of
+ * the reduction (sum the slabs); R, kdim, Bp multiples of 64; nd = 4..6.  Timed with CUDA events on `stream` over `reps`
+ * repetitions: ms_gemm = MMA kernel alone, ms_total = digit planes of X + MMA kernel (either may be NULL). */
+int mbrf_tc_product_device(const double *A, int R, int kdim, const double *X, int Bp, int nd, int nslab, double *C, int reps,
+                           float *ms_gemm, float *ms_total, void *stream);
 int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk,
                            double *c, double *lo, double *hi, double *bl, double *bu,   /* destroyed: compacted */
                            const int *pair_i, const int *pair_j, int npairs, double *rho,

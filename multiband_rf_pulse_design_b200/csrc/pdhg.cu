@@ -227,42 +227,41 @@ dgemm_mma_kernel(const double *__restrict__ AT, int ldat, const double *__restri
 // coalesced loads, the vector kept in shared memory, warp-shuffle reduction.
 //   out[r] = sum_k A[r][k] * x[k]      A row-major [R x ld], kdim multiple of 64
 // ---------------------------------------------------------------------------
-// out[o][b] = sum_k AT[k][o] * x[k][b]  for NB = 1, 2, 4 or 8 designs, AT k-major exactly as in the GEMM kernels.
-// A CTA owns 64 outputs; its 4 warps-pairs ("quarters") take every 4th k of a 64-row tile, so a thread issues one
-// coalesced 8-byte load of AT per 1..8 FMAs against the broadcast x tile in shared memory; the quarters are summed
-// through shared memory.  blockIdx.y splits a long reduction into slabs like the GEMM's split-K.
+// out[r][b] = sum_k A[r][k] * x[k][b]  for NB = 1, 2, 4 or 8 designs; A row-major [R x ld] (k contiguous: K for K z, K^T for
+// K^T y).  One warp per output row: 16-byte coalesced loads (512 contiguous bytes per warp instruction), NB accumulators
+// per lane, warp-shuffle reduction.  blockIdx.y splits a long reduction into slabs like the GEMM's split-K.  The matrix
+// (tens of MB) stays in the 126 MB L2, so the pass is L2-bandwidth-bound; the column-major variant this replaces had 89
+// CTAs for K z and ran at 0.4 TB/s.
 template <int NB>
 __global__ void __launch_bounds__(256)
-thin_kernel(const double *__restrict__ AT, int ldat, const double *__restrict__ X, double *__restrict__ C, int kdim,
-            int kchunk, long long slab)
+gemv_rows_kernel(const double *__restrict__ A, int ld, const double *__restrict__ X, double *__restrict__ C, int R, int kdim,
+                 int kchunk, long long slab)
 {
-    __shared__ double xs[64 * NB];
-    __shared__ double red[4][64][NB];
-    const int tid = threadIdx.x, ol = tid & 63, q = tid >> 6;
-    const int o = blockIdx.x * 64 + ol;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= R) return;
     const int k_begin = blockIdx.y * kchunk, k_end = min(kdim, k_begin + kchunk);
+    const double *a = A + (size_t)r * ld;
     double acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.0;
-    for (int k0 = k_begin; k0 < k_end; k0 += 64) {
-        const int nk = min(64, k_end - k0);
-        for (int e = tid; e < nk * NB; e += 256) xs[e] = X[(size_t)k0 * NB + e];
-        __syncthreads();
 #pragma unroll 4
-        for (int kk = q; kk < nk; kk += 4) {
-            const double a = AT[(size_t)(k0 + kk) * ldat + o];
+    for (int k = k_begin + 2 * lane; k < k_end; k += 64) {          // k ranges are multiples of 64
+        const double2 av = *reinterpret_cast<const double2 *>(a + k);
 #pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = fma(a, xs[kk * NB + b], acc[b]);
+        for (int b = 0; b < NB; ++b) {
+            acc[b] = fma(av.x, __ldg(X + (size_t)k * NB + b), acc[b]);
+            acc[b] = fma(av.y, __ldg(X + (size_t)(k + 1) * NB + b), acc[b]);
         }
-        __syncthreads();
     }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) red[q][ol][b] = acc[b];
-    __syncthreads();
-    if (q == 0) {
-        double *out = C + (size_t)blockIdx.y * slab + (size_t)o * NB;
+    for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) out[b] = red[0][ol][b] + red[1][ol][b] + red[2][ol][b] + red[3][ol][b];
+        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+    if (lane == 0) {
+        double *out = C + (size_t)blockIdx.y * slab + (size_t)r * NB;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = acc[b];
     }
 }
 
@@ -270,10 +269,10 @@ template <typename... Args>
 static void launch_thin(int nb, dim3 grid, cudaStream_t st, Args... args)
 {
     switch (nb) {
-    case 1: thin_kernel<1><<<grid, 256, 0, st>>>(args...); break;
-    case 2: thin_kernel<2><<<grid, 256, 0, st>>>(args...); break;
-    case 4: thin_kernel<4><<<grid, 256, 0, st>>>(args...); break;
-    default: thin_kernel<8><<<grid, 256, 0, st>>>(args...); break;
+    case 1: gemv_rows_kernel<1><<<grid, 256, 0, st>>>(args...); break;
+    case 2: gemv_rows_kernel<2><<<grid, 256, 0, st>>>(args...); break;
+    case 4: gemv_rows_kernel<4><<<grid, 256, 0, st>>>(args...); break;
+    default: gemv_rows_kernel<8><<<grid, 256, 0, st>>>(args...); break;
     }
 }
 
@@ -349,6 +348,28 @@ __global__ void z_hat_kernel(Problem p)
         if (j < p.nn) s2 = fma(zh, zh, s2);
     }
     atomicAdd(p.nrm + b, s2);
+}
+// thin batches (Bp <= 8): one CTA per design, the coordinates spread over its threads
+__global__ void __launch_bounds__(256) z_hat_thin_kernel(Problem p)
+{
+    __shared__ double sh[256];
+    const int b = blockIdx.x;
+    const double tau = p.ctl[b].tau;
+    const size_t stride = (size_t)p.Np * p.Bp;
+    double s2 = 0.0;
+    for (int j = threadIdx.x; j < p.Np; j += 256) {
+        const size_t o = (size_t)j * p.Bp + b;
+        double g = p.c[o];
+        for (int s = 0; s < p.P; ++s) g += p.G[s * stride + o];
+        double zh = p.z[o] - tau * g;
+        zh = fmin(fmax(zh, p.bl[o]), p.bu[o]);
+        p.zbar[o] = zh;
+        if (j < p.nn) s2 = fma(zh, zh, s2);
+    }
+    sh[threadIdx.x] = s2;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k]; __syncthreads(); }
+    if (threadIdx.x == 0) p.nrm[b] = sh[0];
 }
 __global__ void z_shrink_kernel(Problem p)
 {
@@ -693,6 +714,73 @@ __global__ void group_update_kernel(Problem p)
     }
 }
 
+// Group blocks of up to 32*R pairs: the pairs of a design stay in its warp's registers across the Michelot passes
+template <int R>
+__global__ void __launch_bounds__(256) group_update_reg_kernel(Problem p)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= p.Bp) return;
+    const double sig = p.ctl[b].sigma, w = p.gw[b];
+    double v1[R], v2[R], nr[R];
+    double sum = 0.0;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        const int i = lane + 32 * u;
+        v1[u] = v2[u] = nr[u] = 0.0;
+        if (i < p.ng) {
+            const size_t o = (size_t)(p.grow0 + 2 * i) * p.Bp + b;
+            v1[u] = p.y[o] + sig * p.S[o];
+            v2[u] = p.y[o + p.Bp] + sig * p.S[o + p.Bp];
+            nr[u] = hypot(v1[u], v2[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) sum += nr[u];
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+    double theta = 0.0;
+    if (sum > w) {                           // outside the ball: threshold the norms
+        int prev = p.ng;
+        theta = (sum - w) / p.ng;
+        for (int pass = 0; pass < 64; ++pass) {
+            double s2 = 0.0;
+            int c2 = 0;
+#pragma unroll
+            for (int u = 0; u < R; ++u)
+                if (lane + 32 * u < p.ng && nr[u] > theta) { s2 += nr[u]; ++c2; }
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, k); c2 += __shfl_xor_sync(0xffffffffu, c2, k); }
+            if (c2 == 0) break;
+            theta = (s2 - w) / c2;
+            if (c2 == prev) break;
+            prev = c2;
+        }
+    }
+    double m = 0.0;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        const int i = lane + 32 * u;
+        if (i < p.ng) {
+            const size_t o = (size_t)(p.grow0 + 2 * i) * p.Bp + b;
+            double a1 = v1[u], a2 = v2[u];
+            if (theta > 0.0) {
+                const double f = nr[u] > theta ? (nr[u] - theta) / nr[u] : 0.0;
+                a1 *= f; a2 *= f;
+            }
+            if (!(w > 0.0)) { a1 = 0.0; a2 = 0.0; }
+            p.y[o] = a1; p.y[o + p.Bp] = a2;
+            p.ys[o] += a1; p.ys[o + p.Bp] += a2;
+            m = fmax(m, fmax(fabs(a1), fabs(a2)));
+        }
+    }
+    if (p.mxy) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+        if (lane == 0) atomic_max_pos(p.mxy + b, m);
+    }
+}
+
 // reduce split-K slabs: G2 = sum_p G_p
 __global__ void reduce_slabs_kernel(Problem p)
 {
@@ -998,7 +1086,7 @@ static int split_k_tc(int Mp, int Np, int Bp)
 template <int ND>
 static int tc_product_nd(const TcState &t, const double *X, int kdim, int Bp, const CUtensorMap &mA, const CUtensorMap &mX,
                          const double *sa, int R, double *C, int P, long long slab, double *mx, bool have_max,
-                         double *zero_other, cudaStream_t st)
+                         double *zero_other, cudaStream_t st, bool gemm_only = false)
 {
     static bool attr = false;
     if (!attr) {
@@ -1012,8 +1100,10 @@ static int tc_product_nd(const TcState &t, const double *X, int kdim, int Bp, co
         tc::col_absmax_kernel<<<dim3(Bp / 64, gy), 256, 0, st>>>(X, kdim, Bp, mx);
         MBRF_LAUNCH_CHECK();
     }
-    tc::slice_cols_kernel<ND><<<dim3(Bp / 64, kdim / 64), 256, 0, st>>>(X, kdim, Bp, mx, t.pX, t.sx, zero_other);
-    MBRF_LAUNCH_CHECK();
+    if (!gemm_only) {
+        tc::slice_cols_kernel<ND><<<dim3(Bp / 64, kdim / 64), 256, 0, st>>>(X, kdim, Bp, mx, t.pX, t.sx, zero_other);
+        MBRF_LAUNCH_CHECK();
+    }
     tc::Params q;
     q.C = C; q.slab = slab; q.ldc = Bp; q.R = R; q.kdim_total = kdim;
     q.kchunk = up((kdim + P - 1) / P, tc::KB); q.sa = sa; q.sx = t.sx; q.nslab = P;
@@ -1042,7 +1132,7 @@ static void tc_slice_rows(const double *A, int ld, int R, int kdim, int8_t *out,
 static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st, const TcState *tcs = nullptr, bool have_max = false)
 {
     if (p.Bp <= 8) {   // thin batch (1..8 designs): one pass over K^T, bound by streaming the matrix
-        launch_thin(p.Bp, dim3(p.Mp / 64, 1), st, p.KT, p.Mp, X, C, p.Np, p.Np, 0LL);
+        launch_thin(p.Bp, dim3(p.Mp / 8, 1), st, p.K, p.ldk, X, C, p.Mp, p.Np, p.Np, 0LL);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     }
@@ -1059,7 +1149,7 @@ static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st
 {
     if (p.Bp <= 8) {   // thin batch: one pass over K, the long reduction split into p.P slabs
         const int kc = up((p.Mp + p.P - 1) / p.P, 64);
-        launch_thin(p.Bp, dim3(p.Np / 64, p.P), st, p.K, p.ldk, Y, G, p.Mp, kc, (long long)p.Np * p.Bp);
+        launch_thin(p.Bp, dim3(p.Np / 8, p.P), st, p.KT, p.Mp, Y, G, p.Np, p.Mp, kc, (long long)p.Np * p.Bp);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     }
@@ -1105,6 +1195,74 @@ int mbrf_pdhg_set_option(int which, double value)
     if (which < 0 || which > 4 || !(value > 0.0)) return MBRF_EINVAL;
     g_opt[which] = value;
     return MBRF_OK;
+}
+
+/*
+ * The split-integer tcgen05 product on its own (tests: parity with fp64; bench.py: kernel duration for the roofline).
+ * Device pointers.  C[nslab][R x Bp] = A[R x kdim] * X[kdim x Bp] split over nslab ranges of the reduction (the caller sums
+ * the slabs); R, kdim, Bp multiples of 64, nd = 4..6 digit planes.  reps timed repetitions (CUDA events on `stream`):
+ * ms_gemm = mean duration of the MMA kernel alone, ms_total = per-design maxima + digit planes of X + MMA kernel.
+ */
+int mbrf_tc_product_device(const double *A, int R, int kdim, const double *X, int Bp, int nd, int nslab, double *C, int reps,
+                           float *ms_gemm, float *ms_total, void *stream)
+{
+    if (int rc = require_device()) return rc;
+    if (!A || !X || !C || R < 64 || kdim < 64 || Bp < 64 || R % 64 || kdim % 64 || Bp % 64 || nd < 4 || nd > tc::MAX_ND || nslab < 1 ||
+        reps < 1) {
+        set_error("tc_product: bad arguments (R=%d kdim=%d Bp=%d nd=%d nslab=%d)", R, kdim, Bp, nd, nslab);
+        return MBRF_EINVAL;
+    }
+    if ((double)up((kdim + nslab - 1) / nslab, tc::KB) * nd * 16384.0 >= 2147483648.0) {
+        set_error("tc_product: reduction range too long for exact int32 level sums, use more slabs");
+        return MBRF_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    TcState t;
+    t.nd = nd;
+    char *buf = nullptr;
+    const size_t bA = (size_t)nd * R * kdim, bX = (size_t)nd * Bp * kdim;
+    const size_t total = ((bA + 255) / 256 + (bX + 255) / 256) * 256 + ((size_t)R + 3 * (size_t)Bp) * 8 + 1024;
+    MBRF_CUDA(cudaMalloc(&buf, total));
+    struct Free { char *p; ~Free() { cudaFree(p); } } guard{buf};
+    t.pK = (int8_t *)buf;
+    t.pX = (int8_t *)(buf + (bA + 255) / 256 * 256);
+    t.saK = (double *)((char *)t.pX + (bX + 255) / 256 * 256);
+    t.sx = t.saK + R; t.mxy = t.sx + Bp; t.mxz = t.mxy + Bp;
+    switch (nd) {
+    case 4: tc_slice_rows<4>(A, kdim, R, kdim, t.pK, t.saK, st); break;
+    case 5: tc_slice_rows<5>(A, kdim, R, kdim, t.pK, t.saK, st); break;
+    default: tc_slice_rows<6>(A, kdim, R, kdim, t.pK, t.saK, st); break;
+    }
+    MBRF_LAUNCH_CHECK();
+    if (!tc::make_map(&t.mK, t.pK, kdim, R, nd, tc::TN) || !tc::make_map(&t.mXn, t.pX, kdim, Bp, nd, tc::TM)) {
+        set_error("tc_product: cuTensorMapEncodeTiled failed");
+        return MBRF_ECUDA;
+    }
+    t.on = true;
+    cudaEvent_t e0, e1;
+    MBRF_CUDA(cudaEventCreate(&e0));
+    MBRF_CUDA(cudaEventCreate(&e1));
+    auto timed = [&](bool whole, float *out) -> int {
+        int rc = tc_product(t, X, kdim, Bp, t.mK, t.mXn, t.saK, R, C, nslab, (long long)R * Bp, t.mxy, false, nullptr, st);   // warm
+        if (rc) return rc;
+        MBRF_CUDA(cudaEventRecord(e0, st));
+        for (int i = 0; i < reps && !rc; ++i)
+            rc = whole ? tc_product(t, X, kdim, Bp, t.mK, t.mXn, t.saK, R, C, nslab, (long long)R * Bp, t.mxy, false, nullptr, st)
+                       : tc_product(t, X, kdim, Bp, t.mK, t.mXn, t.saK, R, C, nslab, (long long)R * Bp, t.mxy, true, nullptr, st, true);
+        if (rc) return rc;
+        MBRF_CUDA(cudaEventRecord(e1, st));
+        MBRF_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MBRF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (out) *out = ms / reps;
+        return MBRF_OK;
+    };
+    int rc = timed(true, ms_total);
+    if (!rc && ms_gemm) rc = timed(false, ms_gemm);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    MBRF_CUDA(cudaStreamSynchronize(st));
+    return rc;
 }
 
 // sizes of the padded problem and of the workspace (bytes) for given live sizes
@@ -1331,8 +1489,12 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         const bool wide = p.Bp >= 64;
         if (int rc = gemm_tn(p, p.y, p.G, st, &tcs, !first)) return rc;
         if (p.nn > 0) {
-            MBRF_CUDA(cudaMemsetAsync(p.nrm, 0, (size_t)p.Bp * 8, st));
-            z_hat_kernel<<<dim3((p.Bp + 63) / 64, 16), 64, 0, st>>>(p);
+            if (p.Bp <= 8) {
+                z_hat_thin_kernel<<<p.Bp, 256, 0, st>>>(p);
+            } else {
+                MBRF_CUDA(cudaMemsetAsync(p.nrm, 0, (size_t)p.Bp * 8, st));
+                z_hat_kernel<<<dim3((p.Bp + 63) / 64, 16), 64, 0, st>>>(p);
+            }
             MBRF_LAUNCH_CHECK();
             z_shrink_kernel<<<gz, TPB, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
@@ -1354,7 +1516,8 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             MBRF_LAUNCH_CHECK();
         }
         if (p.ng > 0) {
-            group_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
+            if (p.ng <= 256) group_update_reg_kernel<8><<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
+            else group_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
         }
         return MBRF_OK;
