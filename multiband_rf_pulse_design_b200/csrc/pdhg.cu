@@ -10,7 +10,7 @@
 //   * the two products of an iteration, K * Zbar and K^T * Y, are dense fp64 GEMMs
 //     [Mp x Np] x [Np x Bp] and [Np x Mp] x [Mp x Bp] (kernels dgemm_nn / dgemm_tn below), and
 //   * all vector kernels (prox, projections, reductions) are coalesced over designs.
-// A single design is the same code with Bp = 16 (the matrix then streams from L2: HBM/L2-bound).
+// Batches of 1..8 designs take matrix-vector kernels (the matrix then streams from L2).
 //
 // Iteration (Chambolle-Pock with PDLP-style restarts and primal weight, per design b):
 //     g    = c + K^T y
@@ -21,10 +21,10 @@
 //     err = max(row violation, natural residual ||z - P_X(z - g)||_inf, |c^T z - (-h*(y) + g^T z)|)
 // and the better one becomes the restart candidate (sufficient / necessary decay or 0.36 rule).
 //
-// Precision: fp64 throughout.  The tolerance of the path (constraint violation <= 1e-6 on |H|^2 values
-// of order 1, objective 1e-4 relative on values of order 1e-2) is reached only in the last ~70 % of
-// the iterations, where fp32-accumulate tensor-core products (tcgen05 has no fp64 kind) no longer
-// contract; see DESIGN.md section 6 for the measured numbers and the split-precision plan.
+// Precision: fp64 state and fp64 convergence checks.  The two products of every iteration run on the tcgen05 tensor cores
+// as a split-integer product (tc_gemm.cuh: int8 digit planes, exact int32 level sums in TMEM, ~1e-11 relative: the solver takes
+// exactly the iterations it takes on fp64 tiles); the fp64 mma.sync / SIMT tile kernels below serve the checks, the power
+// iteration and mbrf_pdhg_set_gemm(1 / 0).  See DESIGN.md section 6 for the measured numbers.
 #include "common.h"
 #include "tc_gemm.cuh"
 
