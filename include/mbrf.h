@@ -42,6 +42,7 @@ const char *mbrf_version(void);
 const char *mbrf_last_error(void);
 int  mbrf_device_count(void);             /* >= 0, never fails */
 int  mbrf_set_device(int device);         /* device used by this host thread's later calls */
+int  mbrf_get_device(int *device);        /* the calling host thread's current device (worker threads inherit nothing) */
 int  mbrf_device_sm_count(int *sm_count); /* multiprocessors of the current device */
 /* counts kernel launches made by this library on the calling process (for bench `gpu_launches`) */
 unsigned long long mbrf_launch_count(void);
@@ -228,6 +229,15 @@ int mbrf_fir_pdhg_solve2(const double *w_row, const double *row_phase, const dou
                          const double *obj_upper, const mbrf_pdhg_blocks *blocks,
                          int max_iter, int check_every, double eps_pr, double eps_dr, double eps_gap,
                          double *z_out, double *info_out, double *colscale_out);
+
+/* Warm start of the next mbrf_fir_pdhg_solve / _solve2 call made by this host thread (consumed by that call).  Host pointers in
+ * the caller's units, valid until that call returns; any may be NULL: z_init [N x B], y_init [M x B] starting iterate and
+ * multipliers, omega_init [B] primal weights; y_out [M x B], omega_out [B] receive the final multipliers / primal weights
+ * (for warm-starting a neighbouring design of a sweep, which fir_ap.m-style searches solve one after the other). */
+int mbrf_fir_pdhg_warm_start(const double *z_init, const double *y_init, const double *omega_init, double *y_out,
+                             double *omega_out);
+/* the same for mbrf_pdhg_solve_device: device iterates [Np x Bp] / [Mp x Bp], host primal weights [Bp] in / out */
+int mbrf_pdhg_warm_start_device(const double *z_init, const double *y_init, const double *omega_init, double *omega_out);
 
 /* Device-resident core of the above on a padded batch (Mp, Np, Bp multiples of 64; arrays [dim x Bp]);
  * K row-major [Mp x ldk] with columns already scaled, KT its transpose [Np x Mp]. */

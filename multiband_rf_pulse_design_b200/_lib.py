@@ -38,6 +38,7 @@ SIGNATURES = {
     "mbrf_last_error": (C.c_char_p, []),
     "mbrf_device_count": (_i, []),
     "mbrf_set_device": (_i, [_i]),
+    "mbrf_get_device": (_i, [c_int_p]),
     "mbrf_device_sm_count": (_i, [c_int_p]),
     "mbrf_launch_count": (C.c_ulonglong, []),
     "mbrf_measure_fp64_peak": (_i, [c_double_p, c_double_p]),
@@ -60,6 +61,8 @@ SIGNATURES = {
     "mbrf_pdhg_set_tc_digits": (_i, [_i]),
     "mbrf_tc_product_device": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mbrf_pdhg_set_option": (_i, [_i, _d]),
+    "mbrf_fir_pdhg_warm_start": (_i, [_dp, _dp, _dp, _dp, _dp]),
+    "mbrf_pdhg_warm_start_device": (_i, [_vp, _vp, _vp, _vp]),
     "mbrf_pdhg_workspace_bytes": (C.c_ulonglong, [_i, _i, _i]),
     "mbrf_pdhg_solve_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp,
                                     _vp, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),

@@ -92,6 +92,14 @@ int mbrf_set_device(int device)
     return MBRF_OK;
 }
 
+int mbrf_get_device(int *device)
+{
+    if (!device) return MBRF_EINVAL;
+    if (int rc = mbrf::require_device()) return rc;
+    MBRF_CUDA(cudaGetDevice(device));
+    return MBRF_OK;
+}
+
 int mbrf_device_sm_count(int *out)
 {
     if (!out) return MBRF_EINVAL;

@@ -9,13 +9,17 @@
 // plus one optional extra column with explicit per-row coefficients (ripple_stop of fir_ap_cvx.m:165).
 #include "common.h"
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 extern "C" {
 int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
 unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
+int mbrf_pdhg_warm_start_device(const double *z_init, const double *y_init, const double *omega_init, double *omega_out);
 int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, int ldk, double *c, double *lo,
                            double *hi, double *bl, double *bu, const int *pair_i,
                            const int *pair_j, int npairs, double *rho, int Bp, int B,
@@ -96,6 +100,9 @@ struct Ctx {
     int stream_device = -1;
 };
 static thread_local Ctx t_ctx;
+// warm start / multiplier output of this host thread's next solve (host pointers, caller's units); consumed by that call
+struct WarmHost { const double *z = nullptr, *y = nullptr, *omega = nullptr; double *y_out = nullptr, *omega_out = nullptr; };
+static thread_local WarmHost t_warm_host;
 
 }  // namespace fir
 }  // namespace mbrf
@@ -123,7 +130,12 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
                       const mbrf_pdhg_blocks *blocks, int max_iter, int check_every, double eps_pr, double eps_dr,
                       double eps_gap, double *z_out, double *info_out, double *colscale_out)
 {
+    const WarmHost warm = t_warm_host;
+    t_warm_host = WarmHost();
     if (int rc = require_device()) return rc;
+    const bool timing = getenv("MBRF_TIMING") != nullptr;     // developer trace of the host-side phases (stderr)
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
     if (M <= 0 || N <= 0 || B <= 0 || !w_row || !col_type || !col_kappa || !col_amp || !c || !lo || !hi || !bl ||
         !bu || !z_out || !info_out || npairs < 0 || (npairs && (!pair_i || !pair_j || !rho)) || tcol >= N || nnz < 0 ||
         (nnz && (!ti || !tj || !tv))) {
@@ -149,7 +161,7 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
                  bws = al(mbrf_pdhg_workspace_bytes(Mp, Np, Bp));
     const size_t bnz = al((size_t)(nnz > 0 ? nnz : 1) * 8);
     const size_t total = 3 * bnz + 2 * bw + 2 * al((size_t)Bp * 8) + 2 * bK + 2 * bw + 4 * bcol + 4 * bz /*c,bl,bu,zout*/ + 2 * by /*lo,hi*/ + 2 * bpair + brho +
-                         binfo + 2 * al((size_t)Bp * 8) + bws;
+                         binfo + 2 * al((size_t)Bp * 8) + bws + bz /*z init*/ + 2 * by /*y init, y out*/;
     if (int rc = cx.dev.reserve(total)) return rc;
     char *d = (char *)cx.dev.ptr;
     auto take = [&](size_t b) { char *p = d; d += b; return p; };
@@ -165,6 +177,7 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
     double *drho = (double *)take(brho), *dinfo = (double *)take(binfo), *dupper = (double *)take(al((size_t)Bp * 8)),
            *dsw = (double *)take(al((size_t)Bp * 8));
     void *dws = take(bws);
+    double *dzi = (double *)take(bz), *dyi = (double *)take(by), *dyo = (double *)take(by);
 
     // ---- matrix: build, column norms, scale ----
     MBRF_CUDA(cudaMemcpyAsync(dw, w_row, (size_t)M * 8, cudaMemcpyHostToDevice, st));
@@ -285,11 +298,43 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
         dbk.norm_w = dlam;
     }
 
+    std::vector<double> om_in, om_out;
+    if (warm.z || warm.y || warm.omega || warm.omega_out) {
+        if (warm.z) {
+            h.assign(zn, 0.0);
+            for (int j = 0; j < N; ++j)
+                for (int b = 0; b < B; ++b) h[(size_t)j * Bp + b] = warm.z[(size_t)j * B + b] * cs[j];
+            MBRF_CUDA(cudaMemcpyAsync(dzi, h.data(), zn * 8, cudaMemcpyHostToDevice, st));
+            MBRF_CUDA(cudaStreamSynchronize(st));
+        }
+        if (warm.y) {
+            h.assign(yn, 0.0);
+            for (int i = 0; i < M; ++i)
+                for (int b = 0; b < B; ++b) h[(size_t)i * Bp + b] = warm.y[(size_t)i * B + b];
+            MBRF_CUDA(cudaMemcpyAsync(dyi, h.data(), yn * 8, cudaMemcpyHostToDevice, st));
+            MBRF_CUDA(cudaStreamSynchronize(st));
+        }
+        if (warm.omega) { om_in.assign((size_t)Bp, 1.0); for (int b = 0; b < B; ++b) om_in[b] = warm.omega[b]; }
+        if (warm.omega_out) om_out.assign((size_t)Bp, 1.0);
+        mbrf_pdhg_warm_start_device(warm.z ? dzi : nullptr, warm.y ? dyi : nullptr, warm.omega ? om_in.data() : nullptr,
+                                    warm.omega_out ? om_out.data() : nullptr);
+    }
+    const double t_setup = since();
     int rc = mbrf_pdhg_solve_device(dK, dKT, Mp, Np, ldk, dc, dlo, dhi, dbl, dbu, npairs ? dpi : nullptr,
                                     npairs ? dpj : nullptr, npairs, npairs ? drho : nullptr, Bp, B,
                                     obj_upper ? dupper : nullptr, &dbk, max_iter, check_every, eps_pr, eps_dr, eps_gap,
-                                    dz, nullptr, dinfo, dws, st);
+                                    dz, warm.y_out ? dyo : nullptr, dinfo, dws, st);
     if (rc) return rc;
+    const double t_solved = since();
+    if (warm.y_out) {
+        h.assign(yn, 0.0);
+        MBRF_CUDA(cudaMemcpyAsync(h.data(), dyo, yn * 8, cudaMemcpyDeviceToHost, st));
+        MBRF_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < M; ++i)
+            for (int b = 0; b < B; ++b) warm.y_out[(size_t)i * B + b] = h[(size_t)i * Bp + b];
+    }
+    if (warm.omega_out)
+        for (int b = 0; b < B; ++b) warm.omega_out[b] = om_out[b];
     h.assign(zn, 0.0);
     std::vector<double> info((size_t)Bp * 8);
     MBRF_CUDA(cudaMemcpyAsync(h.data(), dz, zn * 8, cudaMemcpyDeviceToHost, st));
@@ -298,6 +343,21 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
     for (int j = 0; j < N; ++j)
         for (int b = 0; b < B; ++b) z_out[(size_t)j * B + b] = h[(size_t)j * Bp + b] / cs[j];
     memcpy(info_out, info.data(), (size_t)B * 64);
+    if (timing)
+        fprintf(stderr, "fir_pdhg_solve M=%d N=%d B=%d: setup+upload %.3f s, solve %.3f s, download %.3f s\n", M, N, B, t_setup,
+                t_solved - t_setup, since() - t_solved);
+    return MBRF_OK;
+}
+
+/* Warm start of the next mbrf_fir_pdhg_solve / _solve2 call made by this host thread (consumed by that call).  Host pointers
+ * in the caller's units that must stay valid until that call returns; any may be NULL:
+ *   z_init [N x B], y_init [M x B]: starting iterate and multipliers;  omega_init [B]: primal weights (default 1);
+ *   y_out [M x B], omega_out [B]: receive the final multipliers / primal weights (to warm-start a neighbouring design). */
+extern "C" int mbrf_fir_pdhg_warm_start(const double *z_init, const double *y_init, const double *omega_init, double *y_out,
+                                        double *omega_out)
+{
+    t_warm_host.z = z_init; t_warm_host.y = y_init; t_warm_host.omega = omega_init;
+    t_warm_host.y_out = y_out; t_warm_host.omega_out = omega_out;
     return MBRF_OK;
 }
 

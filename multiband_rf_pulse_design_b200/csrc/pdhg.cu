@@ -1170,7 +1170,18 @@ static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st
 using namespace mbrf;
 using namespace mbrf::pdhg;
 
+// Warm start of this host thread's next mbrf_pdhg_solve_device call (consumed by it): device iterates [Np x Bp] / [Mp x Bp],
+// host primal weights [Bp] in, host primal weights [Bp] out.  Any pointer may be null.
+struct WarmHint { const double *z = nullptr, *y = nullptr, *omega = nullptr; double *omega_out = nullptr; };
+static thread_local WarmHint t_warm;
+
 extern "C" {
+
+int mbrf_pdhg_warm_start_device(const double *z_init, const double *y_init, const double *omega_init, double *omega_out)
+{
+    t_warm.z = z_init; t_warm.y = y_init; t_warm.omega = omega_init; t_warm.omega_out = omega_out;
+    return MBRF_OK;
+}
 
 // choose the product kernels of the iterations: 2 = tcgen05 int8 split-integer tiles (default), 1 = FP64 tensor path
 // (mma.sync m8n8k4), 0 = SIMT DFMA
@@ -1324,6 +1335,8 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
                            double eps_pr, double eps_dr, double eps_gap, double *z_out, double *y_out,
                            double *info_out, void *workspace, void *stream)
 {
+    const WarmHint warm = t_warm;
+    t_warm = WarmHint();
     if (int rc = require_device()) return rc;
     mbrf_pdhg_blocks bk;
     memset(&bk, 0, sizeof bk);
@@ -1467,9 +1480,19 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         for (int b = 0; b < Bp; ++b) {
             Ctl &c0 = hc[b];
             memset(&c0, 0, sizeof(Ctl));
-            c0.omega = 1.0; c0.tau = p.eta; c0.sigma = p.eta;
+            c0.omega = (warm.omega && b < B && warm.omega[b] > 0.0 && std::isfinite(warm.omega[b])) ? warm.omega[b] : 1.0;
+            c0.tau = p.eta / c0.omega; c0.sigma = p.eta * c0.omega;
             c0.last_err = DBL_MAX; c0.prev_err = DBL_MAX;
             c0.status = b < B ? 0.0 : 1.0;
+        }
+        if (warm.z) {      // iterate and restart anchor; zbar = z makes the first dual step an ordinary one
+            MBRF_CUDA(cudaMemcpyAsync(p.z, warm.z, zn * 8, cudaMemcpyDeviceToDevice, st));
+            MBRF_CUDA(cudaMemcpyAsync(p.z0, warm.z, zn * 8, cudaMemcpyDeviceToDevice, st));
+            MBRF_CUDA(cudaMemcpyAsync(p.zbar, warm.z, zn * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        if (warm.y) {
+            MBRF_CUDA(cudaMemcpyAsync(p.y, warm.y, yn * 8, cudaMemcpyDeviceToDevice, st));
+            MBRF_CUDA(cudaMemcpyAsync(p.y0, warm.y, yn * 8, cudaMemcpyDeviceToDevice, st));
         }
         MBRF_CUDA(cudaMemcpyAsync(p.ctl, hc.data(), (size_t)Bp * sizeof(Ctl), cudaMemcpyHostToDevice, st));
         MBRF_CUDA(cudaMemcpyAsync(p.active, &B, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1663,8 +1686,8 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         if (trace) {   // developer trace (MBRF_PDHG_TRACE=1): slot 0 after every check
             Ctl t0;
             if (cudaMemcpy(&t0, p.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost) == cudaSuccess)
-                fprintf(stderr, "pdhg it %6d st %.0f obj %.8f dual %.8f pr %.2e dr %.2e omega %.3e restart %.0f avg %.0f since %.0f lasterr %.2e\n",
-                        it, t0.status, t0.obj, t0.dual, t0.pr, t0.dr, t0.omega, t0.restart, t0.use_avg, t0.since, t0.last_err);
+                fprintf(stderr, "pdhg it %6d active %d width %d st %.0f obj %.8f dual %.8f pr %.2e dr %.2e omega %.3e restart %.0f avg %.0f since %.0f lasterr %.2e\n",
+                        it, active, p.Bp, t0.status, t0.obj, t0.dual, t0.pr, t0.dr, t0.omega, t0.restart, t0.use_avg, t0.since, t0.last_err);
         }
         // finished designs leave the batch once they would free at least one 64-design column block
         if (active > 0 && batch_width(active) < p.Bp && it < max_iter) rcode = compact();
@@ -1681,6 +1704,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             double *o = &info[(size_t)b * 8];
             o[0] = c0.status == 0.0 ? 3.0 : c0.status; o[1] = c0.iters; o[2] = c0.obj; o[3] = c0.dual;
             o[4] = c0.pr; o[5] = c0.dr; o[6] = c0.rigorous; o[7] = c0.tmax;
+            if (warm.omega_out) warm.omega_out[b] = c0.omega;
         }
         MBRF_CUDA(cudaMemcpyAsync(info_out, info.data(), info.size() * 8, cudaMemcpyHostToDevice, st));
         MBRF_CUDA(cudaStreamSynchronize(st));

@@ -76,3 +76,24 @@ def test_solver_same_answer_on_both_product_kernels(mbrf):
     rel = np.abs(out[1][ok, 2] - out[2][ok, 2]) / np.abs(out[1][ok, 2])
     assert rel.max() < 1e-6, rel.max()
     assert out[2][ok, 4].max() <= 1e-6
+
+
+def test_seeded_sweep_matches_cold_sweep(mbrf):
+    """fir_ap_cvx_sweep(seed_stride=...) (cold seeds + one warm-started hop, mbrf_fir_pdhg_warm_start) returns the same
+    optima as the cold sweep: both stop at a 5e-5 relative gap, so objectives agree within 1e-4, and every design that the
+    cold sweep solves is solved."""
+    from multiband_rf_pulse_design_b200 import fir
+    f = [-0.6, -0.35, -0.2, 0.18, 0.38, 0.6]
+    a = [0.866, 0.866, 0, 0, 0.707, 0.707]
+    d = [0.02, 0.03, 0.025]
+    objs = np.logspace(-1, 0, 96)              # 0.0105 decades apart -> "auto" picks stride 9
+    cold = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=96, max_iter=40000)
+    warm = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=96, max_iter=40000, seed_stride="auto")
+    ok = cold["info"][:, 0] == 1
+    assert ok.sum() >= 90
+    assert np.all(warm["info"][ok, 0] == 1)
+    rel = np.abs(warm["info"][ok, 2] - cold["info"][ok, 2]) / np.abs(cold["info"][ok, 2])
+    assert rel.max() < 1e-4, rel.max()
+    assert warm["info"][ok, 4].max() <= 1e-6
+    assert warm["info"][ok, 1].sum() < cold["info"][ok, 1].sum()      # fewer iterations in total
+    assert np.abs(warm["x"][ok] - cold["x"][ok]).max() < 5e-3         # same design, up to the tolerance of a first-order solve
