@@ -354,7 +354,8 @@ def run_ours(args):
 
     def step_device():
         # this rank's contiguous spin range, then the one collective of the path: the final gather (NCCL/NVLink)
-        return bloch_sharded(lib, dev_args, nf * npos, out, ws.data_ptr(), stream.cuda_stream, 0, m.GAMMA_C13)
+        # (pipelined in two pieces: the first piece's transfer hides behind the simulation of the second)
+        return bloch_sharded(lib, dev_args, nf * npos, out, ws.data_ptr(), stream, 0, m.GAMMA_C13, chunks=[0.85, 0.15])
 
     def barrier():
         if world > 1:
@@ -369,8 +370,24 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident leg ---------------------------------------------------------------
+    full = None
     for _ in range(args.warmup):
-        step_device()
+        full = step_device()
+    # the gathered planes against this rank simulating other ranks' ranges itself (first and last shard)
+    gather_check = None
+    if rank == 0 and full is not None:
+        torch.cuda.synchronize()
+        gather_check = 0.0
+        ref = torch.empty((3, nlocal), dtype=torch.float64, device=dev)
+        for r in sorted({0, world - 1}):
+            check(lib.mbrf_bloch_device(b1r.data_ptr(), b1i.data_ptr(), gx.data_ptr(), None, None, dts.data_ptr(), nt,
+                                        wl["t1"], wl["t2"], df.data_ptr(), nf, dx.data_ptr(), None, None, npos,
+                                        r * nlocal, nlocal, None, None, None, 1, ref[0].data_ptr(), ref[1].data_ptr(),
+                                        ref[2].data_ptr(), 0, m.GAMMA_C13, ws.data_ptr(), stream.cuda_stream))
+            torch.cuda.synchronize()
+            gather_check = max(gather_check, float((full[:, r * nlocal:(r + 1) * nlocal] - ref).abs().max()))
+        del ref
+    full = None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local)
@@ -528,7 +545,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "pulse": wl["src"], "spins_per_gpu": nlocal, "ntime": nt,
                    "sharding": f"contiguous spin ranges over {world} GPU(s), one NCCL gather to rank 0 per step"
-                   if world > 1 else "single GPU", "l2": "flushed between timed iterations (256 MiB memset)"},
+                   if world > 1 else "single GPU", "l2": "flushed between timed iterations (256 MiB memset)", "gather_check_max_abs": gather_check},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "call": "blochC(b1,gr,tp,t1,t2,df,dp,0) -> mbrf_bloch (C ABI), pinned host buffers",
                 "check_vs_device_leg": chk},

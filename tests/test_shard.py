@@ -51,6 +51,61 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
+def _worker_pieces(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multiband_rf_pulse_design_b200.shard import pipelined_gather, shard_bounds
+    bounds = shard_bounds(n, world)
+    s0, cnt = bounds[rank]
+    width = max(c for _, c in bounds)
+    ok = True
+    for chunks in (1, 3, [0.85, 0.15], [0.5, 0.3, 0.2]):
+        local = torch.full((3, width), float("nan"), dtype=torch.float64)
+
+        def fill(first, size, piece):       # stand-in for the kernel: a known function of the GLOBAL spin index
+            s = torch.arange(s0 + first, s0 + first + size, dtype=torch.float64)
+            piece[0, :size], piece[1, :size], piece[2, :size] = s, -2 * s, s * s
+        full = pipelined_gather(fill, local, bounds, chunks)
+        if rank == 0:
+            ref = torch.arange(n, dtype=torch.float64)
+            ok = ok and (full.shape == (3, n) and torch.equal(full[0], ref) and torch.equal(full[1], -2 * ref)
+                         and torch.equal(full[2], ref * ref))
+        else:
+            assert full is None
+    if rank == 0:
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_piece_widths():
+    from multiband_rf_pulse_design_b200.shard import piece_widths
+    for width in (1, 7, 1000, 10 ** 6):
+        for chunks in (1, 2, 4, [0.85, 0.15], [1, 1, 1]):
+            w = piece_widths(width, chunks)
+            assert sum(w) == width and all(v >= 0 for v in w)
+    with pytest.raises(ValueError):
+        piece_widths(10, [0.5, -0.1])
+
+
+@pytest.mark.parametrize("n", [1001, 4096])
+def test_pipelined_gather_world2_gloo(n):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker_pieces, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
+
+
 @pytest.mark.parametrize("n", [1001, 4096])
 def test_gather_world2_gloo(n):
     with socket.socket() as s:
