@@ -49,8 +49,10 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
 
     int srow0 = 0, srows = 0;
     const double *sw = NULL;
-    if (nrhs < 16 || nrhs > 17 || nlhs > 2)
-        mexErrMsgTxt("Usage: [z, info] = fir_pdhg_mex(w_row,tcoef,col_type,col_kappa,col_amp,tcol,pair_i,pair_j,c,lo,hi,bl,bu,rho,obj_upper,opts,simplex)");
+    double *zi = NULL, *yi = NULL, *yo = NULL, *oo = NULL;
+    const double *oi = NULL;
+    if (nrhs < 16 || nrhs > 20 || nlhs > 4)
+        mexErrMsgTxt("Usage: [z, info, y, omega] = fir_pdhg_mex(w_row,tcoef,col_type,col_kappa,col_amp,tcol,pair_i,pair_j,c,lo,hi,bl,bu,rho,obj_upper,opts,simplex,z_init,y_init,omega_init)");
     M = numel(prhs[0]);
     N = numel(prhs[2]);
     B = (int)mxGetN(prhs[8]);
@@ -73,6 +75,13 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     }
     z = (double *)malloc(sizeof(double) * (size_t)N * B);
     info = (double *)malloc(sizeof(double) * 8 * (size_t)B);
+    /* warm start from a neighbouring design (optional inputs 18-20) and multipliers / primal weights out (outputs 3-4) */
+    if (nrhs > 17 && (int)mxGetM(prhs[17]) == N && (int)mxGetN(prhs[17]) == B) zi = to_rows(prhs[17], N, B);
+    if (nrhs > 18 && (int)mxGetM(prhs[18]) == M && (int)mxGetN(prhs[18]) == B) yi = to_rows(prhs[18], M, B);
+    if (nrhs > 19 && numel(prhs[19]) == B) oi = mxGetPr(prhs[19]);
+    if (nlhs > 2) yo = (double *)malloc(sizeof(double) * (size_t)M * B);
+    if (nlhs > 3) oo = (double *)malloc(sizeof(double) * (size_t)B);
+    if (zi || yi || oi || yo || oo) mbrf_fir_pdhg_warm_start(zi, yi, oi, yo, oo);
 
     rc = mbrf_fir_pdhg_solve(mxGetPr(prhs[0]), numel(prhs[1]) == M ? mxGetPr(prhs[1]) : NULL, M, ctype,
                              mxGetPr(prhs[3]), mxGetPr(prhs[4]), N, tcol, npairs ? pi : NULL, npairs ? pj : NULL, npairs,
@@ -87,7 +96,17 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
             plhs[1] = mxCreateDoubleMatrix(8, (size_t)B, mxREAL);
             for (i = 0; i < 8 * B; i++) mxGetPr(plhs[1])[i] = info[i];
         }
+        if (nlhs > 2) {
+            plhs[2] = mxCreateDoubleMatrix((size_t)M, (size_t)B, mxREAL);
+            for (b = 0; b < B; b++)
+                for (i = 0; i < M; i++) mxGetPr(plhs[2])[(size_t)b * M + i] = yo[(size_t)i * B + b];
+        }
+        if (nlhs > 3) {
+            plhs[3] = mxCreateDoubleMatrix((size_t)B, 1, mxREAL);
+            for (b = 0; b < B; b++) mxGetPr(plhs[3])[b] = oo[b];
+        }
     }
+    free(zi); free(yi); free(yo); free(oo);
     free(ctype); free(pi); free(pj); free(c); free(lo); free(hi); free(bl); free(bu); free(rho); free(z); free(info);
     if (rc != MBRF_OK) mexErrMsgTxt(mbrf_last_error());
 }
