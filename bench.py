@@ -235,9 +235,19 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
         single = {"workload": "cfg3: fir_qp_cvx min-energy multiband FIR, N=256, dual-band H-1 spec, k=120, obj=1, single design",
                   "status": st3, "seconds": time.perf_counter() - t1, "iterations": float(ex3["info"][1]),
                   "objective": float(ex3["info"][2]), "max_violation": float(ex3["info"][4])}
-    roof = None
+    roof, fmp = None, None
     if rank == 0:
         roof = solver_roofline(lib, per_gpu)
+        # the step after the solve (fir_ap_cvx.m:185-202): x -> minimum-phase taps h = fmp2(r), batched on the GPU
+        ok = r["info"][:, 0] == 1
+        if ok.any():
+            R = np.stack([fir._x_to_r(x, n) for x in r["x"][ok]])
+            fir.fmp2_batch(R[:8])
+            t2 = time.perf_counter()
+            fir.fmp2_batch(R)
+            dt = time.perf_counter() - t2
+            fmp = {"call": "fmp2_batch -> mbrf_fmp2_batch (one CTA per design, four 4096-point fp64 FFTs in shared memory), host buffers",
+                   "designs": int(ok.sum()), "seconds": dt, "designs_per_s": float(ok.sum() / dt)}
     info = r["info"]
     solved = int((info[:, 0] == 1).sum())
     iters = float(info[:, 1].max()) if info.size else 0.0
@@ -251,7 +261,7 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
             "(4 and 8 GPUs) every ~0.1 decade is solved cold and the other designs start from the nearest seed; coarser grids run cold", "solved_on_rank0": solved, "local_designs_rank0": int(info.shape[0]),
             "seconds": sec, "iterations_max": iters, "gpu_launches": int(launches),
             "workload": "cfg4 slice: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, obj x Peak trade-off grid",
-            "single_design": single, "roofline": roof,
+            "single_design": single, "roofline": roof, "fmp2": fmp,
             "tolerances": {"eps_pr": fir.EPS_PR, "eps_gap_rel": fir.EPS_GAP, "eps_dr": fir.EPS_DR},
             "gemm_tflops_useful": flops / sec / 1e12, "iterations_mean": float(info[:, 1].mean()) if info.size else 0.0,
             "note": "fp64 restarted PDHG; the two products of every iteration run on tcgen05 int8 tiles (split-integer, 5 base-256 "

@@ -260,6 +260,18 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
                            double *z_out, double *y_out, double *info_out,
                            void *workspace, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched minimum-phase spectral factorisation: hmp = fmp2(h) of fir_ap_cvx.m:262-283 (with fftc :253-255 and
+ * mag2mp :292-303), the step after the solve in fir_ap_cvx.m:185-202.  B sequences of odd length 2n-1 in, the n taps of
+ * the minimum-phase factor out; complex data as split re / im planes like the MEX API (r_im NULL = real input);
+ * row-major [B x (2n-1)] and [B x n].  n <= mbrf_fmp2_max_taps() (512: the padded transform lives in shared memory).
+ * ------------------------------------------------------------------------------------------------ */
+int mbrf_fmp2_max_taps(void);
+int mbrf_fmp2_batch(const double *r_re, const double *r_im, int n, int B, double *h_re, double *h_im);   /* host pointers */
+unsigned long long mbrf_fmp2_workspace_bytes(int n);
+int mbrf_fmp2_batch_device(const double *r_re, const double *r_im, int n, int B, double *h_re, double *h_im,
+                           void *workspace, void *stream);                                                 /* device pointers */
+
 #ifdef __cplusplus
 }
 #endif

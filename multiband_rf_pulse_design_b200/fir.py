@@ -223,34 +223,35 @@ def _solve_batch_ap(n, designs, max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_
 
 
 # --------------------------------------------------------------------------------------------
-# spectral factorisation — fir_ap_cvx.m:185-202, 254-304 (host; SURVEY.md 8(f) "next #1")
+# spectral factorisation — fir_ap_cvx.m:185-202, 253-304, batched on the GPU (csrc/fmp.cu)
 # --------------------------------------------------------------------------------------------
-def _mag2mp(x):
-    nn = x.size                                                           # fir_ap_cvx.m:293-303
-    xlf = np.fft.fft(np.log(x))
-    xlfp = np.zeros(nn, complex)
-    xlfp[0] = xlf[0]
-    xlfp[1:nn // 2] = 2 * xlf[1:nn // 2]
-    xlfp[nn // 2] = xlf[nn // 2]
-    return np.exp(np.fft.ifft(xlfp))
+def fmp2_batch(r):
+    """Minimum-phase spectral factors of B autocorrelation sequences r [B, 2n-1] (complex or real) -> [B, n] complex:
+    fmp2 / mag2mp / fftc of fir_ap_cvx.m:253-304, one CTA per sequence (libmbrf `mbrf_fmp2_batch`)."""
+    r = np.atleast_2d(np.asarray(r))
+    B, ln = r.shape
+    if ln % 2 == 0:
+        raise ValueError("filter length must be odd")                     # :265-268
+    n = (ln + 1) // 2
+    rr = np.ascontiguousarray(r.real, dtype=np.float64)
+    ri = np.ascontiguousarray(r.imag, dtype=np.float64) if np.iscomplexobj(r) else None
+    hr = np.empty((B, n)); hi = np.empty((B, n))
+    check(lib().mbrf_fmp2_batch(_dp(rr), _dp(ri) if ri is not None else None, n, B, _dp(hr), _dp(hi)))
+    return hr + 1j * hi
 
 
 def fmp2(r):
     """Minimum-phase spectral factor of the autocorrelation r (length 2n-1) — fir_ap_cvx.m:262-283."""
-    h = np.asarray(r, complex).ravel()
-    ln = h.size
-    lp = int(round(8 * np.exp(np.ceil(np.log(ln) / np.log(2)) * np.log(2))))
-    hp = np.concatenate([np.zeros(int(np.ceil((lp - ln) / 2))), h, np.zeros(int(np.floor((lp - ln) / 2)))])
-    hpf = np.fft.fftshift(np.fft.fft(np.fft.fftshift(hp)))                # fftc, :253-255
-    hpfmp = _mag2mp(np.sqrt(np.abs(hpf)))
-    hpmp = np.fft.ifft(np.fft.fftshift(np.conj(hpfmp)))
-    return hpmp[:(ln + 1) // 2]
+    return fmp2_batch(np.asarray(r).ravel()[None, :])[0]
+
+
+def _x_to_r(x, n):
+    r = np.concatenate([[x[0]], x[1:n] + 1j * x[n:2 * n - 1]])            # :185
+    return np.concatenate([np.conj(r[:0:-1]), r])                         # :186
 
 
 def _x_to_h(x, n):
-    r = np.concatenate([[x[0]], x[1:n] + 1j * x[n:2 * n - 1]])            # :185
-    r = np.concatenate([np.conj(r[:0:-1]), r])                            # :186
-    return fmp2(r)
+    return fmp2(_x_to_r(x, n))
 
 
 def _solve_concurrently(jobs):
@@ -300,11 +301,13 @@ def fir_ap_cvx_batch(n, f_list, a, d, obj_list, peak_list, return_info=False, **
     d_list = d if isinstance(d, (list, tuple)) and np.ndim(d[0]) else [d] * B
     designs = [assemble_fir_ap(n, f_list[i], a_list[i], d_list[i], obj_list[i], peak_list[i]) for i in range(B)]
     x, t, info = _solve_batch_ap(n, designs, **solver_kw)
-    hs, status = [], []
-    for b in range(B):
-        ok = info[b, 0] == 1.0            # 1 solved; 2 infeasible certificate; 3 iteration limit -> 'Failed'
-        status.append("Solved" if ok else "Failed")   # fir_ap_cvx.m:176-182
-        hs.append(_x_to_h(x[b], n) if ok else None)
+    ok = info[:, 0] == 1.0                # 1 solved; 2 infeasible certificate; 3 iteration limit -> 'Failed'
+    status = ["Solved" if o else "Failed" for o in ok]   # fir_ap_cvx.m:176-182
+    hs = [None] * B
+    if ok.any():                          # h = fmp2(r) for all solved designs in one launch, :185-202
+        hmp = fmp2_batch(np.stack([_x_to_r(x[b], n) for b in np.nonzero(ok)[0]]))
+        for k, b in enumerate(np.nonzero(ok)[0]):
+            hs[b] = hmp[k]
     if return_info:
         return hs, status, dict(x=x, ripple_stop=t, info=info)
     return hs, status

@@ -246,3 +246,38 @@ def solve_fir_qp_reference(p, x0=None, maxiter=3000):
     res = minimize(fun, v0, jac=grad, method="trust-constr", constraints=[NonlinearConstraint(cons, 0, np.inf, jac=jac)],
                    options=dict(maxiter=maxiter, gtol=1e-10, xtol=1e-12, barrier_tol=1e-12, verbose=0))
     return res
+
+
+# --------------------------------------------------------------------------------------------
+# spectral factorisation -- fir_ap_cvx.m:253-304 (fftc, fmp2, mag2mp), numpy restatement line by line.
+# Test infrastructure: the product computes this on the GPU (csrc/fmp.cu).
+# --------------------------------------------------------------------------------------------
+def mag2mp_reference(x):
+    nn = x.size                                                           # fir_ap_cvx.m:292-303
+    xlf = np.fft.fft(np.log(x))                                           # :294-295
+    xlfp = np.zeros(nn, complex)
+    xlfp[0] = xlf[0]                                                      # :296
+    xlfp[1:nn // 2] = 2 * xlf[1:nn // 2]                                  # :297
+    xlfp[nn // 2] = xlf[nn // 2]                                          # :298
+    return np.exp(np.fft.ifft(xlfp))                                      # :300-301
+
+
+def fmp2_reference(r):
+    """hmp = fmp2(h), fir_ap_cvx.m:262-283."""
+    h = np.asarray(r, complex).ravel()
+    ln = h.size
+    if ln % 2 == 0:
+        raise ValueError("filter length must be odd")                     # :265-268
+    lp = int(round(8 * np.exp(np.ceil(np.log(ln) / np.log(2)) * np.log(2))))                            # :269
+    hp = np.concatenate([np.zeros(int(np.ceil((lp - ln) / 2))), h, np.zeros(int(np.floor((lp - ln) / 2)))])   # :270
+    hpf = np.fft.fftshift(np.fft.fft(np.fft.fftshift(hp)))                # fftc, :253-255, :271
+    hpfmp = mag2mp_reference(np.sqrt(np.abs(hpf)))                        # :278
+    hpmp = np.fft.ifft(np.fft.fftshift(np.conj(hpfmp)))                   # :279
+    return hpmp[:(ln + 1) // 2]                                           # :280
+
+
+def x_to_h_reference(x, n):
+    """fir_ap_cvx.m:185-202: autocorrelation coefficients -> two-sided sequence -> minimum-phase taps."""
+    r = np.concatenate([[x[0]], x[1:n] + 1j * x[n:2 * n - 1]])            # :185
+    r = np.concatenate([np.conj(r[:0:-1]), r])                            # :186
+    return fmp2_reference(r)
