@@ -272,6 +272,15 @@ unsigned long long mbrf_fmp2_workspace_bytes(int n);
 int mbrf_fmp2_batch_device(const double *r_re, const double *r_im, int n, int B, double *h_re, double *h_im,
                            void *workspace, void *stream);                                                 /* device pointers */
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched inverse SLR transform (the step after the FIR design, dzrf_mb.m:239-240): aca = b2a(bc) of rf_tools/b2a.m:13-28
+ * (n = 2^k <= 1024: the length-8n transform is radix-2) and rf = ab2rf(ac, bc) of rf_tools/ab2rf.m:12-26 (n <= 2048).
+ * Host pointers, complex data as split re / im planes (imaginary inputs may be NULL), row-major [B x n].
+ * ------------------------------------------------------------------------------------------------ */
+int mbrf_b2a_batch(const double *b_re, const double *b_im, int n, int B, double *a_re, double *a_im);
+int mbrf_ab2rf_batch(const double *a_re, const double *a_im, const double *b_re, const double *b_im, int n, int B,
+                     double *rf_re, double *rf_im);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,8 @@ behaviour) over the C ABI in ``include/mbrf.h`` / ``libmbrf.so``:
 
     blochC, blochH, bloch            <- bloch_simulation/blochC.c, blochH.c (mexFunction)
     abrx, abrm, abr                  <- rf_tools/mex5/abrx.c, rf_tools/abrm.m, rf_tools/abr.m
+    b2a, ab2rf, b2rf                 <- rf_tools/b2a.m, rf_tools/ab2rf.m (batched inverse SLR, dzrf_mb.m:239-240)
+    fmp2                             <- fir_ap_cvx.m:253-304 (batched spectral factorisation)
     fir_ap_cvx, fir_ap               <- fir_ap_cvx.m, fir_ap.m (solve = batched restarted PDHG on the GPU)
 
 There is no CPU fallback: importing works anywhere, computing needs the built library
@@ -13,10 +15,10 @@ and a CUDA device.
 """
 from ._lib import lib, MbrfError, library_path  # noqa: F401
 from .bloch import bloch, blochC, blochH, blochsimfz, GAMMA_C13, GAMMA_H1  # noqa: F401
-from .slr import abr, abrm, abrx  # noqa: F401
+from .slr import ab2rf, abr, abrm, abrx, b2a, b2rf  # noqa: F401
 from .fir import (fir_ap, fir_ap_cvx, fir_ap_cvx_batch, fir_linprog, fir_min_order,  # noqa: F401
                   fir_min_order_linprog, fir_qp_cvx, fmp2)
 
-__all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "fir_ap", "fir_ap_cvx",
+__all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "b2a", "ab2rf", "b2rf", "fir_ap", "fir_ap_cvx",
            "fir_ap_cvx_batch", "fir_linprog", "fir_min_order", "fir_min_order_linprog", "fir_qp_cvx", "fmp2", "lib", "MbrfError",
            "library_path", "GAMMA_C13", "GAMMA_H1"]

@@ -61,6 +61,8 @@ SIGNATURES = {
     "mbrf_pdhg_set_tc_digits": (_i, [_i]),
     "mbrf_tc_product_device": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mbrf_pdhg_set_option": (_i, [_i, _d]),
+    "mbrf_b2a_batch": (_i, [_dp, _dp, _i, _i, _dp, _dp]),
+    "mbrf_ab2rf_batch": (_i, [_dp, _dp, _dp, _dp, _i, _i, _dp, _dp]),
     "mbrf_fmp2_max_taps": (_i, []),
     "mbrf_fmp2_batch": (_i, [_dp, _dp, _i, _i, _dp, _dp]),
     "mbrf_fmp2_workspace_bytes": (C.c_ulonglong, [_i]),

@@ -13,6 +13,7 @@
 // sincospi (the table is 32 KB .. 64 KB and stays in L1/L2).  The fftshifts are index arithmetic folded into the stages
 // around them.  Designs are independent: the grid is the batch.
 #include "common.h"
+#include "fft_smem.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -21,42 +22,10 @@
 namespace mbrf {
 namespace fmp {
 
+using fftsm::fft_inplace;
+using fftsm::twiddle_kernel;
+
 constexpr int THREADS = 512;
-
-__global__ void twiddle_kernel(double2 *tw, int half)   // tw[k] = exp(-2 pi i k / (2 half)), k < half
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= half) return;
-    double s, c;
-    sincospi(-(double)k / (double)half, &s, &c);
-    tw[k] = make_double2(c, s);
-}
-
-// in-place FFT of s[0..N) (N = 2^lg), forward (inverse = false) or unnormalised inverse; all threads of the CTA
-__device__ void fft_inplace(double2 *s, int lg, const double2 *__restrict__ tw, bool inverse)
-{
-    const int N = 1 << lg;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {            // bit-reversal permutation
-        const int j = (int)(__brev((unsigned)i) >> (32 - lg));
-        if (i < j) { const double2 t = s[i]; s[i] = s[j]; s[j] = t; }
-    }
-    __syncthreads();
-    for (int st = 0; st < lg; ++st) {
-        const int half = 1 << st;                                  // butterflies of span `half`
-        const int tstep = (N >> 1) >> st;                          // twiddle index stride: w = exp(-+2 pi i j / (2 half))
-        for (int b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
-            const int j = b & (half - 1);
-            const int i0 = ((b >> st) << (st + 1)) + j, i1 = i0 + half;
-            double2 w = tw[j * tstep];
-            if (inverse) w.y = -w.y;
-            const double2 a = s[i0], c = s[i1];
-            const double tr = fma(c.x, w.x, -c.y * w.y), ti = fma(c.x, w.y, c.y * w.x);
-            s[i0] = make_double2(a.x + tr, a.y + ti);
-            s[i1] = make_double2(a.x - tr, a.y - ti);
-        }
-        __syncthreads();
-    }
-}
 
 // r: [B][l] complex (split planes), h: [B][n] complex (split planes); l = 2n-1, N = 8 * 2^ceil(log2 l) = 2^lg
 __global__ void __launch_bounds__(THREADS) fmp2_kernel(const double *__restrict__ r_re, const double *__restrict__ r_im, int n,

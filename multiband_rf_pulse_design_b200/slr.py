@@ -70,3 +70,43 @@ def abrm(rf, g, x=None, y=None):
     if y is None:
         y = np.zeros(1)                                    # abrm.m:30-32
     return _run(rf, g, x, y, ABRM, use_gy=True)
+
+
+# --------------------------------------------------------------------------------------------
+# inverse SLR (the step after the FIR design, dzrf_mb.m:239-240), batched on the GPU — csrc/islr.cu
+# --------------------------------------------------------------------------------------------
+def _planes(z):
+    z = np.atleast_2d(np.asarray(z))
+    re = np.ascontiguousarray(z.real, dtype=np.float64)
+    im = np.ascontiguousarray(z.imag, dtype=np.float64) if np.iscomplexobj(z) else None
+    return z.shape, re, im
+
+
+def b2a(bc):
+    """aca = b2a(bc) — rf_tools/b2a.m:13-28: minimum-phase, minimum-power alpha polynomial of a beta polynomial.
+    bc: [n] or a batch [B, n]; n must be a power of two <= 1024 (length-8n radix-2 transform in shared memory)."""
+    shape, br, bi = _planes(bc)
+    B, n = shape
+    ar = np.empty((B, n)); ai = np.empty((B, n))
+    check(lib().mbrf_b2a_batch(_p(br), _p(bi), n, B, _p(ar), _p(ai)))
+    out = ar + 1j * ai
+    return out[0] if np.ndim(bc) == 1 else out
+
+
+def ab2rf(ac, bc):
+    """rf = ab2rf(ac, bc) — rf_tools/ab2rf.m:12-26 (complex RF version): the hard-pulse RF that produces alpha, beta.
+    ac, bc: [n] or batches [B, n], n <= 2048."""
+    shape, ar, ai = _planes(ac)
+    shape_b, br, bi = _planes(bc)
+    if shape != shape_b:
+        raise ValueError("ac and bc must have the same shape")
+    B, n = shape
+    rr = np.empty((B, n)); ri = np.empty((B, n))
+    check(lib().mbrf_ab2rf_batch(_p(ar), _p(ai), _p(br), _p(bi), n, B, _p(rr), _p(ri)))
+    out = rr + 1j * ri
+    return out[0] if np.ndim(ac) == 1 else out
+
+
+def b2rf(bc):
+    """rf = ab2rf(b2a(bc), bc) — dzrf_mb.m:239-240, for one beta polynomial or a batch."""
+    return ab2rf(b2a(bc), bc)
