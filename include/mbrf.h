@@ -215,6 +215,8 @@ typedef struct mbrf_pdhg_blocks {
     double *group_w;                  /*   (obj*Peak with norm(F_i*x) <= Peak, fir_qp_cvx.m:147,158-160)        */
     int norm_coords;                  /* adds  norm_w[b] * ||z[0 .. norm_coords)||_2                            */
     double *norm_w;                   /*   (E_total with norm(x,2) <= E_total, fir_qp_cvx.m:147,161)            */
+    int group2_row0, group2_pairs;    /* row pairs adding  group2_w[b] * max_i ||(K z)_pair_i - (lo[r], lo[r+1])||  */
+    double *group2_w;                 /*   (delta of the minimax form, fir_qp_cvx.m:170-177, rows pre-scaled 1/D_i) */
 } mbrf_pdhg_blocks;
 
 /* Matrix description with the extras fir_qp_cvx needs: K[i][j] = row_scale[i] * col_amp[j] *

@@ -86,7 +86,8 @@ class PdhgBlocks(C.Structure):
     _fields_ = [("simplex_row0", C.c_int), ("simplex_rows", C.c_int), ("simplex_w", c_double_p),
                 ("disk_row0", C.c_int), ("disk_pairs", C.c_int),
                 ("group_row0", C.c_int), ("group_pairs", C.c_int), ("group_w", c_double_p),
-                ("norm_coords", C.c_int), ("norm_w", c_double_p)]
+                ("norm_coords", C.c_int), ("norm_w", c_double_p),
+                ("group2_row0", C.c_int), ("group2_pairs", C.c_int), ("group2_w", c_double_p)]
 
 
 def declared_symbols() -> list[str]:

@@ -161,7 +161,7 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
                  bws = al(mbrf_pdhg_workspace_bytes(Mp, Np, Bp));
     const size_t bnz = al((size_t)(nnz > 0 ? nnz : 1) * 8);
     const size_t total = 3 * bnz + 2 * bw + 2 * al((size_t)Bp * 8) + 2 * bK + 2 * bw + 4 * bcol + 4 * bz /*c,bl,bu,zout*/ + 2 * by /*lo,hi*/ + 2 * bpair + brho +
-                         binfo + 2 * al((size_t)Bp * 8) + bws + bz /*z init*/ + 2 * by /*y init, y out*/;
+                         binfo + 2 * al((size_t)Bp * 8) + bws + bz /*z init*/ + 2 * by /*y init, y out*/ + al((size_t)Bp * 8) /*group2 w*/;
     if (int rc = cx.dev.reserve(total)) return rc;
     char *d = (char *)cx.dev.ptr;
     auto take = [&](size_t b) { char *p = d; d += b; return p; };
@@ -178,6 +178,7 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
            *dsw = (double *)take(al((size_t)Bp * 8));
     void *dws = take(bws);
     double *dzi = (double *)take(bz), *dyi = (double *)take(by), *dyo = (double *)take(by);
+    double *dgw2 = (double *)take(al((size_t)Bp * 8));
 
     // ---- matrix: build, column norms, scale ----
     MBRF_CUDA(cudaMemcpyAsync(dw, w_row, (size_t)M * 8, cudaMemcpyHostToDevice, st));
@@ -290,6 +291,11 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
         if (!bk.group_w || bk.group_row0 < 0 || bk.group_row0 + 2 * bk.group_pairs > M) { set_error("fir_pdhg_solve: bad group block"); return MBRF_EINVAL; }
         if (int rc = upload_w(bk.group_w, dgw, 1.0)) return rc;
         dbk.group_w = dgw;
+    }
+    if (bk.group2_pairs > 0) {
+        if (!bk.group2_w || bk.group2_row0 < 0 || bk.group2_row0 + 2 * bk.group2_pairs > M) { set_error("fir_pdhg_solve: bad centred group block"); return MBRF_EINVAL; }
+        if (int rc = upload_w(bk.group2_w, dgw2, 1.0)) return rc;
+        dbk.group2_w = dgw2;
     }
     if (bk.disk_pairs > 0 && (bk.disk_row0 < 0 || bk.disk_row0 + 2 * bk.disk_pairs > M)) { set_error("fir_pdhg_solve: bad disk block"); return MBRF_EINVAL; }
     if (bk.norm_coords > 0) {

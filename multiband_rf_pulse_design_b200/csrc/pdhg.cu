@@ -303,6 +303,8 @@ struct Problem {
                                                 //   centre in lo[pair], R in hi[first row]          (fir_qp_cvx.m:148-157)
     int grow0, ng;                              // group block: row pairs carry  gw_b * max_i ||(K z)_pair_i||  (obj*Peak,
     double *gw;                                 //   fir_qp_cvx.m:147,158-160); multipliers live in the l1,2 ball of radius gw_b
+    int grow2, ng2;                             // centred group block: row pairs carry  gw2_b * max_i ||(K z)_pair_i - (lo_r, lo_r+1)||
+    double *gw2;                                //   (delta of the minimax form, fir_qp_cvx.m:170-177, rows pre-scaled by 1/D_i)
     int nn;                                     // norm term: lam_b * ||z[0..nn)||_2 in the objective (E_total, :147,161)
     double *lam;                                // [Bp]
     double *nrm;                                // [4 x Bp] scratch: ||zhat||^2 per design (z-update), metrics sums
@@ -320,7 +322,7 @@ struct Problem {
     double beta_suff, beta_nec, beta_art, omega_theta;   // restart rule constants (PDLP defaults 0.2, 0.8, 0.36, 0.5)
 };
 
-enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, A_GMAX, A_ZZ, A_ZV, A_VV, NACC };
+enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, A_GMAX, A_ZZ, A_ZV, A_VV, A_GMAX2, NACC };
 
 __device__ __forceinline__ void atomic_max_pos(double *addr, double v)
 {
@@ -453,6 +455,7 @@ __device__ __forceinline__ double y_update_elem(const Problem &p, int row, int b
 {
     if (row >= p.srow0 && row < p.srow0 + p.ns) return 0.0;   // simplex block: simplex_update_kernel
     if (row >= p.grow0 && row < p.grow0 + 2 * p.ng) return 0.0;   // group block: group_update_kernel
+    if (row >= p.grow2 && row < p.grow2 + 2 * p.ng2) return 0.0;  // centred group block: group_update_kernel
     const double sig = p.ctl[b].sigma;
     if (row >= p.drow0 && row < p.drow0 + 2 * p.nd) {     // disk pair: y+ = v - sigma * P_disk(v / sigma)
         if ((row - p.drow0) & 1) return 0.0;              // the first row of the pair does both
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(256) y_update_wide_kernel(Problem p)
         for (int u = 0; u < 4; ++u) {
             const int r = row + u * step;
             plain[u] = r < p.Mp && !(r >= p.srow0 && r < p.srow0 + p.ns) && !(r >= p.grow0 && r < p.grow0 + 2 * p.ng) &&
-                       !(r >= p.drow0 && r < p.drow0 + 2 * p.nd);
+                       !(r >= p.drow0 && r < p.drow0 + 2 * p.nd) && !(r >= p.grow2 && r < p.grow2 + 2 * p.ng2);
             if (plain[u]) {
                 const size_t o = (size_t)r * p.Bp + b;
                 y[u] = p.y[o]; S[u] = p.S[o]; lo[u] = p.lo[o]; hi[u] = p.hi[o]; ys[u] = p.ys[o];
@@ -658,8 +661,19 @@ __global__ void simplex_update_kernel(Problem p)
 // Group block: the objective term  gw * max_i ||(K z)_pair_i||  (obj*Peak with ||(x_i, x_{n+i})|| <= Peak,
 // fir_qp_cvx.m:147,158-160) has as conjugate the indicator of the l1,2 ball {sum_i ||u_i|| <= gw}: the dual step
 // is the projection of v = y + sigma K zbar onto that ball (Michelot on the pair norms).  One warp per design.
-__global__ void group_update_kernel(Problem p)
+// GroupSel picks the block: plain (obj*Peak: centres 0) or centred (delta: f(u) = max_i ||u_i - c_i|| has the conjugate
+// <c, y> + indicator of the same ball, so the dual step projects  y + sigma (K zbar - c)  instead).
+struct GroupSel { int row0, n, centred; const double *w; };
+__device__ __forceinline__ GroupSel group_sel(const Problem &p, int which)
 {
+    return which == 0 ? GroupSel{p.grow0, p.ng, 0, p.gw} : GroupSel{p.grow2, p.ng2, 1, p.gw2};
+}
+__global__ void group_update_kernel(Problem pp, int which)
+{
+    const Problem &p0 = pp;
+    const GroupSel g = group_sel(p0, which);
+    struct { int grow0, ng, Bp; const double *gw; double *y, *S, *ys, *mxy; const Ctl *ctl; const double *lo; } p =
+        {g.row0, g.n, p0.Bp, g.w, p0.y, p0.S, p0.ys, p0.mxy, p0.ctl, p0.lo};
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= p.Bp) return;
@@ -667,7 +681,8 @@ __global__ void group_update_kernel(Problem p)
     double sum = 0.0;
     for (int i = lane; i < p.ng; i += 32) {
         const size_t o = (size_t)(p.grow0 + 2 * i) * p.Bp + b;
-        const double v1 = p.y[o] + sig * p.S[o], v2 = p.y[o + p.Bp] + sig * p.S[o + p.Bp];
+        const double c1 = g.centred ? p.lo[o] : 0.0, c2 = g.centred ? p.lo[o + p.Bp] : 0.0;
+        const double v1 = p.y[o] + sig * (p.S[o] - c1), v2 = p.y[o + p.Bp] + sig * (p.S[o + p.Bp] - c2);
         p.y[o] = v1; p.y[o + p.Bp] = v2;      // stage v in place
         sum += hypot(v1, v2);
     }
@@ -716,8 +731,12 @@ __global__ void group_update_kernel(Problem p)
 
 // Group blocks of up to 32*R pairs: the pairs of a design stay in its warp's registers across the Michelot passes
 template <int R>
-__global__ void __launch_bounds__(256) group_update_reg_kernel(Problem p)
+__global__ void __launch_bounds__(256) group_update_reg_kernel(Problem pp, int which)
 {
+    const Problem &p0 = pp;
+    const GroupSel g = group_sel(p0, which);
+    struct { int grow0, ng, Bp; const double *gw; double *y, *S, *ys, *mxy; const Ctl *ctl; const double *lo; } p =
+        {g.row0, g.n, p0.Bp, g.w, p0.y, p0.S, p0.ys, p0.mxy, p0.ctl, p0.lo};
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= p.Bp) return;
@@ -730,8 +749,9 @@ __global__ void __launch_bounds__(256) group_update_reg_kernel(Problem p)
         v1[u] = v2[u] = nr[u] = 0.0;
         if (i < p.ng) {
             const size_t o = (size_t)(p.grow0 + 2 * i) * p.Bp + b;
-            v1[u] = p.y[o] + sig * p.S[o];
-            v2[u] = p.y[o + p.Bp] + sig * p.S[o + p.Bp];
+            const double c1 = g.centred ? p.lo[o] : 0.0, c2 = g.centred ? p.lo[o + p.Bp] : 0.0;
+            v1[u] = p.y[o] + sig * (p.S[o] - c1);
+            v2[u] = p.y[o + p.Bp] + sig * (p.S[o + p.Bp] - c2);
             nr[u] = hypot(v1[u], v2[u]);
         }
     }
@@ -800,10 +820,21 @@ __global__ void row_metrics_kernel(Problem p, int cand)
     if (b >= p.Bp) return;
     const double inv = cand == 0 ? 1.0 / fmax(p.ctl[b].cnt, 1.0) : 1.0;
     const double *yv = cand == 0 ? p.ys : p.y;
-    double pr = 0.0, hs = 0.0, dy2 = 0.0, tmax = 0.0, gmax = 0.0;
+    double pr = 0.0, hs = 0.0, dy2 = 0.0, tmax = 0.0, gmax = 0.0, gmax2 = 0.0;
     for (int i = blockIdx.y; i < p.Mp; i += gridDim.y) {
         const size_t o = (size_t)i * p.Bp + b;
         const double kz = p.S[o] * inv, y = yv[o] * inv, lo = p.lo[o], hi = p.hi[o];
+        if (i >= p.grow2 && i < p.grow2 + 2 * p.ng2) {   // centred group block: h* = <centre, y>, track max ||K z - centre||
+            const double d = y - p.y0[o];
+            dy2 = fma(d, d, dy2);
+            if (((i - p.grow2) & 1) == 0) {
+                const size_t o2 = o + p.Bp;
+                const double kz2 = p.S[o2] * inv, y2 = yv[o2] * inv, c1 = lo, c2 = p.lo[o2];
+                gmax2 = fmax(gmax2, hypot(kz - c1, kz2 - c2));
+                hs += c1 * y + c2 * y2;
+            }
+            continue;
+        }
         if (i >= p.drow0 && i < p.drow0 + 2 * p.nd) {  // disk pair (first row does both): violation, support function
             const double d = y - p.y0[o];
             dy2 = fma(d, d, dy2);
@@ -837,6 +868,7 @@ __global__ void row_metrics_kernel(Problem p, int cand)
     atomic_max_pos(acc + A_PR * p.Bp + b, pr);
     atomic_max_pos(acc + A_TMAX * p.Bp + b, tmax);
     atomic_max_pos(acc + A_GMAX * p.Bp + b, gmax);
+    atomic_max_pos(acc + A_GMAX2 * p.Bp + b, gmax2);
     atomicAdd(acc + A_HS * p.Bp + b, hs);
     atomicAdd(acc + A_DY2 * p.Bp + b, dy2);
 }
@@ -921,7 +953,8 @@ __global__ void control_kernel(Problem p, int iter_now, int max_iter)
         pr[k] = a[A_PR * p.Bp + b];
         dr[k] = a[A_DR * p.Bp + b];
         tm[k] = a[A_TMAX * p.Bp + b];
-        po[k] = a[A_POBJ * p.Bp + b] + (p.ns > 0 ? p.sw[b] * tm[k] : 0.0) + (p.ng > 0 ? p.gw[b] * a[A_GMAX * p.Bp + b] : 0.0);
+        po[k] = a[A_POBJ * p.Bp + b] + (p.ns > 0 ? p.sw[b] * tm[k] : 0.0) + (p.ng > 0 ? p.gw[b] * a[A_GMAX * p.Bp + b] : 0.0) +
+                (p.ng2 > 0 ? p.gw2[b] * a[A_GMAX2 * p.Bp + b] : 0.0);
         du[k] = -a[A_HS * p.Bp + b] + a[A_GZ * p.Bp + b];
         if (p.nn > 0) {            // norm term: lam*||z|| in both, residual ||z - shrink(z - g)||_2 from the inner products
             const double zz = a[A_ZZ * p.Bp + b], zv = a[A_ZV * p.Bp + b], vv = a[A_VV * p.Bp + b], lam = p.lam[b];
@@ -1346,6 +1379,8 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     if (ns < 0 || (ns > 0 && (!simplex_w || srow0 < 0 || srow0 + ns > Mp)) || bk.disk_pairs < 0 ||
         (bk.disk_pairs > 0 && (bk.disk_row0 < 0 || bk.disk_row0 + 2 * bk.disk_pairs > Mp)) || bk.group_pairs < 0 ||
         (bk.group_pairs > 0 && (!bk.group_w || bk.group_row0 < 0 || bk.group_row0 + 2 * bk.group_pairs > Mp)) ||
+        bk.group2_pairs < 0 ||
+        (bk.group2_pairs > 0 && (!bk.group2_w || bk.group2_row0 < 0 || bk.group2_row0 + 2 * bk.group2_pairs > Mp)) ||
         bk.norm_coords < 0 || bk.norm_coords > Np || (bk.norm_coords > 0 && (!bk.norm_w || npairs > 0))) {
         set_error("pdhg: bad row/column blocks (simplex %d+%d, disks %d+2*%d, groups %d+2*%d, norm %d)", srow0, ns,
                   bk.disk_row0, bk.disk_pairs, bk.group_row0, bk.group_pairs, bk.norm_coords);
@@ -1368,6 +1403,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     p.srow0 = ns > 0 ? srow0 : 0; p.ns = ns; p.sw = ns > 0 ? simplex_w : nullptr;
     p.drow0 = bk.disk_pairs > 0 ? bk.disk_row0 : 0; p.nd = bk.disk_pairs;
     p.grow0 = bk.group_pairs > 0 ? bk.group_row0 : 0; p.ng = bk.group_pairs; p.gw = bk.group_pairs > 0 ? bk.group_w : nullptr;
+    p.grow2 = bk.group2_pairs > 0 ? bk.group2_row0 : 0; p.ng2 = bk.group2_pairs; p.gw2 = bk.group2_pairs > 0 ? bk.group2_w : nullptr;
     p.nn = bk.norm_coords; p.lam = bk.norm_coords > 0 ? bk.norm_w : nullptr;
     p.eps_pr = eps_pr; p.eps_dr = eps_dr; p.eps_gap = eps_gap; p.check_every = check_every;
     const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
@@ -1539,8 +1575,13 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             MBRF_LAUNCH_CHECK();
         }
         if (p.ng > 0) {
-            if (p.ng <= 256) group_update_reg_kernel<8><<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
-            else group_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
+            if (p.ng <= 256) group_update_reg_kernel<8><<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p, 0);
+            else group_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p, 0);
+            MBRF_LAUNCH_CHECK();
+        }
+        if (p.ng2 > 0) {
+            if (p.ng2 <= 256) group_update_reg_kernel<8><<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p, 1);
+            else group_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p, 1);
             MBRF_LAUNCH_CHECK();
         }
         return MBRF_OK;
@@ -1642,6 +1683,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         if (int rc = regather(p.obj_upper, 1, p.G2, INFINITY)) return rc;
         if (int rc = regather(p.sw, 1, p.G2, 0.0)) return rc;
         if (int rc = regather(p.gw, 1, p.G2, 0.0)) return rc;
+        if (int rc = regather(p.gw2, 1, p.G2, 0.0)) return rc;
         if (int rc = regather(p.lam, 1, p.G2, 0.0)) return rc;
         double *mside[] = {p.y, p.ys, p.y0, p.ybest};
         for (double *a : mside)
@@ -1674,7 +1716,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     for (int it = 0; it < max_iter && active > 0 && rcode == MBRF_OK;) {
         if (use_graph) {
             if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("pdhg: graph launch failed"); rcode = MBRF_ECUDA; break; }
-            g_launches.fetch_add((4ull + (tcs.on ? 2 : 0) + (p.ns > 0) + (p.ng > 0) + (p.nn > 0)) * check_every, std::memory_order_relaxed);
+            g_launches.fetch_add((4ull + (tcs.on ? 2 : 0) + (p.ns > 0) + (p.ng > 0) + (p.ng2 > 0) + (p.nn > 0)) * check_every, std::memory_order_relaxed);
         } else {
             for (int i = 0; i < check_every && rcode == MBRF_OK; ++i) rcode = iteration(i == 0);
         }

@@ -724,20 +724,26 @@ def assemble_fir_qp(n, f, a, d, k=100.0, oversamp=10):
 
 
 def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, **solver_kw):
-    """[h, status] = fir_qp_cvx(n, f, a, d, k, obj, dbg) — fir_qp_cvx.m:1-243, scalar `obj` form (:145-166):
+    """[h, status] = fir_qp_cvx(n, f, a, d, k, obj, dbg) — fir_qp_cvx.m:1-243.
 
+    Scalar `obj` (:145-166):
         minimise E_total + obj*Peak   s.t.  ||A_i x - Hd_i|| <= D_i  (bands),  ||A_i x|| <= 1+5 max(d)  (transitions),
                                             ||(x_i, x_{n+i})|| <= Peak,  ||x|| <= E_total.
+    Two-element `obj` (:170-191, minimax on the frequency response):
+        minimise delta + obj(1)*E_total + obj(2)*Peak   s.t.  ||A_i x - Hd_i|| <= D_i*delta  (bands),
+                                            ||A_i x|| <= 1.1  (transitions), Peak and E_total as above.
 
-    E_total and Peak are eliminated (E_total = ||x||, Peak = max_i ||(x_i, x_{n+i})|| at the optimum): the solver sees
-    the norm term, a group block over identity rows, and one disk per grid point — no epigraph variables.
-    The two-element `obj` form (:170-191, minimax with delta) is not implemented."""
-    if np.ndim(obj) != 0 and np.size(obj) != 1:
-        raise NotImplementedError("fir_qp_cvx with length(obj) == 2 (minimax form, fir_qp_cvx.m:170-191)")
+    E_total, Peak and delta are eliminated (E_total = ||x||, Peak = max_i ||(x_i, x_{n+i})||,
+    delta = max_i ||A_i x - Hd_i|| / D_i at the optimum): the solver sees the norm term, a group block over identity
+    rows, one disk per constrained grid point and — for the minimax form — a centred group block over the band rows
+    scaled by 1/D_i.  No epigraph variables."""
+    minimax = np.size(obj) == 2
+    if np.size(obj) not in (1, 2):
+        raise ValueError("invalid input of obj")                          # :193-195
     n = int(n)
-    obj = float(np.ravel(obj)[0])
+    ob = [float(v) for v in np.ravel(obj)]
     p = assemble_fir_qp(n, f, a, d, float(k))
-    m = p["w"].size
+    m, nb = p["w"].size, p["nband"]
     N, M = 2 * n, 2 * m + 2 * n
     w_row = np.concatenate([np.repeat(p["w"], 2), np.zeros(2 * n)])
     row_phase = np.concatenate([np.tile([0.0, np.pi / 2], m), np.zeros(2 * n)])   # [cos sin; -sin cos], :96-109
@@ -753,15 +759,30 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, **solver_kw):
     tv = np.ones(2 * n)
     lo = np.full((M, 1), -np.inf)
     hi = np.full((M, 1), np.inf)
-    lo[0:2 * m:2, 0] = p["center"].real
-    lo[1:2 * m:2, 0] = p["center"].imag
-    hi[0:2 * m:2, 0] = p["radius"]
-    big = 2.0 * p["radius"].max() + 2.0 * np.abs(p["center"]).max()
+    radius = p["radius"].copy()
+    blocks = PdhgBlocks()
+    one = np.array([1.0])
+    if minimax:
+        inv_d = 1.0 / p["radius"][:nb]                                    # band rows / D_i: ||.|| <= delta, :176
+        row_scale[0:2 * nb:2] = inv_d
+        row_scale[1:2 * nb:2] = inv_d
+        lo[0:2 * nb:2, 0] = p["center"][:nb].real * inv_d
+        lo[1:2 * nb:2, 0] = p["center"][:nb].imag * inv_d
+        lo[2 * nb:2 * m, 0] = 0.0                                         # transition disks: centre 0, radius 1 + 0.1, :180
+        hi[2 * nb:2 * m:2, 0] = 1.0 + 0.1
+        radius[nb:] = 1.0 + 0.1
+        blocks.group2_row0, blocks.group2_pairs, blocks.group2_w = 0, nb, _dp(one)
+        blocks.disk_row0, blocks.disk_pairs = 2 * nb, m - nb
+        gw, lam = np.array([ob[1]]), np.array([ob[0]])
+    else:
+        lo[0:2 * m:2, 0] = p["center"].real
+        lo[1:2 * m:2, 0] = p["center"].imag
+        hi[0:2 * m:2, 0] = p["radius"]
+        blocks.disk_row0, blocks.disk_pairs = 0, m
+        gw, lam = np.array([ob[0]]), np.array([1.0])
+    big = 2.0 * p["radius"].max() + 2.0 * np.abs(p["center"]).max() + (2.0 if minimax else 0.0)
     c = np.zeros((N, 1))
     bl, bu = np.full((N, 1), -big), np.full((N, 1), big)
-    gw, lam = np.array([obj]), np.array([1.0])
-    blocks = PdhgBlocks()
-    blocks.disk_row0, blocks.disk_pairs = 0, m
     blocks.group_row0, blocks.group_pairs, blocks.group_w = 2 * m, n, _dp(gw)
     blocks.norm_coords, blocks.norm_w = N, _dp(lam)
     kw = dict(max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR, eps_gap=EPS_GAP)
@@ -780,5 +801,6 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, **solver_kw):
     h = x[:n] + 1j * x[n:] if ok else np.zeros(0)                         # :209
     st = "Solved" if ok else "Failed"                                     # :200-206
     if return_info:
+        p = dict(p, radius=radius)
         return h, st, dict(x=x.copy(), info=info[0].copy(), problem=p)
     return h, st

@@ -209,6 +209,68 @@ def violation_fir_qp(p, x):
     return max(0.0, (np.abs(H - p["center"]) - p["radius"]).max())
 
 
+def objective_fir_qp_minimax(p, x, obj2):
+    """fir_qp_cvx.m:170-191 with the epigraph variables at their optimal values:
+    delta = max_i |H(w_i) - Hd_i| / D_i over the band rows, E_total = ||x||, Peak = max_i |h_i|."""
+    n, nb = p["n"], p["nband"]
+    H = response_fir_qp(p["w"][:nb], n, x)
+    delta = (np.abs(H - p["center"][:nb]) / p["radius"][:nb]).max()
+    return delta + obj2[0] * np.linalg.norm(x) + obj2[1] * np.hypot(x[:n], x[n:]).max()
+
+
+def violation_fir_qp_minimax(p, x):
+    """Only the transition rows are constraints in the minimax form: |H(w_i)| <= 1 + 0.1 (:180)."""
+    nb = p["nband"]
+    if p["w"].size == nb:
+        return 0.0
+    H = response_fir_qp(p["w"][nb:], p["n"], x)
+    return max(0.0, (np.abs(H) - 1.1).max())
+
+
+def solve_fir_qp_minimax_reference(p, obj2, maxiter=30000):
+    """Independent CPU solve of the minimax form (SciPy trust-constr, smooth squared-norm constraints, epigraph variables
+    delta, E_total, Peak).  v = [x (2n), delta, E, P]."""
+    from scipy.optimize import NonlinearConstraint, minimize
+    n, nb = p["n"], p["nband"]
+    kk = np.arange(n)
+    Ew = np.exp(-1j * np.outer(p["w"], kk))
+    Ar = np.hstack([Ew.real, -Ew.imag])
+    Ai = np.hstack([Ew.imag, Ew.real])
+    cr, ci, D = p["center"].real[:nb], p["center"].imag[:nb], p["radius"][:nb]
+    nt = p["w"].size - nb
+
+    def fun(v):
+        return v[2 * n] + obj2[0] * v[2 * n + 1] + obj2[1] * v[2 * n + 2]
+
+    def grad(v):
+        g = np.zeros_like(v); g[2 * n] = 1; g[2 * n + 1] = obj2[0]; g[2 * n + 2] = obj2[1]; return g
+
+    def cons(v):
+        x, dl, E, P = v[:2 * n], v[2 * n], v[2 * n + 1], v[2 * n + 2]
+        hr, hi = Ar @ x, Ai @ x
+        band = (D * dl) ** 2 - (hr[:nb] - cr) ** 2 - (hi[:nb] - ci) ** 2
+        tran = 1.1 ** 2 - hr[nb:] ** 2 - hi[nb:] ** 2
+        return np.concatenate([band, tran, P ** 2 - x[:n] ** 2 - x[n:] ** 2, [E ** 2 - x @ x], [dl, E, P]])
+
+    def jac(v):
+        x, dl, E, P = v[:2 * n], v[2 * n], v[2 * n + 1], v[2 * n + 2]
+        hr, hi = Ar @ x, Ai @ x
+        Jb = np.hstack([-2 * ((hr[:nb] - cr)[:, None] * Ar[:nb] + (hi[:nb] - ci)[:, None] * Ai[:nb]),
+                        (2 * D ** 2 * dl)[:, None], np.zeros((nb, 2))])
+        Jt = np.hstack([-2 * (hr[nb:, None] * Ar[nb:] + hi[nb:, None] * Ai[nb:]), np.zeros((nt, 3))])
+        J2 = np.zeros((n, 2 * n + 3))
+        J2[np.arange(n), np.arange(n)] = -2 * x[:n]; J2[np.arange(n), n + np.arange(n)] = -2 * x[n:]; J2[:, 2 * n + 2] = 2 * P
+        J3 = np.concatenate([-2 * x, [0, 2 * E, 0]])[None, :]
+        J4 = np.zeros((3, 2 * n + 3)); J4[0, 2 * n] = 1; J4[1, 2 * n + 1] = 1; J4[2, 2 * n + 2] = 1
+        return np.vstack([Jb, Jt, J2, J3, J4])
+    x0 = np.linalg.lstsq(np.vstack([Ar[:nb], Ai[:nb]]), np.concatenate([cr, ci]), rcond=None)[0]
+    H0 = response_fir_qp(p["w"][:nb], n, x0)
+    v0 = np.concatenate([x0, [(np.abs(H0 - p["center"][:nb]) / D).max() * 1.01 + 1e-3, np.linalg.norm(x0) * 1.01 + 1e-3,
+                              np.hypot(x0[:n], x0[n:]).max() * 1.01 + 1e-3]])
+    return minimize(fun, v0, jac=grad, method="trust-constr", constraints=[NonlinearConstraint(cons, 0, np.inf, jac=jac)],
+                    options=dict(maxiter=maxiter, gtol=1e-10, xtol=1e-12, barrier_tol=1e-12, verbose=0))
+
+
 def solve_fir_qp_reference(p, x0=None, maxiter=3000):
     """Independent CPU solve (SciPy trust-constr on the smooth squared-norm form with epigraph variables)."""
     from scipy.optimize import NonlinearConstraint, minimize

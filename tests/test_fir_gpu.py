@@ -171,8 +171,23 @@ def test_fir_qp_cvx_config3(mbrf):
     # the solver's own objective and its dual value bracket the optimum to 1e-4
     assert abs(ex["info"][2] - objective_fir_qp(p, ex["x"])) <= 1e-9
     assert abs(ex["info"][2] - ex["info"][3]) <= TOL_OBJ * ex["info"][2]
-    with pytest.raises(NotImplementedError):
-        mbrf.fir_qp_cvx(16, [-0.5, 0.5], [1, 1], [0.1], 2, [1.0, 1.0])
+    with pytest.raises(ValueError):
+        mbrf.fir_qp_cvx(16, [-0.5, 0.5], [1, 1], [0.1], 2, [1.0, 1.0, 1.0])     # fir_qp_cvx.m:193-195 "invalid input of obj"
+
+
+@pytest.mark.parametrize("case", ["mm_n16_a", "mm_n16_b", "mm_n12_c"])
+def test_fir_qp_cvx_minimax_vs_scipy_reference(mbrf, case):
+    """Two-element obj (fir_qp_cvx.m:170-191): delta + obj(1)*E_total + obj(2)*Peak within 1e-4 relative of SciPy
+    trust-constr, transition rows within 1.1 to 1e-6."""
+    from oracle.fir_problems import build_fir_qp, objective_fir_qp_minimax, violation_fir_qp_minimax
+    k = json.load(open(os.path.join(GOLDEN, "fir_qp_minimax_known.json")))[case]
+    h, st, ex = mbrf.fir_qp_cvx(k["n"], k["f"], k["a"], k["d"], k["k"], k["obj"], return_info=True)
+    assert st == "Solved" and h.size == k["n"]
+    p = build_fir_qp(k["n"], k["f"], k["a"], k["d"], k["k"], 0.0)
+    x = ex["x"]
+    assert abs(ex["info"][2] - objective_fir_qp_minimax(p, x, k["obj"])) <= 1e-9 * max(1.0, ex["info"][2])
+    assert abs(objective_fir_qp_minimax(p, x, k["obj"]) - k["objective"]) <= TOL_OBJ * k["objective"]
+    assert violation_fir_qp_minimax(p, x) <= TOL_VIOL
 
 
 def test_fir_ap_min_order_search(mbrf):
