@@ -248,6 +248,21 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
             dt = time.perf_counter() - t2
             fmp = {"call": "fmp2_batch -> mbrf_fmp2_batch (one CTA per design, four 4096-point fp64 FFTs in shared memory), host buffers",
                    "designs": int(ok.sum()), "seconds": dt, "designs_per_s": float(ok.sum() / dt)}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # CPU baseline of the solver path: CVX/SeDuMi/linprog are not installable offline, so the restated
+        # problem of ONE design of this sweep goes to HiGHS (SciPy) on one host core -- the LP without the 2-D Peak cones,
+        # i.e. less work than the reference solve.  Bounded sample: one design (~50 s).
+        from oracle.fir_problems import build_fir_ap, solve_fir_ap_highs
+        o_mid, p_mid = float(objs[len(objs) // 2]), float(peaks[len(peaks) // 2])
+        pr = build_fir_ap(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], o_mid, p_mid)
+        t3 = time.perf_counter()
+        res, _ = solve_fir_ap_highs(pr, 0)
+        dt3 = time.perf_counter() - t3
+        cpu = {"value": 1.0 / dt3, "unit": "designs/s", "cores": 1, "kind": "port", "seconds": dt3,
+               "highs_status": int(res.status), "objective": float(res.fun) if res.status == 0 else None,
+               "sample": "1 design of the same sweep (obj=%.3g, Peak=%.3g), N=256, 7686-row grid: HiGHS via scipy.optimize.linprog on "
+                         "the restated LP without the Peak cones (oracle/fir_problems.py); CVX/SeDuMi are not installable offline" % (o_mid, p_mid)}
     info = r["info"]
     solved = int((info[:, 0] == 1).sum())
     iters = float(info[:, 1].max()) if info.size else 0.0
@@ -261,7 +276,7 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
             "(4 and 8 GPUs) every ~0.1 decade is solved cold and the other designs start from the nearest seed; coarser grids run cold", "solved_on_rank0": solved, "local_designs_rank0": int(info.shape[0]),
             "seconds": sec, "iterations_max": iters, "gpu_launches": int(launches),
             "workload": "cfg4 slice: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, obj x Peak trade-off grid",
-            "single_design": single, "roofline": roof, "fmp2": fmp,
+            "single_design": single, "roofline": roof, "fmp2": fmp, "cpu_baseline": cpu,
             "tolerances": {"eps_pr": fir.EPS_PR, "eps_gap_rel": fir.EPS_GAP, "eps_dr": fir.EPS_DR},
             "gemm_tflops_useful": flops / sec / 1e12, "iterations_mean": float(info[:, 1].mean()) if info.size else 0.0,
             "note": "fp64 restarted PDHG; the two products of every iteration run on tcgen05 int8 tiles (split-integer, 5 base-256 "

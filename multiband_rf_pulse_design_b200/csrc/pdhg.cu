@@ -265,14 +265,137 @@ gemv_rows_kernel(const double *__restrict__ A, int ld, const double *__restrict_
     }
 }
 
-template <typename... Args>
-static void launch_thin(int nb, dim3 grid, cudaStream_t st, Args... args)
+// The same product for NB = 2, 4, 8 designs with the x tile staged in shared memory, design-major ([b][k]): a CTA owns 32 rows
+// (8 warps x 4 rows), per 64-k block every lane loads its k-pair of each of its 4 rows (LDG.128) and, per design, the matching
+// x pair (conflict-free LDS.128), i.e. 8 NB FMAs for 4 + NB loads.  One pass over the L2-resident matrix for the whole batch.
+template <int NB>
+__global__ void __launch_bounds__(256)
+gemv_rows4_kernel(const double *__restrict__ A, int ld, const double *__restrict__ X, double *__restrict__ C, int R, int kdim,
+                  int kchunk, long long slab)
 {
-    switch (nb) {
-    case 1: gemv_rows_kernel<1><<<grid, 256, 0, st>>>(args...); break;
-    case 2: gemv_rows_kernel<2><<<grid, 256, 0, st>>>(args...); break;
-    case 4: gemv_rows_kernel<4><<<grid, 256, 0, st>>>(args...); break;
-    default: gemv_rows_kernel<8><<<grid, 256, 0, st>>>(args...); break;
+    __shared__ __align__(16) double xs[NB][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * 32 + warp * 4;
+    const int k_begin = blockIdx.y * kchunk, k_end = min(kdim, k_begin + kchunk);
+    double acc[4][NB];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[i][b] = 0.0;
+    for (int k0 = k_begin; k0 < k_end; k0 += 64) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 64 * NB; e += 256) xs[e % NB][e / NB] = X[(size_t)k0 * NB + e];
+        __syncthreads();
+        double2 av[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            av[i] = r0 + i < R ? *reinterpret_cast<const double2 *>(A + (size_t)(r0 + i) * ld + k0 + 2 * lane) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const double2 xv = *reinterpret_cast<const double2 *>(&xs[b][2 * lane]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][b] = fma(av[i].y, xv.y, fma(av[i].x, xv.x, acc[i][b]));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i][b] += __shfl_xor_sync(0xffffffffu, acc[i][b], o);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (r0 + i < R) {
+                double *out = C + (size_t)blockIdx.y * slab + (size_t)(r0 + i) * NB;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) out[b] = acc[i][b];
+            }
+    }
+}
+
+// out[o][b] = sum_k AT[k][o] * x[k][b] with AT k-major ([kdim x ldat], the output index contiguous) for NB = 2, 4, 8 designs:
+// a CTA owns 64 outputs, its four quarters take every 4th k of a 64-row tile, the x tile is broadcast from shared memory
+// (NB FMAs per loaded matrix element), the quarters are summed through shared memory.  Measured on the cfg4 LP
+// (7808 x 512): faster than the warp-per-row kernel above for NB >= 2 (there every lane fetches 2 NB values of x per
+// matrix pair: 279 us per iteration at NB = 8), slower for NB <= 2.
+template <int NB>
+__global__ void __launch_bounds__(256)
+thin_kernel(const double *__restrict__ AT, int ldat, const double *__restrict__ X, double *__restrict__ C, int kdim,
+            int kchunk, long long slab)
+{
+    __shared__ double xs[64 * NB];
+    __shared__ double red[4][64][NB];
+    const int tid = threadIdx.x, ol = tid & 63, q = tid >> 6;
+    const int o = blockIdx.x * 64 + ol;
+    const int k_begin = blockIdx.y * kchunk, k_end = min(kdim, k_begin + kchunk);
+    double acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.0;
+    for (int k0 = k_begin; k0 < k_end; k0 += 64) {
+        const int nk = min(64, k_end - k0);
+        for (int e = tid; e < nk * NB; e += 256) xs[e] = X[(size_t)k0 * NB + e];
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = q; kk < nk; kk += 4) {
+            const double a = AT[(size_t)(k0 + kk) * ldat + o];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = fma(a, xs[kk * NB + b], acc[b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) red[q][ol][b] = acc[b];
+    __syncthreads();
+    if (q == 0) {
+        double *out = C + (size_t)blockIdx.y * slab + (size_t)o * NB;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = red[0][ol][b] + red[1][ol][b] + red[2][ol][b] + red[3][ol][b];
+    }
+}
+
+// which kernel serves a thin batch (measured on the cfg4 LP, 7808 x 512, us per PDHG iteration, rows / staged rows / columns):
+//   NB = 1: 34 / -- / 65     NB = 2: 46 / 35 / 64     NB = 4: 93 / 38 / 43     NB = 8: 279 / 58 / 53
+// MBRF_THIN_KERNEL = rows | staged | columns forces one (developer switch)
+enum { THIN_ROWS = 0, THIN_STAGED = 1, THIN_COLUMNS = 2 };
+static int thin_choice(int nb)
+{
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("MBRF_THIN_KERNEL");
+        forced = !e ? -1 : !strcmp(e, "rows") ? THIN_ROWS : !strcmp(e, "staged") ? THIN_STAGED : !strcmp(e, "columns") ? THIN_COLUMNS : -1;
+    }
+    if (forced >= 0) return (forced == THIN_STAGED && nb == 1) ? THIN_ROWS : forced;
+    return nb == 1 ? THIN_ROWS : nb <= 4 ? THIN_STAGED : THIN_COLUMNS;
+}
+// A: row-major [R x ld] for the rows kernels; AT: the same matrix k-major [kdim x ldat] for the column kernel
+static void launch_thin(int nb, cudaStream_t st, const double *A, int ld, const double *AT, int ldat, const double *X, double *C,
+                        int R, int kdim, int kchunk, int nslab, long long slab)
+{
+    const int which = thin_choice(nb);
+    if (which == THIN_STAGED) {
+        const dim3 grid((R + 31) / 32, nslab);
+        switch (nb) {
+        case 2: gemv_rows4_kernel<2><<<grid, 256, 0, st>>>(A, ld, X, C, R, kdim, kchunk, slab); break;
+        case 4: gemv_rows4_kernel<4><<<grid, 256, 0, st>>>(A, ld, X, C, R, kdim, kchunk, slab); break;
+        default: gemv_rows4_kernel<8><<<grid, 256, 0, st>>>(A, ld, X, C, R, kdim, kchunk, slab); break;
+        }
+    } else if (which == THIN_ROWS) {
+        const dim3 grid(R / 8, nslab);
+        switch (nb) {
+        case 1: gemv_rows_kernel<1><<<grid, 256, 0, st>>>(A, ld, X, C, R, kdim, kchunk, slab); break;
+        case 2: gemv_rows_kernel<2><<<grid, 256, 0, st>>>(A, ld, X, C, R, kdim, kchunk, slab); break;
+        case 4: gemv_rows_kernel<4><<<grid, 256, 0, st>>>(A, ld, X, C, R, kdim, kchunk, slab); break;
+        default: gemv_rows_kernel<8><<<grid, 256, 0, st>>>(A, ld, X, C, R, kdim, kchunk, slab); break;
+        }
+    } else {
+        const dim3 grid(R / 64, nslab);
+        switch (nb) {
+        case 1: thin_kernel<1><<<grid, 256, 0, st>>>(AT, ldat, X, C, kdim, kchunk, slab); break;
+        case 2: thin_kernel<2><<<grid, 256, 0, st>>>(AT, ldat, X, C, kdim, kchunk, slab); break;
+        case 4: thin_kernel<4><<<grid, 256, 0, st>>>(AT, ldat, X, C, kdim, kchunk, slab); break;
+        default: thin_kernel<8><<<grid, 256, 0, st>>>(AT, ldat, X, C, kdim, kchunk, slab); break;
+        }
     }
 }
 
@@ -1165,7 +1288,7 @@ static void tc_slice_rows(const double *A, int ld, int R, int kdim, int8_t *out,
 static int gemm_nn(const Problem &p, const double *X, double *C, cudaStream_t st, const TcState *tcs = nullptr, bool have_max = false)
 {
     if (p.Bp <= 8) {   // thin batch (1..8 designs): one pass over K^T, bound by streaming the matrix
-        launch_thin(p.Bp, dim3(p.Mp / 8, 1), st, p.K, p.ldk, X, C, p.Mp, p.Np, p.Np, 0LL);
+        launch_thin(p.Bp, st, p.K, p.ldk, p.KT, p.Mp, X, C, p.Mp, p.Np, p.Np, 1, 0LL);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     }
@@ -1182,7 +1305,7 @@ static int gemm_tn(const Problem &p, const double *Y, double *G, cudaStream_t st
 {
     if (p.Bp <= 8) {   // thin batch: one pass over K, the long reduction split into p.P slabs
         const int kc = up((p.Mp + p.P - 1) / p.P, 64);
-        launch_thin(p.Bp, dim3(p.Np / 8, p.P), st, p.KT, p.Mp, Y, G, p.Np, p.Mp, kc, (long long)p.Np * p.Bp);
+        launch_thin(p.Bp, st, p.KT, p.Mp, p.K, p.ldk, Y, G, p.Np, p.Mp, kc, p.P, (long long)p.Np * p.Bp);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     }
