@@ -276,7 +276,7 @@ int mbrf_fmp2_batch_device(const double *r_re, const double *r_im, int n, int B,
 
 /* ------------------------------------------------------------------------------------------------
  * Batched inverse SLR transform (the step after the FIR design, dzrf_mb.m:239-240): aca = b2a(bc) of rf_tools/b2a.m:13-28
- * (n = 2^k <= 1024: the length-8n transform is radix-2) and rf = ab2rf(ac, bc) of rf_tools/ab2rf.m:12-26 (n <= 2048).
+ * (n = 2^k <= 1024: radix-2 transform of length 8n; any other n <= 512: Bluestein) and rf = ab2rf(ac, bc) of rf_tools/ab2rf.m:12-26 (n <= 2048).
  * Host pointers, complex data as split re / im planes (imaginary inputs may be NULL), row-major [B x n].
  * ------------------------------------------------------------------------------------------------ */
 int mbrf_b2a_batch(const double *b_re, const double *b_im, int n, int B, double *a_re, double *a_im);

@@ -8,7 +8,7 @@
 //                        rf_i = 2 atan2(|s|, c) exp(j angle(s)),
 //                        a <- (c a + s b)(2:i),  b <- (-conj(s) a + c b)(1:i-1)                            (ab2rf.m:16-26)
 // The recursion is inherently serial in i (n steps, one CTA barrier each, i complex updates spread over the CTA):
-// parallelism comes from the batch.  b2a needs a length-8n FFT: the radix-2 kernel takes n = 2^k <= 1024.
+// parallelism comes from the batch.  b2a needs a length-8n DFT: radix-2 for n = 2^k <= 1024, Bluestein for other n <= 512.
 #include "common.h"
 #include "fft_smem.cuh"
 
@@ -29,18 +29,75 @@ __device__ __forceinline__ double2 cdiv(double2 a, double2 b)
     return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
 }
 
-// b: [B][n] complex (split planes) -> a: [B][n]; N = 8n = 2^lg
-__global__ void __launch_bounds__(THREADS) b2a_kernel(const double *__restrict__ b_re, const double *__restrict__ b_im, int n, int lg,
-                                                      const double2 *__restrict__ tw, double *__restrict__ a_re,
-                                                      double *__restrict__ a_im)
+// DFT of s[0..N) in place for ANY even N (all threads of the CTA).  N = 2^lg: radix-2.  Otherwise Bluestein's chirp-z
+// identity  k m = (k^2 + m^2 - (k-m)^2) / 2:  X_k = c_k sum_m (x_m c_m) conj(c)_{k-m},  c_m = exp(-i pi m^2 / N), a circular
+// convolution of length L = 2^lgL >= 2N-1 done with three radix-2 transforms (the transform of the chirp, Bhat, is computed
+// once per call).  The buffer s must hold L entries; entries >= N are scratch.  Unnormalised inverse on request.
+struct DftPlan {
+    int N, lgL;                 // lgL = log2 N when N is a power of two (then chirp = Bhat = nullptr)
+    const double2 *tw;          // twiddles of the length-2^lgL transform
+    const double2 *chirp;       // [N]
+    const double2 *Bhat;        // [2^lgL]
+};
+__device__ void dft_inplace(double2 *s, const DftPlan &pl, bool inverse)
+{
+    if (!pl.chirp) { fft_inplace(s, pl.lgL, pl.tw, inverse); return; }
+    const int N = pl.N, L = 1 << pl.lgL;
+    for (int m = threadIdx.x; m < L; m += blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (m < N) {
+            v = s[m];
+            if (inverse) v.y = -v.y;                      // idft(x) = conj(dft(conj(x)))
+            v = cmul(v, pl.chirp[m]);
+        }
+        s[m] = v;
+    }
+    __syncthreads();
+    fft_inplace(s, pl.lgL, pl.tw, false);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s[i] = cmul(s[i], pl.Bhat[i]);
+    __syncthreads();
+    fft_inplace(s, pl.lgL, pl.tw, true);
+    const double invL = 1.0 / (double)L;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        double2 v = cmul(pl.chirp[k], s[k]);
+        v.x *= invL; v.y *= invL;
+        if (inverse) v.y = -v.y;
+        s[k] = v;
+    }
+    __syncthreads();
+}
+// one CTA: chirp[m] = exp(-i pi m^2 / N) (m^2 reduced mod 2N in integers) and Bhat = FFT_L of conj(chirp) wrapped to (-N, N)
+__global__ void __launch_bounds__(THREADS) bluestein_setup_kernel(int N, int lgL, const double2 *__restrict__ tw, double2 *chirp,
+                                                                  double2 *Bhat)
+{
+    extern __shared__ double2 s[];
+    const int L = 1 << lgL;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (int m = threadIdx.x; m < N; m += blockDim.x) {
+        const long long r = ((long long)m * m) % (2LL * N);
+        double sn, cs;
+        sincospi(-(double)r / (double)N, &sn, &cs);
+        chirp[m] = make_double2(cs, sn);
+        s[m] = make_double2(cs, -sn);
+        if (m > 0) s[L - m] = make_double2(cs, -sn);
+    }
+    __syncthreads();
+    fft_inplace(s, lgL, tw, false);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) Bhat[i] = s[i];
+}
+
+// b: [B][n] complex (split planes) -> a: [B][n]; N = 8n (any n: dft_inplace)
+__global__ void __launch_bounds__(THREADS) b2a_kernel(const double *__restrict__ b_re, const double *__restrict__ b_im, int n,
+                                                      const DftPlan pl, double *__restrict__ a_re, double *__restrict__ a_im)
 {
     extern __shared__ double2 s[];
     __shared__ double red[THREADS];
-    const int N = 1 << lg, H = N >> 1, q = blockIdx.x;
+    const int N = pl.N, H = N >> 1, q = blockIdx.x;
     for (int i = threadIdx.x; i < N; i += blockDim.x)
         s[i] = i < n ? make_double2(b_re[(size_t)q * n + i], b_im ? b_im[(size_t)q * n + i] : 0.0) : make_double2(0.0, 0.0);
     __syncthreads();
-    fft_inplace(s, lg, tw, false);                                  // bf
+    dft_inplace(s, pl, false);                                      // bf
     double m = 0.0;
     for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmax(m, hypot(s[i].x, s[i].y));
     red[threadIdx.x] = m;
@@ -53,13 +110,13 @@ __global__ void __launch_bounds__(THREADS) b2a_kernel(const double *__restrict__
         s[i] = make_double2(log(sqrt(1.0 - (re * re + im * im))), 0.0);
     }
     __syncthreads();
-    fft_inplace(s, lg, tw, false);                                  // xlf
+    dft_inplace(s, pl, false);                                      // xlf
     for (int k = threadIdx.x; k < N; k += blockDim.x) {             // mag2mp.m:28-31
         const double g = (k == 0 || k == H) ? 1.0 : (k < H ? 2.0 : 0.0);
         s[k] = make_double2(s[k].x * g, s[k].y * g);
     }
     __syncthreads();
-    fft_inplace(s, lg, tw, true);
+    dft_inplace(s, pl, true);
     const double invN = 1.0 / (double)N;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {             // afa = exp(xlaf)
         const double mag = exp(s[i].x * invN);
@@ -68,7 +125,7 @@ __global__ void __launch_bounds__(THREADS) b2a_kernel(const double *__restrict__
         s[i] = make_double2(mag * cs, mag * sn);
     }
     __syncthreads();
-    fft_inplace(s, lg, tw, false);                                  // aca = fft(afa) / blp, reversed first n
+    dft_inplace(s, pl, false);                                      // aca = fft(afa) / blp, reversed first n
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         a_re[(size_t)q * n + i] = s[n - 1 - i].x * invN;
         a_im[(size_t)q * n + i] = s[n - 1 - i].y * invN;
@@ -134,36 +191,49 @@ using namespace mbrf::islr;
 
 extern "C" {
 
-/* aca = b2a(bc) for B beta polynomials of n = 2^k <= 1024 coefficients (rf_tools/b2a.m:13-28); host pointers, split planes,
- * row-major [B x n]; b_im may be NULL. */
+/* aca = b2a(bc) for B beta polynomials of n coefficients (rf_tools/b2a.m:13-28); host pointers, split planes, row-major [B x n];
+ * b_im may be NULL.  n = 2^k <= 1024 runs a radix-2 transform of length 8n, any other n <= 512 Bluestein's algorithm. */
 int mbrf_b2a_batch(const double *b_re, const double *b_im, int n, int B, double *a_re, double *a_im)
 {
     if (int rc = require_device()) return rc;
     if (!b_re || !a_re || !a_im || n < 1 || B < 1) { set_error("b2a: bad arguments (n=%d B=%d)", n, B); return MBRF_EINVAL; }
-    const int lg = lg8n(n);
-    if (lg < 0 || n > 1024) {
-        set_error("b2a: n=%d is not a power of two <= 1024 (the length-8n transform is radix-2 in shared memory)", n);
+    const int N = 8 * n;
+    int lg = lg8n(n);
+    const bool pow2 = lg >= 0;
+    if (!pow2) { lg = 0; while ((1 << lg) < 2 * N - 1) ++lg; }
+    const int L = 1 << lg;
+    if ((size_t)L * sizeof(double2) > 200 * 1024) {
+        set_error("b2a: n=%d too long for the shared-memory transform (n = 2^k <= 1024, other n <= 512)", n);
         return MBRF_EINVAL;
     }
-    const int N = 1 << lg;
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t nb = (size_t)n * B * 8;
     Ctx &cx = t_ctx;
-    if (int rc = cx.dev.reserve(4 * al(nb) + al((size_t)N / 2 * 16))) return rc;
+    if (int rc = cx.dev.reserve(4 * al(nb) + al((size_t)L / 2 * 16) + al((size_t)N * 16) + al((size_t)L * 16))) return rc;
     char *d = (char *)cx.dev.ptr;
     double *dbr = (double *)d, *dbi = (double *)(d + al(nb)), *dar = (double *)(d + 2 * al(nb)), *dai = (double *)(d + 3 * al(nb));
     double2 *tw = (double2 *)(d + 4 * al(nb));
+    double2 *chirp = (double2 *)((char *)tw + al((size_t)L / 2 * 16));
+    double2 *Bhat = (double2 *)((char *)chirp + al((size_t)N * 16));
     MBRF_CUDA(cudaMemcpyAsync(dbr, b_re, nb, cudaMemcpyHostToDevice, 0));
     if (b_im) MBRF_CUDA(cudaMemcpyAsync(dbi, b_im, nb, cudaMemcpyHostToDevice, 0));
-    twiddle_kernel<<<(N / 2 + 255) / 256, 256>>>(tw, N / 2);
+    twiddle_kernel<<<(L / 2 + 255) / 256, 256>>>(tw, L / 2);
     MBRF_LAUNCH_CHECK();
-    const size_t smem = (size_t)N * sizeof(double2);
+    const size_t smem = (size_t)L * sizeof(double2);
     static size_t attr_set = 0;
     if (smem > 40 * 1024 && smem > attr_set) {
         MBRF_CUDA(cudaFuncSetAttribute(b2a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MBRF_CUDA(cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    b2a_kernel<<<B, THREADS, smem>>>(dbr, b_im ? dbi : nullptr, n, lg, tw, dar, dai);
+    DftPlan pl;
+    pl.N = N; pl.lgL = lg; pl.tw = tw; pl.chirp = nullptr; pl.Bhat = nullptr;
+    if (!pow2) {
+        bluestein_setup_kernel<<<1, THREADS, smem>>>(N, lg, tw, chirp, Bhat);
+        MBRF_LAUNCH_CHECK();
+        pl.chirp = chirp; pl.Bhat = Bhat;
+    }
+    b2a_kernel<<<B, THREADS, smem>>>(dbr, b_im ? dbi : nullptr, n, pl, dar, dai);
     MBRF_LAUNCH_CHECK();
     MBRF_CUDA(cudaMemcpyAsync(a_re, dar, nb, cudaMemcpyDeviceToHost, 0));
     MBRF_CUDA(cudaMemcpyAsync(a_im, dai, nb, cudaMemcpyDeviceToHost, 0));

@@ -84,7 +84,7 @@ def _planes(z):
 
 def b2a(bc):
     """aca = b2a(bc) — rf_tools/b2a.m:13-28: minimum-phase, minimum-power alpha polynomial of a beta polynomial.
-    bc: [n] or a batch [B, n]; n must be a power of two <= 1024 (length-8n radix-2 transform in shared memory)."""
+    bc: [n] or a batch [B, n]; n = 2^k <= 1024 (radix-2 transform of length 8n in shared memory) or any other n <= 512 (Bluestein)."""
     shape, br, bi = _planes(bc)
     B, n = shape
     ar = np.empty((B, n)); ai = np.empty((B, n))

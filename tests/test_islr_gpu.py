@@ -25,7 +25,7 @@ def _betas(n, B, seed, complex_b):
     return np.stack(out)
 
 
-@pytest.mark.parametrize("n", [16, 64, 256, 512])
+@pytest.mark.parametrize("n", [16, 64, 256, 512, 48, 260, 500])      # 2^k: radix-2; others: Bluestein (dzrf_mb uses n = 260)
 @pytest.mark.parametrize("complex_b", [False, True])
 def test_b2a_and_ab2rf_match_reference(mbrf, oracle, n, complex_b):
     bc = _betas(n, 5, n, complex_b)
@@ -70,7 +70,7 @@ def test_inverse_then_forward_slr_round_trip(mbrf):
 
 def test_islr_argument_checks(mbrf):
     with pytest.raises(mbrf.MbrfError):
-        mbrf.b2a(np.ones(48))                              # not a power of two
+        mbrf.b2a(np.ones(600) * 1e-3)                      # not a power of two and > 512
     with pytest.raises(mbrf.MbrfError):
         mbrf.b2a(np.ones(2048) * 1e-3)                     # beyond the shared-memory transform
     with pytest.raises(ValueError):
