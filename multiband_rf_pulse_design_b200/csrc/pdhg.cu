@@ -937,14 +937,22 @@ __global__ void reduce_slabs_kernel(Problem p)
 
 // Row-side metrics of a candidate (cand 0: running average = sums/cnt, cand 1: current iterate):
 //   pr = max violation of K z, hs = h*(y), dy2 = ||y - y0||^2.   S holds K*(zs or z).
-__global__ void row_metrics_kernel(Problem p, int cand)
+__global__ void __launch_bounds__(256) row_metrics_kernel(Problem p, int cand)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per design, rows strided over blockIdx.y
-    if (b >= p.Bp) return;
+    // blockDim = (64 designs, 4 row lanes): rows strided over the row lanes and blockIdx.y, the row lanes are combined in
+    // shared memory before the atomics (one thread per design and 64 row blocks was latency-bound: 130 us per call)
+    __shared__ double red[6][4][64];
+    const int b = blockIdx.x * 64 + threadIdx.x;
+    const bool live = b < p.Bp;
+    const int bb = live ? b : 0;
+    {
+    const int b = bb;
     const double inv = cand == 0 ? 1.0 / fmax(p.ctl[b].cnt, 1.0) : 1.0;
     const double *yv = cand == 0 ? p.ys : p.y;
     double pr = 0.0, hs = 0.0, dy2 = 0.0, tmax = 0.0, gmax = 0.0, gmax2 = 0.0;
-    for (int i = blockIdx.y; i < p.Mp; i += gridDim.y) {
+    // disk / group pairs are handled by the thread that meets their first (even) row: keep pairs inside one row lane
+    for (int i2 = blockIdx.y * 4 + threadIdx.y; i2 < (p.Mp >> 1); i2 += 4 * gridDim.y)
+    for (int i = 2 * i2; i < 2 * i2 + 2 && live; ++i) {
         const size_t o = (size_t)i * p.Bp + b;
         const double kz = p.S[o] * inv, y = yv[o] * inv, lo = p.lo[o], hi = p.hi[o];
         if (i >= p.grow2 && i < p.grow2 + 2 * p.ng2) {   // centred group block: h* = <centre, y>, track max ||K z - centre||
@@ -987,13 +995,21 @@ __global__ void row_metrics_kernel(Problem p, int cand)
         const double d = y - p.y0[o];
         dy2 = fma(d, d, dy2);
     }
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    red[0][ty][tx] = pr; red[1][ty][tx] = tmax; red[2][ty][tx] = gmax; red[3][ty][tx] = gmax2; red[4][ty][tx] = hs; red[5][ty][tx] = dy2;
+    }
+    __syncthreads();
+    if (threadIdx.y != 0 || !live) return;
+    const int tx = threadIdx.x;
+    auto mx4 = [&](int k) { return fmax(fmax(red[k][0][tx], red[k][1][tx]), fmax(red[k][2][tx], red[k][3][tx])); };
+    auto sm4 = [&](int k) { return (red[k][0][tx] + red[k][1][tx]) + (red[k][2][tx] + red[k][3][tx]); };
     double *acc = p.acc + (size_t)cand * NACC * p.Bp;
-    atomic_max_pos(acc + A_PR * p.Bp + b, pr);
-    atomic_max_pos(acc + A_TMAX * p.Bp + b, tmax);
-    atomic_max_pos(acc + A_GMAX * p.Bp + b, gmax);
-    atomic_max_pos(acc + A_GMAX2 * p.Bp + b, gmax2);
-    atomicAdd(acc + A_HS * p.Bp + b, hs);
-    atomicAdd(acc + A_DY2 * p.Bp + b, dy2);
+    atomic_max_pos(acc + A_PR * p.Bp + b, mx4(0));
+    atomic_max_pos(acc + A_TMAX * p.Bp + b, mx4(1));
+    atomic_max_pos(acc + A_GMAX * p.Bp + b, mx4(2));
+    atomic_max_pos(acc + A_GMAX2 * p.Bp + b, mx4(3));
+    atomicAdd(acc + A_HS * p.Bp + b, sm4(4));
+    atomicAdd(acc + A_DY2 * p.Bp + b, sm4(5));
 }
 
 // Column-side metrics: pobj = c^T z, gz = g^T z, dr = ||z - P_X(z - g)||_inf, dz2 = ||z - z0||^2,
@@ -1681,7 +1697,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             z_shrink_kernel<<<gz, TPB, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
         } else if (wide) {
-            z_update_wide_kernel<<<dim3(p.Bp / 64, 32), 256, 0, st>>>(p);
+            z_update_wide_kernel<<<dim3(p.Bp / 64, p.Np / 4 < 128 ? p.Np / 4 : 128), 256, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
         } else {
             z_update_kernel<<<gz, TPB, 0, st>>>(p);
@@ -1717,7 +1733,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         pc.P = split_k(p.Mp, p.Np, p.Bp);
         for (int cand = 0; cand < 2; ++cand) {
             if (int rc = gemm_nn(pc, cand == 0 ? p.zs : p.z, p.S, st)) return rc;
-            row_metrics_kernel<<<gm, 64, 0, st>>>(p, cand);
+            row_metrics_kernel<<<gm, dim3(64, 4), 0, st>>>(p, cand);
             MBRF_LAUNCH_CHECK();
             if (int rc = gemm_tn(pc, cand == 0 ? p.ys : p.y, p.G, st)) return rc;
             reduce_slabs_kernel<<<gz, TPB, 0, st>>>(pc);
