@@ -221,11 +221,16 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
     fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], objs[:8], peaks, [0.0],
                          max_iter=512)                  # warm-up: context, buffers, kernels
     barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
+    if sampler:
+        sampler.start()
     l0 = lib.mbrf_launch_count()
     t0 = time.perf_counter()
     r = fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], objs, peaks, [0.0], rank=rank,
                              world=world, batch=per_gpu, max_iter=60000, seed_stride="auto")
-    sec = max_over_ranks(time.perf_counter() - t0)
+    t1s = time.perf_counter()
+    sec = max_over_ranks(t1s - t0)
+    clocks = sampler.stop(t0, t1s) if sampler else None
     launches = lib.mbrf_launch_count() - l0
     barrier()
     single = None
@@ -276,7 +281,7 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
             "(4 and 8 GPUs) every ~0.1 decade is solved cold and the other designs start from the nearest seed; coarser grids run cold", "solved_on_rank0": solved, "local_designs_rank0": int(info.shape[0]),
             "seconds": sec, "iterations_max": iters, "gpu_launches": int(launches),
             "workload": "cfg4 slice: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, obj x Peak trade-off grid",
-            "single_design": single, "roofline": roof, "fmp2": fmp, "cpu_baseline": cpu,
+            "single_design": single, "roofline": roof, "fmp2": fmp, "cpu_baseline": cpu, "clocks": clocks,
             "tolerances": {"eps_pr": fir.EPS_PR, "eps_gap_rel": fir.EPS_GAP, "eps_dr": fir.EPS_DR},
             "gemm_tflops_useful": flops / sec / 1e12, "iterations_mean": float(info[:, 1].mean()) if info.size else 0.0,
             "note": "fp64 restarted PDHG; the two products of every iteration run on tcgen05 int8 tiles (split-integer, 5 base-256 "
