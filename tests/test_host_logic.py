@@ -64,3 +64,41 @@ def test_speculation_lists_only_reachable_probes():
     probes = fir._speculate((2, 256, 129), step, 3)
     assert probes[0] == 129 and set(probes) == {129, 66, 193, 34, 98, 161, 225}
     assert fir._speculate((2, 3, None), step, 3) == []
+
+
+def test_seeded_sweep_solves_every_design_once_and_warm_starts_from_the_nearest_seed(monkeypatch):
+    """fir._solve_seeded host logic with a fake solver: cold seeds every `stride`-th member of a (band edges, Peak) chain plus
+    the largest weight, every other design solved exactly once in the second pass, started from the nearest seed's solution."""
+    import numpy as np
+    from multiband_rf_pulse_design_b200 import fir
+    calls = []
+
+    def fake(n, designs, warm=None, want_dual=False, **kw):
+        ids = [d["id"] for d in designs]
+        calls.append((ids, warm))
+        B = len(designs)
+        x = np.array([[d["id"]] * (2 * n - 1) for d in designs], float)
+        info = np.zeros((B, 8)); info[:, 0] = 1
+        if want_dual:
+            return x, np.zeros(B), info, np.array([[100.0 + d["id"]] * 5 for d in designs]), np.array([2.0 + d["id"] for d in designs])
+        return x, np.zeros(B), info
+    monkeypatch.setattr(fir, "_solve_batch_ap", fake)
+    objs = list(np.logspace(-1, 0, 40)) * 2
+    peaks = [1e-3] * 40 + [2e-3] * 40
+    perm = np.random.default_rng(0).permutation(80)
+    designs = [dict(id=int(i)) for i in perm]
+    x, t, info = fir._solve_seeded(4, designs, [b"f"] * 80, [peaks[i] for i in perm], [objs[i] for i in perm], 8)
+    assert np.array_equal(x[:, 0], perm)                      # every design got its own answer back, in the caller's order
+    assert len(calls) == 2 and calls[0][1] is None            # pass 1 cold
+    seeds, rest = calls[0][0], calls[1][0]
+    assert sorted(seeds + rest) == list(range(80)) and not set(seeds) & set(rest)
+    for chain in (range(0, 40), range(40, 80)):
+        s = sorted(i for i in seeds if i in chain)
+        assert s == sorted(set(list(chain)[4::8]) | {chain[-1]})     # stride 8 from offset 4, plus the largest weight
+    x0, y0, om = calls[1][1]
+    for k, i in enumerate(rest):
+        chain = [s for s in seeds if (s < 40) == (i < 40)]
+        dist = min(abs(np.log(objs[s]) - np.log(objs[i])) for s in chain)
+        used = int(x0[k, 0])
+        assert used in chain and abs(abs(np.log(objs[used]) - np.log(objs[i])) - dist) < 1e-12      # a nearest seed (ties: either)
+        assert y0[k, 0] == 100.0 + used and om[k] == 2.0 + used

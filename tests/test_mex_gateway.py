@@ -16,7 +16,7 @@ MEX = os.path.join(ROOT, "multiband_rf_pulse_design_b200", "matlab")
 @pytest.fixture(scope="module")
 def gateways(mbrf):
     subprocess.check_call(["make", "-s", "-C", MEX, "check"])
-    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg")}
+    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "b2a", "ab2rf", "fmp2")}
 
 
 def test_gateways_link_and_report_errors_like_the_reference(gateways, oracle, mbrf):
@@ -97,3 +97,38 @@ def test_fir_pdhg_gateway_solves_like_the_python_mirror(gateways, oracle, mbrf):
     assert k["outer_obj"] * (1 - 1e-4) <= info[2, 0] <= k["inner_obj"] * (1 + 1e-4)   # x1 + obj*ripple_stop
     out, err = oracle.mex_call(gateways["fir_pdhg"], 2, w_row)
     assert out is None and err.startswith("Usage:")
+
+
+def test_postprocessing_gateways_usage_errors(gateways, oracle):
+    """b2a / ab2rf / fmp2 gateways (matlab/islr_mex.c): arity and shape errors through mexErrMsgTxt, before any device work."""
+    out, err = oracle.mex_call(gateways["b2a"], 1, np.ones(8), np.ones(8))
+    assert out is None and err == "Usage: aca = b2a(bc)"
+    out, err = oracle.mex_call(gateways["ab2rf"], 1, np.ones(8), np.ones(9))
+    assert out is None and err == "ab2rf: ac and bc must have the same size"
+    out, err = oracle.mex_call(gateways["fmp2"], 1, np.ones(8))
+    assert out is None and err == "filter length must be odd"            # fir_ap_cvx.m:265-268
+
+
+@pytest.mark.gpu
+def test_postprocessing_gateways_vs_restatements(gateways, oracle):
+    """One polynomial (vector) and a batch (n-by-B matrix) through the b2a / ab2rf / fmp2 gateways vs oracle/ restatements."""
+    from oracle.fir_problems import fmp2_reference
+    n, B = 64, 3
+    k = np.arange(n) - (n - 1) / 2
+    bc = np.stack([np.sinc(k * (3.0 + q) / n) * np.hamming(n) * 0.3 / (n / 8) * np.exp(1j * 0.01 * q * k) for q in range(B)], axis=1)
+    (a1,), err = oracle.mex_call(gateways["b2a"], 1, bc[:, 0])
+    assert err is None, err
+    assert np.abs(a1.ravel() - oracle.b2a_m(bc[:, 0])).max() < 1e-11
+    (ab,), err = oracle.mex_call(gateways["b2a"], 1, bc)
+    assert err is None and ab.shape == (n, B)
+    (rf,), err = oracle.mex_call(gateways["ab2rf"], 1, ab, bc)
+    assert err is None and rf.shape == (n, B)
+    for q in range(B):
+        a_ref = oracle.b2a_m(bc[:, q])
+        assert np.abs(ab[:, q] - a_ref).max() < 1e-11
+        assert np.abs(rf[:, q] - oracle.ab2rf_m(a_ref, bc[:, q])).max() < 1e-9
+    h = np.random.default_rng(0).standard_normal(33) * np.exp(-np.arange(33) / 9.0)
+    r = np.correlate(h, h, mode="full"); r[32] *= 1.000001
+    (hm,), err = oracle.mex_call(gateways["fmp2"], 1, r)
+    assert err is None and hm.size == 33
+    assert np.abs(hm.ravel() - fmp2_reference(r)).max() < 1e-10
