@@ -240,7 +240,15 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
         single = {"workload": "cfg3: fir_qp_cvx min-energy multiband FIR, N=256, dual-band H-1 spec, k=120, obj=1, single design",
                   "status": st3, "seconds": time.perf_counter() - t1, "iterations": float(ex3["info"][1]),
                   "objective": float(ex3["info"][2]), "max_violation": float(ex3["info"][4])}
-    roof, fmp = None, None
+    roof, fmp, osearch = None, None, None
+    if rank == 0 and getattr(args, "order_search", False):
+        # BASELINE config 5 shape: fir_ap(..., min_order=1) = bisection over the order with fir_ap_cvx probes (fir_ap.m:143-162),
+        # here from n = 512 on the dual-band H-1 spec (the C-13 bSSFP spec needs the toolbox's spec builders, out of scope);
+        # every round of the search solves its speculative probes concurrently (different orders = different matrices)
+        t4 = time.perf_counter()
+        _, st4, n_op, _ = fir.fir_ap(512, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 1e-3, 1, 0, 0, max_iter=60000)
+        osearch = {"workload": "fir_ap(512, f, a, d, Peak=1e-3, min_order=1): minimal order of the dual-band H-1 spec, orders searched 1..512",
+                   "status": st4, "minimal_order": int(n_op), "seconds": time.perf_counter() - t4}
     if rank == 0:
         roof = solver_roofline(lib, per_gpu)
         # the step after the solve (fir_ap_cvx.m:185-202): x -> minimum-phase taps h = fmp2(r), batched on the GPU
@@ -281,7 +289,7 @@ def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
             "(4 and 8 GPUs) every ~0.1 decade is solved cold and the other designs start from the nearest seed; coarser grids run cold", "solved_on_rank0": solved, "local_designs_rank0": int(info.shape[0]),
             "seconds": sec, "iterations_max": iters, "gpu_launches": int(launches),
             "workload": "cfg4 slice: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, obj x Peak trade-off grid",
-            "single_design": single, "roofline": roof, "fmp2": fmp, "cpu_baseline": cpu, "clocks": clocks,
+            "single_design": single, "roofline": roof, "fmp2": fmp, "cpu_baseline": cpu, "clocks": clocks, "order_search": osearch,
             "tolerances": {"eps_pr": fir.EPS_PR, "eps_gap_rel": fir.EPS_GAP, "eps_dr": fir.EPS_DR},
             "gemm_tflops_useful": flops / sec / 1e12, "iterations_mean": float(info[:, 1].mean()) if info.size else 0.0,
             "note": "fp64 restarted PDHG; the two products of every iteration run on tcgen05 int8 tiles (split-integer, 5 base-256 "
@@ -612,6 +620,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solver", action="store_true", help="skip the FIR-design leg")
     ap.add_argument("--solver-designs", type=int, default=512, help="fir_ap_cvx designs per GPU in the solver leg")
+    ap.add_argument("--order-search", action="store_true",
+                    help="also time the arbitrary-phase order search from n=512 (BASELINE config 5 shape, ~16 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:
