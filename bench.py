@@ -336,8 +336,13 @@ def solver_roofline(lib, per_gpu, nd=5):
     else:
         peak, src = 4500.0, "fallback: nominal dense int8 4.5 POP/s (B200_PROFILING.md: 2 x bf16 2.25 PFLOP/s)"
     ach = 2 * ops / (t * 1e-3) / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "solver_tc_traffic.json"))).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     return {"bound": "tensor", "kernel": "mbrf::tc::tc_i8_gemm_kernel<%d>" % nd, "achieved": ach, "peak": peak, "unit": "TOP/s (int8)",
-            "frac": ach / peak, "traffic": None, "peak_source": src,
+            "frac": ach / peak, "traffic": traffic, "peak_source": src,
             "fp64_equivalent_tflops": 2 * 2.0 * Mp * Np * Bp / (t * 1e-3) / 1e12,
             "kernel_ms": {k: v[0] for k, v in ms.items()}, "with_digit_planes_ms": {k: v[1] for k, v in ms.items()},
             "shape": {"Mp": Mp, "Np": Np, "Bp": Bp, "digit_planes": nd, "split_k": P},

@@ -428,6 +428,7 @@ struct Problem {
     double *gw;                                 //   fir_qp_cvx.m:147,158-160); multipliers live in the l1,2 ball of radius gw_b
     int grow2, ng2;                             // centred group block: row pairs carry  gw2_b * max_i ||(K z)_pair_i - (lo_r, lo_r+1)||
     double *gw2;                                //   (delta of the minimax form, fir_qp_cvx.m:170-177, rows pre-scaled by 1/D_i)
+    int sp_lo, sp_hi;                           // rows outside [sp_lo, sp_hi) are plain interval rows (no block owns them)
     int nn;                                     // norm term: lam_b * ||z[0..nn)||_2 in the objective (E_total, :147,161)
     double *lam;                                // [Bp]
     double *nrm;                                // [4 x Bp] scratch: ||zhat||^2 per design (z-update), metrics sums
@@ -627,8 +628,7 @@ __global__ void __launch_bounds__(256) y_update_wide_kernel(Problem p)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int r = row + u * step;
-            plain[u] = r < p.Mp && !(r >= p.srow0 && r < p.srow0 + p.ns) && !(r >= p.grow0 && r < p.grow0 + 2 * p.ng) &&
-                       !(r >= p.drow0 && r < p.drow0 + 2 * p.nd) && !(r >= p.grow2 && r < p.grow2 + 2 * p.ng2);
+            plain[u] = r < p.Mp && (r < p.sp_lo || r >= p.sp_hi);
             if (plain[u]) {
                 const size_t o = (size_t)r * p.Bp + b;
                 y[u] = p.y[o]; S[u] = p.S[o]; lo[u] = p.lo[o]; hi[u] = p.hi[o]; ys[u] = p.ys[o];
@@ -1544,6 +1544,9 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     p.grow0 = bk.group_pairs > 0 ? bk.group_row0 : 0; p.ng = bk.group_pairs; p.gw = bk.group_pairs > 0 ? bk.group_w : nullptr;
     p.grow2 = bk.group2_pairs > 0 ? bk.group2_row0 : 0; p.ng2 = bk.group2_pairs; p.gw2 = bk.group2_pairs > 0 ? bk.group2_w : nullptr;
     p.nn = bk.norm_coords; p.lam = bk.norm_coords > 0 ? bk.norm_w : nullptr;
+    p.sp_lo = Mp; p.sp_hi = 0;
+    auto own = [&](int r0, int cnt) { if (cnt > 0) { if (r0 < p.sp_lo) p.sp_lo = r0; if (r0 + cnt > p.sp_hi) p.sp_hi = r0 + cnt; } };
+    own(p.srow0, p.ns); own(p.drow0, 2 * p.nd); own(p.grow0, 2 * p.ng); own(p.grow2, 2 * p.ng2);
     p.eps_pr = eps_pr; p.eps_dr = eps_dr; p.eps_gap = eps_gap; p.check_every = check_every;
     const size_t zn = (size_t)Np * Bp, yn = (size_t)Mp * Bp;
     double *w = (double *)workspace;
