@@ -18,11 +18,11 @@ fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], ob
 for rep in range(int(os.environ.get("REPS", "1")) - 1):
     t0 = time.perf_counter()
     fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], objs, peaks, [0.0], rank=rank, world=world,
-                         batch=per_gpu, max_iter=60000, seed_stride=int(os.environ.get('SEED', '0')))
+                         batch=per_gpu, max_iter=60000, seed_stride=(lambda v: v if v == 'auto' else int(v))(os.environ.get('SEED', '0')))
     print(f"world {world} rank {rank} rep {rep}: {time.perf_counter() - t0:.2f} s", flush=True)
 t0 = time.perf_counter()
 r = fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], objs, peaks, [0.0], rank=rank, world=world,
-                         batch=per_gpu, max_iter=60000, seed_stride=int(os.environ.get('SEED', '0')))
+                         batch=per_gpu, max_iter=60000, seed_stride=(lambda v: v if v == 'auto' else int(v))(os.environ.get('SEED', '0')))
 sec = time.perf_counter() - t0
 info = r["info"]
 print(f"world {world} rank {rank}: {sec:.2f} s, solved {(info[:,0]==1).sum()}/{info.shape[0]}, iters mean {info[:,1].mean():.0f} max {info[:,1].max():.0f}", flush=True)
