@@ -559,6 +559,54 @@ __global__ void z_update_kernel(Problem p)
     if (j >= p.Np) return;
     z_update_elem(p, j, b);
 }
+// Thin batches (<= 8 designs): one warp per (coordinate, design); the lanes read the split-K slabs of the gradient (up to 32) in
+// parallel and shuffle-reduce them.  With one thread per item the 25 dependent slab loads made this the longest kernel of a
+// thin iteration (23 us of 34 at one design); the update itself is z_update_elem's.
+__global__ void __launch_bounds__(256) z_update_thin_kernel(Problem p)
+{
+    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (item >= p.Np * p.Bp) return;
+    const int b = item % p.Bp, j = item / p.Bp;
+    const int pr = p.pair_of[j];
+    if (pr >= 0 && p.pair_j[pr] == j) return;      // second member: done by the first
+    const size_t stride = (size_t)p.Np * p.Bp;
+    auto grad = [&](int jj) {
+        double g = 0.0;
+        for (int s = lane; s < p.P; s += 32) g += p.G[s * stride + (size_t)jj * p.Bp + b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        return g + p.c[(size_t)jj * p.Bp + b];
+    };
+    const double tau = p.ctl[b].tau;
+    const size_t o = (size_t)j * p.Bp + b;
+    if (pr < 0) {
+        const double g = grad(j);
+        if (lane) return;
+        const double zo = p.z[o];
+        double zn = zo - tau * g;
+        zn = fmin(fmax(zn, p.bl[o]), p.bu[o]);
+        p.z[o] = zn;
+        p.zbar[o] = 2.0 * zn - zo;
+        p.zs[o] += zn;
+        return;
+    }
+    const int j2 = p.pair_j[pr];
+    const double g1 = grad(j), g2 = grad(j2);
+    if (lane) return;
+    const size_t o2 = (size_t)j2 * p.Bp + b;
+    const double z1 = p.z[o], z2 = p.z[o2];
+    double a = z1 - tau * g1, c2 = z2 - tau * g2;
+    const double r = hypot(a, c2), rho = p.rho[(size_t)pr * p.Bp + b];
+    if (r > rho) {
+        const double sc = rho / r;
+        a *= sc;
+        c2 *= sc;
+    }
+    p.z[o] = a; p.z[o2] = c2;
+    p.zbar[o] = 2.0 * a - z1; p.zbar[o2] = 2.0 * c2 - z2;
+    p.zs[o] += a; p.zs[o2] += c2;
+}
+
 // Batches of >= 64 designs: a CTA owns 64 designs (tx) and strides the coordinates (ty, blockIdx.y), so that the per-design
 // max |zbar| the tcgen05 digit planes need costs one shared-memory reduction and one atomic per design and CTA.
 __global__ void __launch_bounds__(256) z_update_wide_kernel(Problem p)
@@ -1701,6 +1749,9 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             MBRF_LAUNCH_CHECK();
         } else if (wide) {
             z_update_wide_kernel<<<dim3(p.Bp / 64, p.Np / 4 < 128 ? p.Np / 4 : 128), 256, 0, st>>>(p);
+            MBRF_LAUNCH_CHECK();
+        } else if (p.Bp <= 8) {
+            z_update_thin_kernel<<<(unsigned)(((size_t)p.Np * p.Bp * 32 + 255) / 256), 256, 0, st>>>(p);
             MBRF_LAUNCH_CHECK();
         } else {
             z_update_kernel<<<gz, TPB, 0, st>>>(p);
