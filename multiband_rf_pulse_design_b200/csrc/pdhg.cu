@@ -713,11 +713,8 @@ __global__ void __launch_bounds__(256) y_update_wide_kernel(Problem p)
 // Blocks of up to 32*R rows (the stop band of fir_ap_cvx has ~120): one warp per design keeps its rows in registers, so
 // the Michelot passes are shuffles only instead of dependent global re-reads (the general kernel below is latency-bound).
 template <int R>
-__global__ void __launch_bounds__(256) simplex_update_reg_kernel(Problem p)
+__device__ __forceinline__ void simplex_update_reg(const Problem &p, int b, int lane)
 {
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (b >= p.Bp) return;
     const double sig = p.ctl[b].sigma, w = p.sw[b];
     double v[R], ys[R];
     double sum = 0.0;
@@ -772,6 +769,28 @@ __global__ void __launch_bounds__(256) simplex_update_reg_kernel(Problem p)
         for (int k = 16; k > 0; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
         if (lane == 0) atomic_max_pos(p.mxy + b, m);
     }
+}
+template <int R>
+__global__ void __launch_bounds__(256) simplex_update_reg_kernel(Problem p)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= p.Bp) return;
+    simplex_update_reg<R>(p, b, threadIdx.x & 31);
+}
+// Thin batches: the interval rows and the simplex block in ONE launch (they touch disjoint rows): the first `yblocks` CTAs do
+// the flat y update, the following ones the register-resident simplex projection (one warp per design).  One launch and one
+// dependent latency less on the thin iteration's critical path.
+template <int R>
+__global__ void __launch_bounds__(256) y_simplex_thin_kernel(Problem p, int yblocks)
+{
+    if ((int)blockIdx.x < yblocks) {
+        const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx < (long long)p.Mp * p.Bp) y_update_elem(p, (int)(idx / p.Bp), (int)(idx % p.Bp), idx);
+        return;
+    }
+    const int b = (((int)blockIdx.x - yblocks) * blockDim.x + threadIdx.x) >> 5;
+    if (b >= p.Bp) return;
+    simplex_update_reg<R>(p, b, threadIdx.x & 31);
 }
 __global__ void simplex_update_kernel(Problem p)
 
@@ -1758,10 +1777,13 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             MBRF_LAUNCH_CHECK();
         }
         if (int rc = gemm_nn(p, p.zbar, p.S, st, &tcs, p.nn == 0 && wide)) return rc;
+        const bool fused_thin = !wide && p.ns > 0 && p.ns <= 256;
         if (wide) y_update_wide_kernel<<<dim3(p.Bp / 64, 128), 256, 0, st>>>(p);
+        else if (fused_thin && p.ns <= 128) y_simplex_thin_kernel<4><<<gy + (p.Bp * 32 + 255) / 256, 256, 0, st>>>(p, (int)gy);
+        else if (fused_thin) y_simplex_thin_kernel<8><<<gy + (p.Bp * 32 + 255) / 256, 256, 0, st>>>(p, (int)gy);
         else y_update_kernel<<<gy, TPB, 0, st>>>(p);
         MBRF_LAUNCH_CHECK();
-        if (p.ns > 0) {
+        if (p.ns > 0 && !fused_thin) {
             if (p.ns <= 128) simplex_update_reg_kernel<4><<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
             else if (p.ns <= 256) simplex_update_reg_kernel<8><<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
             else simplex_update_kernel<<<(p.Bp * 32 + 255) / 256, 256, 0, st>>>(p);
@@ -1909,7 +1931,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     for (int it = 0; it < max_iter && active > 0 && rcode == MBRF_OK;) {
         if (use_graph) {
             if (cudaGraphLaunch(exec, st) != cudaSuccess) { set_error("pdhg: graph launch failed"); rcode = MBRF_ECUDA; break; }
-            g_launches.fetch_add((4ull + (tcs.on ? 2 : 0) + (p.ns > 0) + (p.ng > 0) + (p.ng2 > 0) + (p.nn > 0)) * check_every, std::memory_order_relaxed);
+            g_launches.fetch_add((4ull + (tcs.on ? 2 : 0) + (p.ns > 0 && !(p.Bp <= 8 && p.ns <= 256)) + (p.ng > 0) + (p.ng2 > 0) + (p.nn > 0)) * check_every, std::memory_order_relaxed);
         } else {
             for (int i = 0; i < check_every && rcode == MBRF_OK; ++i) rcode = iteration(i == 0);
         }
