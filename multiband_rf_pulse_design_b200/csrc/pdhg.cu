@@ -441,6 +441,7 @@ struct Problem {
     double *mxy, *mxz;                          // [Bp] max |y|, max |zbar| per design for the tcgen05 digit planes (or null)
     Ctl *ctl;
     int *active;                                // number of designs still running
+    int *iter_dev;                              // iterations done (advanced by the check block, so the check can live in the graph)
     double eta, eps_pr, eps_dr, eps_gap;
     int check_every;
     double beta_suff, beta_nec, beta_art, omega_theta;   // restart rule constants (PDLP defaults 0.2, 0.8, 0.36, 0.5)
@@ -1140,16 +1141,18 @@ __global__ void col_metrics_kernel(Problem p, int cand)
 __global__ void advance_kernel(Problem p)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *p.iter_dev += p.check_every;
     if (b >= p.Bp) return;
     p.ctl[b].since += p.check_every;
     p.ctl[b].cnt += p.check_every;
 }
 
 // One thread per design: score both candidates, decide convergence / infeasibility / restart.
-__global__ void control_kernel(Problem p, int iter_now, int max_iter)
+__global__ void control_kernel(Problem p, int max_iter)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.Bp) return;
+    const int iter_now = *p.iter_dev;
     Ctl &c = p.ctl[b];
     c.restart = 0.0;
     if (b >= p.B) { c.status = 1.0; return; }     // padding designs
@@ -1625,7 +1628,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     p.acc = w; w += 2 * NACC * (size_t)Bp;
     p.nrm = w; w += 4 * (size_t)Bp;
     p.ctl = (Ctl *)w; w = (double *)((char *)w + (size_t)Bp * sizeof(Ctl));
-    p.active = (int *)w; w += 32;
+    p.active = (int *)w; p.iter_dev = p.active + 1; w += 32;
     int *pair_of = (int *)w;
     p.pair_of = pair_of;
     int *d_slot = pair_of + Np, *d_orig = d_slot + Bp;   // compaction maps
@@ -1801,7 +1804,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         }
         return MBRF_OK;
     };
-    auto check = [&](int iter_now) -> int {
+    auto check = [&]() -> int {
         MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)p.Bp * 8, st));
         advance_kernel<<<(p.Bp + 63) / 64, 64, 0, st>>>(p);
         MBRF_LAUNCH_CHECK();
@@ -1817,7 +1820,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             col_metrics_kernel<<<gm, 64, 0, st>>>(p, cand);
             MBRF_LAUNCH_CHECK();
         }
-        control_kernel<<<(p.Bp + 63) / 64, 64, 0, st>>>(p, iter_now, max_iter);
+        control_kernel<<<(p.Bp + 63) / 64, 64, 0, st>>>(p, max_iter);
         MBRF_LAUNCH_CHECK();
         apply_kernel<<<gz, TPB, 0, st>>>(p, 0);
         MBRF_LAUNCH_CHECK();
@@ -1840,6 +1843,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int rc = MBRF_OK;
             for (int i = 0; i < check_every && rc == MBRF_OK; ++i) rc = iteration(i == 0);
+            if (rc == MBRF_OK) rc = check();   // the convergence check is part of the graph: three API calls per block on the host
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             if (rc != MBRF_OK || e != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) use_graph = false;
         } else {
@@ -1934,9 +1938,9 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             g_launches.fetch_add((4ull + (tcs.on ? 2 : 0) + (p.ns > 0 && !(p.Bp <= 8 && p.ns <= 256)) + (p.ng > 0) + (p.ng2 > 0) + (p.nn > 0)) * check_every, std::memory_order_relaxed);
         } else {
             for (int i = 0; i < check_every && rcode == MBRF_OK; ++i) rcode = iteration(i == 0);
+            if (rcode == MBRF_OK) rcode = check();
         }
         it += check_every;
-        if (rcode == MBRF_OK) rcode = check(it);
         if (rcode != MBRF_OK) break;
         if (cudaMemcpyAsync(&active, p.active, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) { set_error("pdhg: status readback failed: %s", cudaGetErrorString(cudaGetLastError())); rcode = MBRF_ECUDA; break; }
