@@ -1,4 +1,6 @@
 """CPU tests: pin the oracle restatement to the reference's own C and to the golden fixtures."""
+import os
+
 import numpy as np
 import pytest
 
@@ -166,3 +168,21 @@ def test_slr_matches_bloch_without_relaxation(oracle):
     df = -x * (2 * np.pi / n) / (6.283185 * dt)                         # rotz = -df*TWOPI*dt = x*g
     m = oracle.blochsimfz_oracle(b1, None, None, None, dt, 1e30, 1e30, df, np.zeros(1))
     assert np.abs(m[2] - mz_slr).max() < 1e-12
+
+
+@pytest.mark.parametrize("tb,flip", [(2.0, np.pi / 2), (4.0, 0.6), (8.0, 2.5)])
+def test_inverse_slr_restatement_pinned_to_the_reference_c(oracle, tb, flip):
+    """The numpy restatements of rf_tools/b2a.m + ab2rf.m (the oracle of the GPU inverse SLR, tests/test_islr_gpu.py) against
+    the UNMODIFIED reference C pair b2a.code.c + cabc2rf.code.c run through the reference's own b2rf mexFunction
+    (oracle/_ref/libb2rf.so): real beta, n = 256 (the compiled reference overflows its static arrays for n >= 512,
+    b2a.code.c:16-17,33-38).  The .m and .c variants pad differently (x8 vs x16) yet agree to 1e-15."""
+    if not os.path.exists(os.path.join(oracle.REF_DIR, "libb2rf.so")):
+        pytest.skip("oracle/_ref/libb2rf.so not built (needs /root/reference)")
+    n = 256
+    k = np.arange(n) - (n - 1) / 2
+    b = np.sinc(k * tb / n) * np.hamming(n)
+    b = b / np.abs(np.fft.fft(b, 8 * n)).max() * np.sin(flip / 2)
+    rf_c = oracle.b2rf_ref(b)
+    rf_m = oracle.ab2rf_m(oracle.b2a_m(b), b)
+    assert np.abs(rf_m.imag).max() < 1e-15
+    assert np.abs(np.real(rf_c) - rf_m.real).max() < 1e-14
