@@ -59,6 +59,7 @@ SIGNATURES = {
     "mbrf_pdhg_padded_sizes": (_i, [_i, _i, _i, c_int_p, c_int_p, c_int_p]),
     "mbrf_pdhg_set_gemm": (_i, [_i]),
     "mbrf_pdhg_set_tc_digits": (_i, [_i]),
+    "mbrf_pdhg_set_halpern": (_i, [_i]),
     "mbrf_tc_product_device": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mbrf_pdhg_set_option": (_i, [_i, _d]),
     "mbrf_b2a_batch": (_i, [_dp, _dp, _i, _i, _dp, _dp]),

@@ -97,3 +97,25 @@ def test_seeded_sweep_matches_cold_sweep(mbrf):
     assert warm["info"][ok, 4].max() <= 1e-6
     assert warm["info"][ok, 1].sum() < cold["info"][ok, 1].sum()      # fewer iterations in total
     assert np.abs(warm["x"][ok] - cold["x"][ok]).max() < 5e-3         # same design, up to the tolerance of a first-order solve
+
+
+def test_halpern_option_solves_to_the_same_tolerances(mbrf):
+    """mbrf_pdhg_set_halpern(1): the reflected Halpern iteration reaches the same optima (objective within 1e-4) on a small
+    trade-off grid; the option is off by default."""
+    from multiband_rf_pulse_design_b200 import fir
+    lib = mbrf.lib()
+    f = [-0.6, -0.35, -0.2, 0.18, 0.38, 0.6]
+    a = [0.866, 0.866, 0, 0, 0.707, 0.707]
+    d = [0.02, 0.03, 0.025]
+    objs = np.logspace(-2, 0, 8)
+    out = {}
+    try:
+        for mode in (0, 1):
+            assert lib.mbrf_pdhg_set_halpern(mode) == 0
+            out[mode] = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=8, max_iter=40000)["info"]
+    finally:
+        lib.mbrf_pdhg_set_halpern(0)
+    assert np.all(out[0][:, 0] == 1) and np.all(out[1][:, 0] == 1)
+    rel = np.abs(out[0][:, 2] - out[1][:, 2]) / np.abs(out[0][:, 2])
+    assert rel.max() < 1e-4, rel.max()
+    assert out[1][:, 4].max() <= 1e-6
