@@ -247,7 +247,8 @@ int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
 int mbrf_pdhg_set_option(int which, double value);   /* 0 eta factor, 1-3 restart betas, 4 primal-weight smoothing */
 int mbrf_pdhg_set_gemm(int mode);       /* product kernels of the iterations: 2 (default) tcgen05 int8 split-integer tiles,
                                            1 FP64 tensor tiles mma.sync.m8n8k4, 0 SIMT DFMA tiles; checks always run in fp64 */
-int mbrf_pdhg_set_halpern(int on);      /* 1: reflected Halpern PDHG iteration (r2HPDHG), 0: averaged restarts (default) */
+int mbrf_pdhg_set_halpern(int mode);    /* reflected Halpern PDHG iteration (r2HPDHG): 2 (default) on, candidate = better of PDHG output and
+                                           Halpern iterate; 1 on, candidate = PDHG output; 0 off (restarts to running averages) */
 int mbrf_pdhg_set_tc_digits(int nd);    /* base-256 digit planes of the split-integer product: 4, 5 (default) or 6 */
 unsigned long long mbrf_pdhg_workspace_bytes(int Mp, int Np, int Bp);
 /* The tcgen05 split-integer product alone, device pointers: C[nslab][R x Bp] = A[R x kdim] * X[kdim x Bp] over nslab ranges of

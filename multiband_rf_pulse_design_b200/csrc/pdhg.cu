@@ -1205,7 +1205,7 @@ __global__ void control_kernel(Problem p, int max_iter)
         err[k] = fmax(fmax(pr[k], dr[k]), fabs(po[k] - du[k]));
         if (!(err[k] == err[k])) err[k] = DBL_MAX;   // NaN never wins
     }
-    const int k = p.halpern ? 0 : (err[0] < err[1] ? 0 : 1);   // Halpern mode: the PDHG output T(z, y) is the candidate
+    const int k = p.halpern == 1 ? 0 : (err[0] < err[1] ? 0 : 1);   // Halpern mode 1: the PDHG output T(z, y) is the candidate
     c.use_avg = k == 0 ? 1.0 : 0.0;
     if (c.status == 0.0) {
         c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = p.nn > 0 ? -DBL_MAX : fmax(rig[0], rig[1]);
@@ -1311,7 +1311,8 @@ static double g_opt[5] = {0.9, 0.2, 0.8, 0.36, 0.5};   // eta factor, beta_suff,
 // product kernels of the iterations (mbrf_pdhg_set_gemm): 2 = tcgen05 int8 split-integer tiles (tc_gemm.cuh), 1 = FP64
 // tensor path mma.sync m8n8k4, 0 = SIMT DFMA tiles.  The convergence checks always use an fp64 kernel (1 unless 0).
 static int g_gemm_mode = 2;
-static int g_halpern = 0;    // 1: reflected Halpern iteration instead of averaged restarts (mbrf_pdhg_set_halpern)
+static int g_halpern = 2;    // reflected Halpern iteration (mbrf_pdhg_set_halpern): 0 off (averaged restarts), 1 candidate = PDHG output,
+                             // 2 (default) candidate = the better of PDHG output and Halpern iterate
 static int g_tc_digits = 5;  // digit planes / level accumulators of the split-integer product (4..6)
 
 // digit planes, scales and tensor maps of the tcgen05 path (device memory lives in the caller's workspace)
@@ -1460,11 +1461,12 @@ int mbrf_pdhg_set_gemm(int mode)
     g_gemm_mode = mode;
     return MBRF_OK;
 }
-// 1: reflected Halpern PDHG (the iterate is anchored at the restart point, the PDHG output is the candidate), 0: restarts to the
-// better of running average and current iterate
-int mbrf_pdhg_set_halpern(int on)
+// 0: restarts to the better of running average and current iterate; 1: reflected Halpern PDHG, the PDHG output is the candidate;
+// 2 (default): reflected Halpern PDHG, the better of PDHG output and Halpern iterate is the candidate
+int mbrf_pdhg_set_halpern(int mode)
 {
-    g_halpern = on ? 1 : 0;
+    if (mode < 0 || mode > 2) return MBRF_EINVAL;
+    g_halpern = mode;
     return MBRF_OK;
 }
 // digit planes of the split-integer product: 4, 5 (default: ~1e-11 of |row|max * |column|max per term) or 6 (~1e-13)
@@ -1645,7 +1647,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
     p.obj_upper = obj_upper; p.P = split_k(Mp, Np, Bp); p.mxy = p.mxz = nullptr;
     {
         const char *e = getenv("MBRF_HALPERN");     // developer override of mbrf_pdhg_set_halpern
-        p.halpern = e ? (atoi(e) != 0) : g_halpern;
+        p.halpern = e ? atoi(e) : g_halpern;          // 2: Halpern with the better of {PDHG output, Halpern iterate} as candidate
     }
     p.kk = 0;
     p.srow0 = ns > 0 ? srow0 : 0; p.ns = ns; p.sw = ns > 0 ? simplex_w : nullptr;

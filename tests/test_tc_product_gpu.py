@@ -100,8 +100,8 @@ def test_seeded_sweep_matches_cold_sweep(mbrf):
 
 
 def test_halpern_option_solves_to_the_same_tolerances(mbrf):
-    """mbrf_pdhg_set_halpern(1): the reflected Halpern iteration reaches the same optima (objective within 1e-4) on a small
-    trade-off grid; the option is off by default."""
+    """mbrf_pdhg_set_halpern: the reflected Halpern iteration (default, mode 2) and the averaged restarts (mode 0) reach the
+    same optima (objective within 1e-4) on a small trade-off grid."""
     from multiband_rf_pulse_design_b200 import fir
     lib = mbrf.lib()
     f = [-0.6, -0.35, -0.2, 0.18, 0.38, 0.6]
@@ -110,12 +110,13 @@ def test_halpern_option_solves_to_the_same_tolerances(mbrf):
     objs = np.logspace(-2, 0, 8)
     out = {}
     try:
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             assert lib.mbrf_pdhg_set_halpern(mode) == 0
             out[mode] = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=8, max_iter=40000)["info"]
     finally:
-        lib.mbrf_pdhg_set_halpern(0)
-    assert np.all(out[0][:, 0] == 1) and np.all(out[1][:, 0] == 1)
-    rel = np.abs(out[0][:, 2] - out[1][:, 2]) / np.abs(out[0][:, 2])
-    assert rel.max() < 1e-4, rel.max()
-    assert out[1][:, 4].max() <= 1e-6
+        lib.mbrf_pdhg_set_halpern(2)
+    for mode in (1, 2):
+        assert np.all(out[0][:, 0] == 1) and np.all(out[mode][:, 0] == 1)
+        rel = np.abs(out[0][:, 2] - out[mode][:, 2]) / np.abs(out[0][:, 2])
+        assert rel.max() < 1e-4, (mode, rel.max())
+        assert out[mode][:, 4].max() <= 1e-6
