@@ -1762,8 +1762,21 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)Bp * 8, st));
     }
     if (int rc = tc_setup_width()) return rc;
-    p.eta = g_opt[0] / sqrt(knorm2);
-    p.beta_suff = g_opt[1]; p.beta_nec = g_opt[2]; p.beta_art = g_opt[3]; p.omega_theta = g_opt[4];
+    double opt[5];
+    memcpy(opt, g_opt, sizeof opt);
+    if (const char *e = getenv("MBRF_PDHG_OPTS")) {      // developer override of mbrf_pdhg_set_option: "which:value,which:value"
+        while (*e) {
+            char *end = nullptr;
+            const long which = strtol(e, &end, 10);
+            if (end == e || *end != ':') break;
+            const double v = strtod(end + 1, &end);
+            if (which >= 0 && which < 5 && v > 0.0) opt[which] = v;
+            e = *end == ',' ? end + 1 : end;
+            if (*end != ',') break;
+        }
+    }
+    p.eta = opt[0] / sqrt(knorm2);
+    p.beta_suff = opt[1]; p.beta_nec = opt[2]; p.beta_art = opt[3]; p.omega_theta = opt[4];
     {
         std::vector<Ctl> hc((size_t)Bp);
         for (int b = 0; b < Bp; ++b) {
