@@ -244,7 +244,8 @@ int mbrf_pdhg_warm_start_device(const double *z_init, const double *y_init, cons
 /* Device-resident core of the above on a padded batch (Mp, Np, Bp multiples of 64; arrays [dim x Bp]);
  * K row-major [Mp x ldk] with columns already scaled, KT its transpose [Np x Mp]. */
 int mbrf_pdhg_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
-int mbrf_pdhg_set_option(int which, double value);   /* 0 eta factor, 1-3 restart betas, 4 primal-weight smoothing */
+int mbrf_pdhg_set_option(int which, double value);   /* 0 eta factor, 1-3 restart betas, 4 primal-weight smoothing,
+                                                        5 minimum iterations between restarts (default 1: none) */
 int mbrf_pdhg_set_gemm(int mode);       /* product kernels of the iterations: 2 (default) tcgen05 int8 split-integer tiles,
                                            1 FP64 tensor tiles mma.sync.m8n8k4, 0 SIMT DFMA tiles; checks always run in fp64 */
 int mbrf_pdhg_set_halpern(int mode);    /* reflected Halpern PDHG iteration (r2HPDHG): 2 (default) on, candidate = better of PDHG output and

@@ -445,7 +445,7 @@ struct Problem {
     int *iter_dev;                              // iterations done (advanced by the check block, so the check can live in the graph)
     double eta, eps_pr, eps_dr, eps_gap;
     int check_every;
-    double beta_suff, beta_nec, beta_art, omega_theta;   // restart rule constants (PDLP defaults 0.2, 0.8, 0.36, 0.5)
+    double beta_suff, beta_nec, beta_art, omega_theta, min_since;   // restart rule constants (PDLP defaults 0.2, 0.8, 0.36, 0.5)
 };
 
 enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, A_GMAX, A_ZZ, A_ZV, A_VV, A_GMAX2, NACC };
@@ -1222,8 +1222,8 @@ __global__ void control_kernel(Problem p, int max_iter)
     if (c.status != 0.0 && c.restart == 0.0) return;
     // restart rules (PDLP): sufficient decay, necessary decay + no progress, or long since last restart
     const double e = err[k];
-    const bool doit = e <= p.beta_suff * c.last_err || (e <= p.beta_nec * c.last_err && e > c.prev_err) ||
-                      c.since >= p.beta_art * (double)iter_now;
+    const bool doit = (e <= p.beta_suff * c.last_err || (e <= p.beta_nec * c.last_err && e > c.prev_err) ||
+                       c.since >= p.beta_art * (double)iter_now) && c.since >= p.min_since;
     c.prev_err = e;
     if (doit && c.status == 0.0) {
         if (dz[k] > 1e-12 && dy[k] > 1e-12) c.omega = exp(p.omega_theta * log(dy[k] / dz[k]) + (1.0 - p.omega_theta) * log(c.omega));
@@ -1307,7 +1307,7 @@ static inline int up(int v, int a) { return (v + a - 1) / a * a; }
 // batch widths the products support: 1, 2, 4, 8 (matrix-vector pass) or a multiple of 64 (GEMM tiles)
 static inline int batch_width(int b) { return b <= 1 ? 1 : b <= 2 ? 2 : b <= 4 ? 4 : b <= 8 ? 8 : up(b, 64); }
 
-static double g_opt[5] = {0.9, 0.2, 0.8, 0.36, 0.5};   // eta factor, beta_suff, beta_nec, beta_art, omega_theta
+static double g_opt[6] = {0.9, 0.2, 0.8, 0.36, 0.5, 1.0};   // eta factor, beta_suff, beta_nec, beta_art, omega_theta, min restart interval
 // product kernels of the iterations (mbrf_pdhg_set_gemm): 2 = tcgen05 int8 split-integer tiles (tc_gemm.cuh), 1 = FP64
 // tensor path mma.sync m8n8k4, 0 = SIMT DFMA tiles.  The convergence checks always use an fp64 kernel (1 unless 0).
 static int g_gemm_mode = 2;
@@ -1481,7 +1481,7 @@ int mbrf_pdhg_set_tc_digits(int nd)
 // 3 artificial-restart fraction (0.36), 4 primal-weight smoothing (0.5)
 int mbrf_pdhg_set_option(int which, double value)
 {
-    if (which < 0 || which > 4 || !(value > 0.0)) return MBRF_EINVAL;
+    if (which < 0 || which > 5 || !(value > 0.0)) return MBRF_EINVAL;
     g_opt[which] = value;
     return MBRF_OK;
 }
@@ -1762,7 +1762,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
         MBRF_CUDA(cudaMemsetAsync(p.acc, 0, 2 * NACC * (size_t)Bp * 8, st));
     }
     if (int rc = tc_setup_width()) return rc;
-    double opt[5];
+    double opt[6];
     memcpy(opt, g_opt, sizeof opt);
     if (const char *e = getenv("MBRF_PDHG_OPTS")) {      // developer override of mbrf_pdhg_set_option: "which:value,which:value"
         while (*e) {
@@ -1770,13 +1770,13 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
             const long which = strtol(e, &end, 10);
             if (end == e || *end != ':') break;
             const double v = strtod(end + 1, &end);
-            if (which >= 0 && which < 5 && v > 0.0) opt[which] = v;
+            if (which >= 0 && which < 6 && v > 0.0) opt[which] = v;
             e = *end == ',' ? end + 1 : end;
             if (*end != ',') break;
         }
     }
     p.eta = opt[0] / sqrt(knorm2);
-    p.beta_suff = opt[1]; p.beta_nec = opt[2]; p.beta_art = opt[3]; p.omega_theta = opt[4];
+    p.beta_suff = opt[1]; p.beta_nec = opt[2]; p.beta_art = opt[3]; p.omega_theta = opt[4]; p.min_since = opt[5];
     {
         std::vector<Ctl> hc((size_t)Bp);
         for (int b = 0; b < Bp; ++b) {
