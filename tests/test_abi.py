@@ -60,3 +60,18 @@ def test_abrx_argument_errors_match_reference(mbrf):
     # abrx.c:44-45 — same message as the reference's mexErrMsgTxt
     with pytest.raises(ValueError, match="rf and gradient vectors are of different lengths"):
         mbrf.abrx(np.ones(8), np.ones(7), np.zeros(3))
+
+
+def test_solver_option_range(mbrf):
+    # host-side knobs of the PDHG solver (include/mbrf.h): indices 0..5, positive values only; no device needed
+    lib = mbrf.lib()
+    defaults = {0: 0.9, 1: 0.2, 2: 0.8, 3: 0.36, 4: 0.5, 5: 1.0}
+    for which in (-1, 6, 99):
+        assert lib.mbrf_pdhg_set_option(which, 1.0) != 0
+    for bad in (0.0, -1.0, float("nan")):
+        assert lib.mbrf_pdhg_set_option(2, bad) != 0
+    for which in range(6):
+        assert lib.mbrf_pdhg_set_option(which, defaults[which]) == 0
+    for mode in (-1, 3):
+        assert lib.mbrf_pdhg_set_halpern(mode) != 0
+    assert lib.mbrf_pdhg_set_halpern(2) == 0
