@@ -33,6 +33,24 @@ MAX_ITER = 200000
 CHECK_EVERY = 64
 
 
+_OPTION_INDEX = {"eta_factor": 0, "beta_sufficient": 1, "beta_necessary": 2, "beta_artificial": 3, "omega_smoothing": 4,
+                 "min_restart_interval": 5}
+
+
+def set_solver_options(halpern=None, gemm=None, tc_digits=None, **restart):
+    """Process-wide knobs of the PDHG solver (include/mbrf.h: mbrf_pdhg_set_option / _set_halpern / _set_gemm /
+    _set_tc_digits); host state only, no device needed.  restart: eta_factor (step = eta_factor / ||K||), the three constants
+    of the PDLP restart test, omega_smoothing (primal-weight update), min_restart_interval (iterations)."""
+    for name, value in restart.items():
+        if name not in _OPTION_INDEX:
+            raise TypeError(f"unknown solver option {name!r}; known: {sorted(_OPTION_INDEX)}")
+        if lib().mbrf_pdhg_set_option(_OPTION_INDEX[name], float(value)) != 0:
+            raise ValueError(f"solver option {name} must be positive, got {value!r}")
+    for fn, value in (("mbrf_pdhg_set_halpern", halpern), ("mbrf_pdhg_set_gemm", gemm), ("mbrf_pdhg_set_tc_digits", tc_digits)):
+        if value is not None and getattr(lib(), fn)(int(value)) != 0:
+            raise ValueError(f"{fn}: value {value!r} out of range")
+
+
 def _dp(a):
     return a.ctypes.data_as(c_double_p)
 

@@ -102,3 +102,16 @@ def test_seeded_sweep_solves_every_design_once_and_warm_starts_from_the_nearest_
         used = int(x0[k, 0])
         assert used in chain and abs(abs(np.log(objs[used]) - np.log(objs[i])) - dist) < 1e-12      # a nearest seed (ties: either)
         assert y0[k, 0] == 100.0 + used and om[k] == 2.0 + used
+
+
+def test_set_solver_options_names_and_ranges():
+    # host-side knobs only: no device involved.  Values written back are the library defaults.
+    from multiband_rf_pulse_design_b200 import fir
+    fir.set_solver_options(eta_factor=0.9, beta_sufficient=0.2, beta_necessary=0.8, beta_artificial=0.36, omega_smoothing=0.5,
+                           min_restart_interval=1, halpern=2, gemm=2, tc_digits=5)
+    with pytest.raises(TypeError):
+        fir.set_solver_options(beta_nec=0.9)
+    with pytest.raises(ValueError):
+        fir.set_solver_options(min_restart_interval=0)
+    with pytest.raises(ValueError):
+        fir.set_solver_options(tc_digits=9)

@@ -1,6 +1,6 @@
 """CPU prototype (numpy twin of the solver): reflected Halpern PDHG with different restart parameters / restart tests on hard
 (large stop-band weight) designs.  Developer experiment for DESIGN.md 7b item 1; nothing here ships.
-usage: python tools/halpern_restart_variants.py [n]"""
+usage: python tools/halpern_restart_variants.py [n [number of variants to run]]"""
 import sys, time
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,7 +8,7 @@ import numpy as np
 from oracle.fir_problems import build_fir_ap
 from oracle import pdhg_reference as R
 
-def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap=5e-5, crit="kkt", b_suff=0.2, b_nec=0.8, b_art=0.36, omega_theta=0.5):
+def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap=5e-5, crit="kkt", b_suff=0.2, b_nec=0.8, b_art=0.36, omega_theta=0.5, min_since=1):
     K = q["K"]; M, N = K.shape; B = q["c"].shape[1]
     rng = np.random.default_rng(0); v = rng.normal(size=N)
     for _ in range(60):
@@ -58,7 +58,7 @@ def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap
         if (status != 0).all():
             break
         me = fp if crit == "fp" else ce
-        do = (me <= b_suff * last_err) | ((me <= b_nec * last_err) & (me > prev_err)) | (since >= b_art * tot)
+        do = ((me <= b_suff * last_err) | ((me <= b_nec * last_err) & (me > prev_err)) | (since >= b_art * tot)) & (since >= min_since)
         prev_err = me
         if do.any():
             dz = np.linalg.norm(cz - z0, axis=0); dy = np.linalg.norm(cy - y0, axis=0)
@@ -75,7 +75,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 f = [-0.6, -0.35, -0.2, 0.18, 0.38, 0.6]; a = [0.866, 0.866, 0, 0, 0.707, 0.707]; d = [0.02, 0.03, 0.025]
 objs = [1.0, 3.0, 6.0, 10.0, 10.0, 10.0]; peaks = [10**-1.5]*4 + [10**-1.8, 10**-2.0]
 q = R.assemble_fir_ap([build_fir_ap(n, f, a, d, o, pk) for o, pk in zip(objs, peaks)])
-for name, kw in [("kkt default", {}), ("fp criterion", dict(crit="fp")), ("kkt b_art 0.2", dict(b_art=0.2)), ("kkt b_art 0.6", dict(b_art=0.6)),
-                 ("kkt suff 0.1 nec 0.9", dict(b_suff=0.1, b_nec=0.9)), ("kkt check 32", dict(check_every=32)), ("kkt theta 0.2", dict(omega_theta=0.2))]:
+for name, kw in [("kkt default", {}), ("nec 0.9", dict(b_nec=0.9)), ("nec 0.9 min 256", dict(b_nec=0.9, min_since=256)),
+                 ("nec 0.95 min 256", dict(b_nec=0.95, min_since=256)), ("min 256", dict(min_since=256)), ("fp criterion", dict(crit="fp")), ("kkt b_art 0.2", dict(b_art=0.2)), ("kkt b_art 0.6", dict(b_art=0.6)),
+                 ("kkt suff 0.1 nec 0.9", dict(b_suff=0.1, b_nec=0.9)), ("kkt check 32", dict(check_every=32)), ("kkt theta 0.2", dict(omega_theta=0.2))][:int(sys.argv[2]) if len(sys.argv) > 2 else None]:
     t = time.time(); it, st = solve_h(q, **kw)
     print(f"{name:22s}", it, st, f"{time.time()-t:.0f} s", flush=True)
