@@ -8,7 +8,7 @@ import numpy as np
 from oracle.fir_problems import build_fir_ap
 from oracle import pdhg_reference as R
 
-def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap=5e-5, crit="kkt", b_suff=0.2, b_nec=0.8, b_art=0.36, omega_theta=0.5, min_since=1):
+def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap=5e-5, crit="kkt", b_suff=0.2, b_nec=0.8, b_art=0.36, omega_theta=0.5, min_since=1, want_z=False):
     K = q["K"]; M, N = K.shape; B = q["c"].shape[1]
     rng = np.random.default_rng(0); v = rng.normal(size=N)
     for _ in range(60):
@@ -19,6 +19,7 @@ def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap
     z0, y0 = z.copy(), y.copy()
     last_err = np.full(B, np.inf); prev_err = np.full(B, np.inf)
     status = np.zeros(B, int); done = np.zeros(B, int); since = np.zeros(B); tot = 0
+    zsol = np.zeros((N, B))
     s0, ns = q["srow0"], q["ns"]
     def metrics(zz, yy):
         Kz = K @ zz
@@ -54,7 +55,7 @@ def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap
         cz, cy = np.where(use, zh, z), np.where(use, yh, y)
         ce = np.where(use, ea, ec); cp = np.where(use, pa, pc); cr = np.where(use, ra, rc); co = np.where(use, oa, oc); cd = np.where(use, da, dc)
         solved = (cp <= eps_pr) & (cr <= eps_dr) & (np.abs(co - cd) <= eps_gap * np.maximum(np.abs(co), 1e-12)) & (status == 0)
-        status[solved] = 1; done[solved] = it
+        status[solved] = 1; done[solved] = it; zsol[:, solved] = cz[:, solved]
         if (status != 0).all():
             break
         me = fp if crit == "fp" else ce
@@ -69,14 +70,21 @@ def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap
             # the fixed-point residual at the restart point is what later residuals are compared with
             last_err = np.where(do, me, last_err); since = np.where(do, 0.0, since)
     done[status == 0] = tot
+    if want_z:
+        return done, status, zsol
     return done, status
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
-f = [-0.6, -0.35, -0.2, 0.18, 0.38, 0.6]; a = [0.866, 0.866, 0, 0, 0.707, 0.707]; d = [0.02, 0.03, 0.025]
-objs = [1.0, 3.0, 6.0, 10.0, 10.0, 10.0]; peaks = [10**-1.5]*4 + [10**-1.8, 10**-2.0]
-q = R.assemble_fir_ap([build_fir_ap(n, f, a, d, o, pk) for o, pk in zip(objs, peaks)])
-for name, kw in [("kkt default", {}), ("nec 0.9", dict(b_nec=0.9)), ("nec 0.9 min 256", dict(b_nec=0.9, min_since=256)),
-                 ("nec 0.95 min 256", dict(b_nec=0.95, min_since=256)), ("min 256", dict(min_since=256)), ("fp criterion", dict(crit="fp")), ("kkt b_art 0.2", dict(b_art=0.2)), ("kkt b_art 0.6", dict(b_art=0.6)),
-                 ("kkt suff 0.1 nec 0.9", dict(b_suff=0.1, b_nec=0.9)), ("kkt check 32", dict(check_every=32)), ("kkt theta 0.2", dict(omega_theta=0.2))][:int(sys.argv[2]) if len(sys.argv) > 2 else None]:
-    t = time.time(); it, st = solve_h(q, **kw)
-    print(f"{name:22s}", it, st, f"{time.time()-t:.0f} s", flush=True)
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+    f = [-0.6, -0.35, -0.2, 0.18, 0.38, 0.6]; a = [0.866, 0.866, 0, 0, 0.707, 0.707]; d = [0.02, 0.03, 0.025]
+    objs = [1.0, 3.0, 6.0, 10.0, 10.0, 10.0]; peaks = [10**-1.5]*4 + [10**-1.8, 10**-2.0]
+    q = R.assemble_fir_ap([build_fir_ap(n, f, a, d, o, pk) for o, pk in zip(objs, peaks)])
+    for name, kw in [("kkt default", {}), ("nec 0.9", dict(b_nec=0.9)), ("nec 0.9 min 256", dict(b_nec=0.9, min_since=256)),
+                     ("nec 0.95 min 256", dict(b_nec=0.95, min_since=256)), ("min 256", dict(min_since=256)), ("fp criterion", dict(crit="fp")), ("kkt b_art 0.2", dict(b_art=0.2)), ("kkt b_art 0.6", dict(b_art=0.6)),
+                     ("kkt suff 0.1 nec 0.9", dict(b_suff=0.1, b_nec=0.9)), ("kkt check 32", dict(check_every=32)), ("kkt theta 0.2", dict(omega_theta=0.2))][:int(sys.argv[2]) if len(sys.argv) > 2 else None]:
+        t = time.time(); it, st = solve_h(q, **kw)
+        print(f"{name:22s}", it, st, f"{time.time()-t:.0f} s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
