@@ -19,7 +19,7 @@ def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap
     z0, y0 = z.copy(), y.copy()
     last_err = np.full(B, np.inf); prev_err = np.full(B, np.inf)
     status = np.zeros(B, int); done = np.zeros(B, int); since = np.zeros(B); tot = 0
-    zsol = np.zeros((N, B))
+    zsol = np.zeros((N, B)); ysol = np.zeros((M, B))
     s0, ns = q["srow0"], q["ns"]
     def metrics(zz, yy):
         Kz = K @ zz
@@ -55,7 +55,7 @@ def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap
         cz, cy = np.where(use, zh, z), np.where(use, yh, y)
         ce = np.where(use, ea, ec); cp = np.where(use, pa, pc); cr = np.where(use, ra, rc); co = np.where(use, oa, oc); cd = np.where(use, da, dc)
         solved = (cp <= eps_pr) & (cr <= eps_dr) & (np.abs(co - cd) <= eps_gap * np.maximum(np.abs(co), 1e-12)) & (status == 0)
-        status[solved] = 1; done[solved] = it; zsol[:, solved] = cz[:, solved]
+        status[solved] = 1; done[solved] = it; zsol[:, solved] = cz[:, solved]; ysol[:, solved] = cy[:, solved]
         if (status != 0).all():
             break
         me = fp if crit == "fp" else ce
@@ -71,7 +71,7 @@ def solve_h(q, max_iter=80000, check_every=64, eps_pr=8e-7, eps_dr=1e-4, eps_gap
             last_err = np.where(do, me, last_err); since = np.where(do, 0.0, since)
     done[status == 0] = tot
     if want_z:
-        return done, status, zsol
+        return (done, status, zsol, ysol) if want_z == 2 else (done, status, zsol)
     return done, status
 
 def main():
