@@ -265,6 +265,34 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
                            double *z_out, double *y_out, double *info_out,
                            void *workspace, void *stream);
 
+/* ---- convex FIR design step: batched interior-point solver (csrc/ipm.cu) --------------------------------
+ *
+ * Second-order companion of mbrf_fir_pdhg_solve for the SAME problem description (same arrays, same meaning; the
+ * explicit column tcoef/tcol is not supported).  It replaces the solve inside fir_ap_cvx.m:160-169 and ss/fir_linprog.m:246-252
+ * where the reference's own callers need interior-point accuracy: stop-band weights obj = 1e4 / 1e5 (dzrf_mb.m:167-170,
+ * fir_qp.m:47) make the objective lexicographic in all but name, which a first-order method does not resolve to 1e-4.
+ * Homogeneous self-dual embedding, Nesterov-Todd scaling, Mehrotra predictor-corrector; the normal matrix of every design is
+ * assembled from the Toeplitz/Hankel moments of its row weights (one contraction of the shared trigonometric table with the
+ * weight vectors of the batch) and factorised by a batched Cholesky, in double-double once the complementarity gap is small.
+ *   Column frequencies col_kappa must be multiples of 1/2 (all the reference's matrices: fir_ap_cvx.m:100 k = 1..n-1,
+ *   ss/fir_linprog.m:195-217 k or k + 1/2).  bl / bu may be NULL (no bounds); infinite entries mean "no bound".
+ *   feastol (relative primal / dual residual, default 1e-7), reltol (relative gap, default 2e-6), abstol (default 1e-12).
+ *   A design whose last iterations lose feasibility again (fp64 cone scalings at the boundary) ends with its best iterate if that was
+ *   within 10x of the tolerances (CVX's "Inaccurate/Solved", accepted as 'Solved' by fir_ap_cvx.m:176-182).
+ *   info_out [B x 8] as mbrf_fir_pdhg_solve: status 1 optimal, 2 primal infeasible (a Farkas certificate was found),
+ *   3 iteration limit or numerical failure; iterations; objective; dual objective; max violation of the returned point
+ *   (recomputed from it); relative dual residual; dual objective; max_i (K z)_i over the stop block (= ripple_stop).
+ */
+int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const double *col_kappa, const double *col_amp, int N,
+                       const int *pair_i, const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
+                       const double *bl, const double *bu, const double *rho, int B, int simplex_row0, int simplex_rows,
+                       const double *simplex_w, int max_iter, double feastol, double reltol, double abstol, double *z_out,
+                       double *info_out);
+int mbrf_ipm_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
+/* 0: precision of the Newton systems (0 fp64, 1 double-double, 2 auto = double-double once mu < switch * mu0; default 2),
+ * 1: that switch (default 1e-3), 2: refinement steps per solve (default 1), 3: trace the first `value` designs on stderr */
+int mbrf_ipm_set_option(int which, double value);
+
 /* ------------------------------------------------------------------------------------------------
  * Batched minimum-phase spectral factorisation: hmp = fmp2(h) of fir_ap_cvx.m:262-283 (with fftc :253-255 and
  * mag2mp :292-303), the step after the solve in fir_ap_cvx.m:185-202.  B sequences of odd length 2n-1 in, the n taps of

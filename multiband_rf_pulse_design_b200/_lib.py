@@ -76,6 +76,10 @@ SIGNATURES = {
     "mbrf_fir_pdhg_solve2": (_i, [_dp, _dp, _dp, _i, c_int_p, _dp, _dp, _i, _i, c_int_p, c_int_p, _dp,
                                   c_int_p, c_int_p, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _vp,
                                   _i, _i, _d, _d, _d, _dp, _dp, _dp]),
+    "mbrf_fir_ipm_solve": (_i, [_dp, _i, c_int_p, _dp, _dp, _i, c_int_p, c_int_p, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _i, _i,
+                                _dp, _i, _d, _d, _d, _dp, _dp]),
+    "mbrf_ipm_padded_sizes": (_i, [_i, _i, _i, c_int_p, c_int_p, c_int_p]),
+    "mbrf_ipm_set_option": (_i, [_i, _d]),
     "mbrf_fir_pdhg_solve": (_i, [_dp, _dp, _i, c_int_p, _dp, _dp, _i, _i, c_int_p, c_int_p, _i,
                                  _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _i, _i, _dp, _i, _i, _d, _d, _d,
                                  _dp, _dp, _dp]),

@@ -31,6 +31,15 @@ EPS_DR = 1e-4      # natural residual ||z - P_X(z - c - K^T y)||_inf in column-s
 EPS_GAP = 5e-5     # |primal - dual| / |primal|                              (<= 1e-4 required)
 MAX_ITER = 200000
 CHECK_EVERY = 64
+# interior-point solver (csrc/ipm.cu): relative residuals, relative gap, absolute gap, iteration limit
+IPM_FEASTOL = 1e-7
+IPM_RELTOL = 2e-6
+IPM_ABSTOL = 1e-12
+IPM_MAX_ITER = 100
+# which solver the mirrors use: "ipm" (second order, meets the 1e-4 objective tolerance at the reference's own weights
+# obj = 1e4 / 1e5) or "pdhg" (first order); MBRF_FIR_METHOD overrides
+import os as _os
+DEFAULT_METHOD = _os.environ.get("MBRF_FIR_METHOD", "ipm")
 
 
 _OPTION_INDEX = {"eta_factor": 0, "beta_sufficient": 1, "beta_necessary": 2, "beta_artificial": 3, "omega_smoothing": 4,
@@ -128,8 +137,8 @@ def assemble_fir_ap(n, f, a, d, obj, peak, oversamp=15):
     return dict(n=n, w=w, lo=L_b, hi=U_b, stop=stop, obj=float(obj), radius=radius)
 
 
-def _solve_batch_ap(n, designs, max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR,
-                    eps_gap=EPS_GAP, warm=None, want_dual=False):
+def _solve_batch_ap(n, designs, max_iter=None, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR,
+                    eps_gap=EPS_GAP, warm=None, want_dual=False, method=None):
     """Solve designs (assemble_fir_ap dicts with one n) as ONE batch sharing one matrix.
 
     Rows of the shared matrix = union over the batch of the designs' grid points (the base grid is common,
@@ -216,6 +225,18 @@ def _solve_batch_ap(n, designs, max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_
     arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho,
                                                                   upper, sw)]
     w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho, upper, sw = arrs
+    method = method or DEFAULT_METHOD
+    if method == "ipm":
+        if warm is not None or want_dual:
+            raise ValueError("warm starts belong to the first-order solver (method='pdhg')")
+        check(lib().mbrf_fir_ipm_solve(_dp(w_row), M, _ip(col_type), _dp(col_kappa), _dp(col_amp), N, _ip(pair_i), _ip(pair_j),
+                                       n - 1, _dp(c), _dp(lo), _dp(hi), _dp(bl), _dp(bu), _dp(rho), B, M1, int(srows.size),
+                                       _dp(sw), int(max_iter or IPM_MAX_ITER), IPM_FEASTOL, IPM_RELTOL, IPM_ABSTOL, _dp(z),
+                                       _dp(info)))
+        return z.T.copy(), info[:, 7].copy(), info
+    if method != "pdhg":
+        raise ValueError(f"unknown method {method!r}: 'ipm' or 'pdhg'")
+    max_iter = max_iter or MAX_ITER
     keep = []                                   # host arrays the C side reads / writes during the solve
     if warm is not None or want_dual:
         x0, y0, om0 = warm if warm is not None else (None, None, None)
