@@ -871,7 +871,8 @@ assemble_kernel(P p, const T *__restrict__ MC, const T *__restrict__ MS, const T
     const int NV = p.NV, NVp = p.NVp, N = p.N, Bp = p.Bp;
     auto mom = [&](const T *m, int nlag, int lag) {
         T s = m[(size_t)lag * Bp + b];
-        for (int q = 1; q < nsplit; ++q) s = Num<T>::add(s, m[((size_t)q * nlag + lag) * Bp + b]);
+        const int ns_ = m == MC || m == MS ? nsplit : 1;          // the border moments are computed unsplit
+        for (int q = 1; q < ns_; ++q) s = Num<T>::add(s, m[((size_t)q * nlag + lag) * Bp + b]);
         return s;
     };
     for (long long e = (long long)blockIdx.y * blockDim.x + threadIdx.x; e < (long long)NVp * NVp; e += (long long)gridDim.y * blockDim.x) {
@@ -1336,6 +1337,9 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
     for (int r = 0; r < NRHS; ++r) { fill(p.UT[r], Bp, 0.0); fill(p.RHST[r], Bp, 0.0); fill(p.UX[r], (size_t)Np * Bp, 0.0); }
     fill(p.DXV, (size_t)Np * Bp, 0.0);
     fill(p.CU, (size_t)Mp * Bp, 0.0); fill(p.CL, (size_t)Mp * Bp, 0.0);
+    // inputs of the products: the padding rows [M, Mp) are never written again and must be finite (0 * NaN = NaN)
+    for (double *a : {p.YZ, p.YR, p.D, p.DS, p.Y[0], p.Y[1], p.Y[2], p.AX, p.GUX[0], p.GUX[1], p.GUX[2]}) fill(a, (size_t)Mp * Bp, 0.0);
+    for (double *a : {p.KTY, p.KTQ, p.RHS[0], p.RHS[1], p.RHS[2], p.XB}) fill(a, (size_t)Np * Bp, 0.0);
     MBRF_CUDA(cudaMemsetAsync(p.acc, 0, (size_t)NACC * Bp * 8, st));
     init_kernel<<<(Bp + 127) / 128, 128, 0, st>>>(p);
     MBRF_LAUNCH_CHECK();
@@ -1387,8 +1391,11 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
     const size_t sm_trs_dd = (size_t)(NVp + PANEL * (PANEL + 1)) * sizeof(dd), sm_trs_d = (size_t)(NVp + PANEL * (PANEL + 1)) * sizeof(double);
     MBRF_CUDA(cudaFuncSetAttribute(cholesky_kernel<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_dd));
     MBRF_CUDA(cudaFuncSetAttribute(cholesky_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_d));
-    MBRF_CUDA(cudaFuncSetAttribute(trsolve_kernel<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trs_dd));
-    MBRF_CUDA(cudaFuncSetAttribute(trsolve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trs_d));
+    // a constant limit: concurrent host threads (order searches) solve different sizes, and the attribute is per function
+    constexpr int SM_TRS_MAX = 200 * 1024;
+    if (sm_trs_dd > (size_t)SM_TRS_MAX) { set_error("fir_ipm_solve: %d variables exceed the triangular-solve kernel", N); return MBRF_EINVAL; }
+    MBRF_CUDA(cudaFuncSetAttribute(trsolve_kernel<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TRS_MAX));
+    MBRF_CUDA(cudaFuncSetAttribute(trsolve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TRS_MAX));
 
     bool use_dd = g_precision == 1;
     auto factor = [&]() -> int {

@@ -138,7 +138,7 @@ def assemble_fir_ap(n, f, a, d, obj, peak, oversamp=15):
 
 
 def _solve_batch_ap(n, designs, max_iter=None, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR,
-                    eps_gap=EPS_GAP, warm=None, want_dual=False, method=None):
+                    eps_gap=EPS_GAP, warm=None, want_dual=False, method=None, ipm_max_iter=None):
     """Solve designs (assemble_fir_ap dicts with one n) as ONE batch sharing one matrix.
 
     Rows of the shared matrix = union over the batch of the designs' grid points (the base grid is common,
@@ -231,7 +231,7 @@ def _solve_batch_ap(n, designs, max_iter=None, check_every=CHECK_EVERY, eps_pr=E
             raise ValueError("warm starts belong to the first-order solver (method='pdhg')")
         check(lib().mbrf_fir_ipm_solve(_dp(w_row), M, _ip(col_type), _dp(col_kappa), _dp(col_amp), N, _ip(pair_i), _ip(pair_j),
                                        n - 1, _dp(c), _dp(lo), _dp(hi), _dp(bl), _dp(bu), _dp(rho), B, M1, int(srows.size),
-                                       _dp(sw), int(max_iter or IPM_MAX_ITER), IPM_FEASTOL, IPM_RELTOL, IPM_ABSTOL, _dp(z),
+                                       _dp(sw), int(ipm_max_iter or IPM_MAX_ITER), IPM_FEASTOL, IPM_RELTOL, IPM_ABSTOL, _dp(z),
                                        _dp(info)))
         return z.T.copy(), info[:, 7].copy(), info
     if method != "pdhg":
@@ -630,29 +630,41 @@ def _fill_h(x, p):
 def fir_linprog(n, f, a, d, h0=None, dbg=0, return_info=False, **solver_kw):
     """[h, status] = fir_linprog(n, f, a, d, h0, dbg) — ss/fir_linprog.m:2-272.
 
-    The LP `min fmin*x s.t. [A;-A]x <= [U,-L]` (:246-252) is solved on the GPU.  h0 (the reference's warm
-    start for linprog, :157) is accepted and ignored: the first-order solver starts from zero.
-    The redundant box |x_j| <= 2*max|bounds| is added so that the dual bound certifies infeasibility
-    (|H| <= max U on a 15x oversampled grid bounds every Fourier coefficient by it)."""
+    The LP `min fmin*x s.t. [A;-A]x <= [U,-L]` (:246-252) is solved on the GPU, by default with the interior-point
+    solver (method="ipm"; infeasible specifications end with a Farkas certificate -> 'Failed').  h0 is the reference's
+    starting point for linprog's medium-scale algorithm (:157); an interior-point method starts from its own centred point
+    (MATLAB's linprog ignores x0 for its interior-point algorithm too), so h0 does not change the result and is not used.
+    method="pdhg" (first order) adds the redundant box |x_j| <= 2*max|bounds| so that its dual bound certifies
+    infeasibility (|H| <= max U on a 15x oversampled grid bounds every Fourier coefficient by it)."""
     n = int(n)
     p = assemble_fir_linprog(n, f, a, d)
     if p is None:
         return np.zeros(0), "Failed"                                      # :68-72
     M, N = p["w"].size, p["col_type"].size
     c = _lp_objective(p)
-    big = 2.0 * max(np.abs(p["hi"]).max(), np.abs(p["lo"]).max())
     arr = lambda v: np.ascontiguousarray(v, dtype=np.float64)            # noqa: E731
     lo, hi, cc = arr(p["lo"].reshape(M, 1)), arr(p["hi"].reshape(M, 1)), arr(c.reshape(N, 1))
-    bl, bu = arr(np.full((N, 1), -big)), arr(np.full((N, 1), big))
-    upper = arr([p["ntran"] * p["hi"].max() + 1e-9])                      # fmin*x = sum_tran H <= ntran*max U
     z, info = np.zeros((N, 1)), np.zeros((1, 8))
-    kw = dict(max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR, eps_gap=EPS_GAP)
-    kw.update(solver_kw)
     w_row, kap, amp = arr(p["w"]), arr(p["col_kappa"]), arr(p["col_amp"])
-    check(lib().mbrf_fir_pdhg_solve(_dp(w_row), None, M, _ip(p["col_type"]), _dp(kap), _dp(amp), N, -1, None, None, 0,
-                                    _dp(cc), _dp(lo), _dp(hi), _dp(bl), _dp(bu), None, 1, _dp(upper), 0, 0, None,
-                                    int(kw["max_iter"]), int(kw["check_every"]), float(kw["eps_pr"]),
-                                    float(kw["eps_dr"]), float(kw["eps_gap"]), _dp(z), _dp(info), None))
+    method = solver_kw.pop("method", None) or DEFAULT_METHOD
+    ipm_max_iter = solver_kw.pop("ipm_max_iter", None)
+    if method == "ipm":
+        # interior point (csrc/ipm.cu): the LP exactly as posed, no auxiliary box
+        check(lib().mbrf_fir_ipm_solve(_dp(w_row), M, _ip(p["col_type"]), _dp(kap), _dp(amp), N, None, None, 0, _dp(cc), _dp(lo),
+                                       _dp(hi), None, None, None, 1, 0, 0, None, int(ipm_max_iter or IPM_MAX_ITER),
+                                       IPM_FEASTOL, IPM_RELTOL, IPM_ABSTOL, _dp(z), _dp(info)))
+    elif method == "pdhg":
+        big = 2.0 * max(np.abs(p["hi"]).max(), np.abs(p["lo"]).max())
+        bl, bu = arr(np.full((N, 1), -big)), arr(np.full((N, 1), big))
+        upper = arr([p["ntran"] * p["hi"].max() + 1e-9])                  # fmin*x = sum_tran H <= ntran*max U
+        kw = dict(max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR, eps_gap=EPS_GAP)
+        kw.update(solver_kw)
+        check(lib().mbrf_fir_pdhg_solve(_dp(w_row), None, M, _ip(p["col_type"]), _dp(kap), _dp(amp), N, -1, None, None, 0,
+                                        _dp(cc), _dp(lo), _dp(hi), _dp(bl), _dp(bu), None, 1, _dp(upper), 0, 0, None,
+                                        int(kw["max_iter"] or MAX_ITER), int(kw["check_every"]), float(kw["eps_pr"]),
+                                        float(kw["eps_dr"]), float(kw["eps_gap"]), _dp(z), _dp(info), None))
+    else:
+        raise ValueError(f"unknown method {method!r}: 'ipm' or 'pdhg'")
     ok = info[0, 0] == 1.0                                                # exitflag == 1, :265
     h = _fill_h(z[:, 0], p) if ok else np.zeros(0)
     st = "Solved" if ok else "Failed"

@@ -1,4 +1,5 @@
-"""GPU tests of the convex FIR design step (batched restarted PDHG), through the C ABI (mbrf_fir_pdhg_solve).
+"""GPU tests of the convex FIR design step, through the C ABI, on BOTH solvers: the interior-point method
+(mbrf_fir_ipm_solve, the default of the mirrors) and the batched restarted PDHG (mbrf_fir_pdhg_solve).
 
 Tolerances of BASELINE.json's north star: optimal objective within 1e-4 relative of the reference solve,
 constraint violation <= 1e-6.  The reference solve is HiGHS on the restated problem (cone-free LP, and
@@ -15,6 +16,15 @@ pytestmark = pytest.mark.gpu
 KNOWN = json.load(open(os.path.join(GOLDEN, "fir_ap_known.json")))
 TOL_OBJ = 1e-4     # relative
 TOL_VIOL = 1e-6    # absolute, in the problem's own units (|H|^2, |r_k|)
+
+
+@pytest.fixture(params=["ipm", "pdhg"], autouse=True)
+def solver_method(request):
+    """every test of this file runs once per solver (fir_qp_cvx has the first-order solver only)"""
+    from multiband_rf_pulse_design_b200 import fir
+    old, fir.DEFAULT_METHOD = fir.DEFAULT_METHOD, request.param
+    yield request.param
+    fir.DEFAULT_METHOD = old
 
 
 def _solve(mbrf, k, **kw):

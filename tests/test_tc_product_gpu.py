@@ -67,7 +67,7 @@ def test_solver_same_answer_on_both_product_kernels(mbrf):
     try:
         for mode in (1, 2):
             assert lib.mbrf_pdhg_set_gemm(mode) == 0
-            out[mode] = fir.fir_ap_cvx_sweep(48, f, a, d, objs, peaks, [0.0], batch=64, max_iter=40000)["info"]
+            out[mode] = fir.fir_ap_cvx_sweep(48, f, a, d, objs, peaks, [0.0], batch=64, max_iter=40000, method="pdhg")["info"]
     finally:
         lib.mbrf_pdhg_set_gemm(2)
     assert np.array_equal(out[1][:, 0], out[2][:, 0])
@@ -87,8 +87,8 @@ def test_seeded_sweep_matches_cold_sweep(mbrf):
     a = [0.866, 0.866, 0, 0, 0.707, 0.707]
     d = [0.02, 0.03, 0.025]
     objs = np.logspace(-1, 0, 96)              # 0.0105 decades apart -> "auto" picks stride 9
-    cold = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=96, max_iter=40000)
-    warm = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=96, max_iter=40000, seed_stride="auto")
+    cold = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=96, max_iter=40000, method="pdhg")
+    warm = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=96, max_iter=40000, seed_stride="auto", method="pdhg")
     ok = cold["info"][:, 0] == 1
     assert ok.sum() >= 90
     assert np.all(warm["info"][ok, 0] == 1)
@@ -112,7 +112,7 @@ def test_halpern_option_solves_to_the_same_tolerances(mbrf):
     try:
         for mode in (0, 1, 2):
             assert lib.mbrf_pdhg_set_halpern(mode) == 0
-            out[mode] = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=8, max_iter=40000)["info"]
+            out[mode] = fir.fir_ap_cvx_sweep(48, f, a, d, objs, [10 ** -1.5], [0.0], batch=8, max_iter=40000, method="pdhg")["info"]
     finally:
         lib.mbrf_pdhg_set_halpern(2)
     for mode in (1, 2):
