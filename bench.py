@@ -198,159 +198,221 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------
-# solver leg (reported inside the same JSON line under "solver")
+# solver legs (second hot path: "N=256 FIR pulse designs solved/sec"), reported in the same JSON line
 # ----------------------------------------------------------------------------
 H1_DUALBAND = dict(f=[-0.047006, -0.027115, -0.016335, 0.013779, 0.029671, 0.047006],       # SURVEY.md 8(d):
                    a=[0.865905, 0.865905, 0.0, 0.0, 0.706886, 0.706886],                     # specsat_H1_dualband.m:5-32
                    d=[0.014436, 0.022361, 0.017683])                                         # after dzrf_mb's shift_f
 
 
-def solver_leg(args, m, lib, rank, world, max_over_ranks, barrier):
-    """BASELINE config 4 shape: N=256 fir_ap_cvx designs of the dual-band H-1 saturation spec, a slice of the
-    obj x Peak trade-off grid (band edges fixed), `--solver-designs` per GPU, sharded by design instance.
-    One untimed warm-up batch of 64 designs, then ONE timed solve of the whole local share through the public
-    API fir_ap_cvx_sweep (host assembly + H2D + GPU solve + D2H inside the timed region)."""
+def c13_bssfp_spec(B0=14.0, n=200, T=4.0, FA=60.0, d1=0.01, d2=0.005):
+    """The band specification of BASELINE config 5, restated from the reference's input script (benchmark input generation,
+    SURVEY.md 2.3 M6): bSSFP_pulse_lp_ap.m:8-64 (urea selected, 5 bands of 0.1 kHz), spectrum_C13.m:27-41 (chemical shifts at B0),
+    rf_bandedge.m:133-161 (edges = centre -+ range/2, normalised by fs/2), rf_ripple_GFA.m:180-260 ('ex': flip-angle range by
+    asin, |B| = sin(theta/2)), dzrf_mb.m:100-110 (a = mid, d = half-range).  Returns f (normalised to [-1,1]), a, d, dt (ms)."""
+    gam = 10.705e6                                                         # spectrum_C13.m:27
+    cs = np.array([170.60, 182.98, 176.32, 178.91, 160.9, 163.13])         # pyr, lac, ala, pyr-H2O, bicarb, urea (:28-33)
+    f0 = gam * B0 * (1 + cs * 1e-6)
+    fhz = f0 - f0[0]                                                       # :38-40
+    pick = np.array([6, 1, 3, 4, 2]) - 1                                   # bSSFP_pulse_lp_ap.m:29: urea pyr ala pyr-H2O lac
+    cf = fhz[pick]
+    mb_fa = np.array([FA, 0, 0, 0, 0])                                     # :52-55 ('urea')
+    mb_rip = np.array([d1, d2, d2, d2, d2])
+    cf = (cf - cf[0]) * 1e-3                                               # kHz, selected compound on resonance (:55, :64)
+    dt = T / n                                                             # :68-74 (0.02 ms is a multiple of 4 us)
+    fs = 1.0 / dt
+    rng = 0.1                                                              # mb_range, kHz (:30)
+    f = np.empty(10)
+    f[0::2], f[1::2] = cf - rng / 2, cf + rng / 2                          # rf_bandedge.m:133-141
+    assert np.all(np.diff(f) > 0) and f[0] >= -fs / 2 and f[-1] <= fs / 2  # :146-161
+    a, d = np.zeros(10), np.zeros(5)
+    for i in range(5):                                                     # rf_ripple_asin 'ex' + rf_ripple_FA2Beta
+        fa = np.deg2rad(mb_fa[i])
+        if np.sin(fa) + mb_rip[i] >= 1:
+            r = np.arcsin(np.sin(fa) - mb_rip[i]); lo_, hi_ = r, np.pi - r
+        elif fa <= np.pi / 2:
+            lo_, hi_ = np.arcsin(np.sin(fa) - mb_rip[i]), np.arcsin(np.sin(fa) + mb_rip[i])
+        else:
+            hi_, lo_ = np.pi - np.arcsin(np.sin(fa) - mb_rip[i]), np.pi - np.arcsin(np.sin(fa) + mb_rip[i])
+        bmin, bmax = np.sin(lo_ / 2), np.sin(hi_ / 2)
+        a[2 * i] = a[2 * i + 1] = (bmax + bmin) / 2                        # dzrf_mb.m:105-110
+        d[i] = (bmax - bmin) / 2
+    return f / (fs / 2), a, d, dt
+
+
+def leg_cfg4(args, m, lib, rank, world, dev, max_over_ranks, barrier):
+    """BASELINE config 4: the dual-band H-1 saturation trade-off sweep -- 16 obj in logspace(-2,4) x 16 Peak in logspace(-4,-2)
+    x 16 band-edge expansions f_add in linspace(0, 0.9 df_min/2) (fir_ap.m:70-83) = 4096 fir_ap_cvx designs at N = 256, the SAME
+    grid at every GPU count (strong scaling): instance i goes to rank i mod world, every rank solves its share in batches of 512
+    on the interior-point solver, the results (x, ripple_stop, status) are gathered on rank 0.  One timed pass through the
+    public API (host assembly + H2D + solve + D2H + gather inside the timed region)."""
     from multiband_rf_pulse_design_b200 import fir
+    from multiband_rf_pulse_design_b200.shard import gather_sweep
     n = 256
-    per_gpu = args.solver_designs
-    total = per_gpu * world
-    n_obj = max(1, total // 8)                          # 8 Peak values x n_obj weights
-    objs = np.logspace(-2, 1, n_obj)                    # stop-band weight; SURVEY.md 8(d) asks logspace(-2,4): above ~10 the
-                                                        # ripple-dominated objective converges too slowly for a bench leg (DESIGN.md 6)
-    peaks = np.logspace(-3.2, -2, 8)                    # Peak values that keep the spec feasible at N=256
-    fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], objs[:8], peaks, [0.0],
-                         max_iter=512)                  # warm-up: context, buffers, kernels
+    no, npk, nfa = args.solver_grid
+    f = np.array(H1_DUALBAND["f"])
+    df_min = float((f[2:-1:2] - f[1:-2:2]).min())
+    objs, peaks, fadds = np.logspace(-2, 4, no), np.logspace(-4, -2, npk), np.linspace(0.0, 0.9 * df_min / 2, nfa)
+    total = no * npk * nfa
+    fir.fir_ap_cvx_sweep(n, f, H1_DUALBAND["a"], H1_DUALBAND["d"], objs[:2], peaks[-2:], fadds[:2], batch=8, method="ipm")   # warm-up
     barrier()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = lib.mbrf_launch_count()
     t0 = time.perf_counter()
-    r = fir.fir_ap_cvx_sweep(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], objs, peaks, [0.0], rank=rank,
-                             world=world, batch=per_gpu, max_iter=60000, seed_stride="auto")
-    t1s = time.perf_counter()
-    sec = max_over_ranks(t1s - t0)
-    clocks = sampler.stop(t0, t1s) if sampler else None
+    r = fir.fir_ap_cvx_sweep(n, f, H1_DUALBAND["a"], H1_DUALBAND["d"], objs, peaks, fadds, rank=rank, world=world, batch=512,
+                             method="ipm")
+    t_solve = time.perf_counter() - t0
+    full = gather_sweep(r, n, total, device=dev if world > 1 else None)
+    t1 = time.perf_counter()
+    sec = max_over_ranks(t1 - t0)
+    sec_solve = max_over_ranks(t_solve)
+    clocks = sampler.stop(t0, t1) if sampler else None
     launches = lib.mbrf_launch_count() - l0
     barrier()
-    single = None
-    if rank == 0:
-        t1 = time.perf_counter()
-        _, st3, ex3 = fir.fir_qp_cvx(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 120, 1.0, return_info=True)
-        single = {"workload": "cfg3: fir_qp_cvx min-energy multiband FIR, N=256, dual-band H-1 spec, k=120, obj=1, single design",
-                  "status": st3, "seconds": time.perf_counter() - t1, "iterations": float(ex3["info"][1]),
-                  "objective": float(ex3["info"][2]), "max_violation": float(ex3["info"][4])}
-    roof, fmp, osearch = None, None, None
-    if rank == 0 and getattr(args, "order_search", False):
-        # BASELINE config 5 shape: fir_ap(..., min_order=1) = bisection over the order with fir_ap_cvx probes (fir_ap.m:143-162),
-        # here from n = 512 on the dual-band H-1 spec (the C-13 bSSFP spec needs the toolbox's spec builders, out of scope);
-        # every round of the search solves its speculative probes concurrently (different orders = different matrices)
-        t4 = time.perf_counter()
-        _, st4, n_op, _ = fir.fir_ap(512, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 1e-3, 1, 0, 0, max_iter=60000)
-        osearch = {"workload": "fir_ap(512, f, a, d, Peak=1e-3, min_order=1): minimal order of the dual-band H-1 spec, orders searched 1..512",
-                   "status": st4, "minimal_order": int(n_op), "seconds": time.perf_counter() - t4}
-    if rank == 0:
-        roof = solver_roofline(lib, per_gpu)
-        # the step after the solve (fir_ap_cvx.m:185-202): x -> minimum-phase taps h = fmp2(r), batched on the GPU
-        ok = r["info"][:, 0] == 1
-        if ok.any():
-            R = np.stack([fir._x_to_r(x, n) for x in r["x"][ok]])
-            fir.fmp2_batch(R[:8])
-            t2 = time.perf_counter()
-            fir.fmp2_batch(R)
-            dt = time.perf_counter() - t2
-            fmp = {"call": "fmp2_batch -> mbrf_fmp2_batch (one CTA per design, four 4096-point fp64 FFTs in shared memory), host buffers",
-                   "designs": int(ok.sum()), "seconds": dt, "designs_per_s": float(ok.sum() / dt)}
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # CPU baseline of the solver path (SURVEY.md 8d): CVX/SeDuMi/linprog are not installable offline, so the restated
-        # problem of ONE design of this sweep goes to HiGHS (SciPy) on one host core -- the LP without the 2-D Peak cones,
-        # i.e. less work than the reference solve.  Bounded sample: one design (~50 s).
-        from oracle.fir_problems import build_fir_ap, solve_fir_ap_highs
-        o_mid, p_mid = float(objs[len(objs) // 2]), float(peaks[len(peaks) // 2])
-        pr = build_fir_ap(n, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], o_mid, p_mid)
-        t3 = time.perf_counter()
-        res, _ = solve_fir_ap_highs(pr, 0)
-        dt3 = time.perf_counter() - t3
-        cpu = {"value": 1.0 / dt3, "unit": "designs/s", "cores": 1, "kind": "port", "seconds": dt3,
-               "highs_status": int(res.status), "objective": float(res.fun) if res.status == 0 else None,
-               "sample": "1 design of the same sweep (obj=%.3g, Peak=%.3g), N=256, 7686-row grid: HiGHS via scipy.optimize.linprog on "
-                         "the restated LP without the Peak cones (oracle/fir_problems.py); CVX/SeDuMi are not installable offline" % (o_mid, p_mid)}
-    info = r["info"]
-    solved = int((info[:, 0] == 1).sum())
-    iters = float(info[:, 1].max()) if info.size else 0.0
-    # the dominant kernels are the two fp64 GEMMs of every iteration: 2 * 2*Mp*Np*Bp flops per iteration
-    Mp, Np, Bp = C.c_int(), C.c_int(), C.c_int()
-    lib.mbrf_pdhg_padded_sizes(7686 + 118, 2 * n, per_gpu, C.byref(Mp), C.byref(Np), C.byref(Bp))
-    # useful GEMM work: every design pays 2 products of 2*Mp*Np flops per iteration it was still in the batch
-    flops = 4.0 * Mp.value * Np.value * float(info[:, 1].sum()) * world
-    return {"metric": "N=256 FIR pulse designs solved/sec", "value": total / sec, "unit": "designs/s",
-            "designs": total, "designs_per_gpu": per_gpu, "sweep": "seed_stride=auto: where the obj grid is finer than 0.0125 decades "
-            "(4 and 8 GPUs) every ~0.1 decade is solved cold and the other designs start from the nearest seed; coarser grids run cold", "solved_on_rank0": solved, "local_designs_rank0": int(info.shape[0]),
-            "seconds": sec, "iterations_max": iters, "gpu_launches": int(launches),
-            "workload": "cfg4 slice: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, obj x Peak trade-off grid",
-            "single_design": single, "roofline": roof, "fmp2": fmp, "cpu_baseline": cpu, "clocks": clocks, "order_search": osearch,
-            "tolerances": {"eps_pr": fir.EPS_PR, "eps_gap_rel": fir.EPS_GAP, "eps_dr": fir.EPS_DR},
-            "caveat": "the termination test is checked against HiGHS within 1e-4 for stop-band weights <= 1; for the weights > 2.5 of "
-                      "this grid (a quarter of the designs) the numpy twin of the solver ends 2.6e-4 (weight 4) to 6.7e-4 (weight 10) "
-                      "above the HiGHS optimum (DESIGN.md 6, known weak spot)",
-            "gemm_tflops_useful": flops / sec / 1e12, "iterations_mean": float(info[:, 1].mean()) if info.size else 0.0,
-            "note": "fp64 restarted PDHG; the two products of every iteration run on tcgen05 int8 tiles (split-integer, 5 base-256 "
-                    "digit planes, exact int32 level sums in TMEM, ~1e-11 relative), convergence checks on fp64 mma.sync tiles; whole "
-                    "call timed on the host (assembly + PCIe + solve); gemm_tflops_useful = fp64-equivalent 4*Mp*Np*sum_b(iterations_b) "
-                    "/ wall time (rank 0's designs x world)"}
-
-
-def solver_roofline(lib, per_gpu, nd=5):
-    """Roofline of the solver's dominant kernel, tc::tc_i8_gemm_kernel<5>: the two products of one PDHG iteration at the
-    bench shape (K: 7808 x 512, `per_gpu` designs), each timed alone with CUDA events inside libmbrf
-    (mbrf_tc_product_device).  Tensor bound: int8 operations 2*R*k*B per digit-plane product, nd(nd+1)/2 = 15 products."""
-    import torch
-    from multiband_rf_pulse_design_b200._lib import check
-    Mp, Np, Bp = C.c_int(), C.c_int(), C.c_int()
-    lib.mbrf_pdhg_padded_sizes(7686 + 118, 511, per_gpu, C.byref(Mp), C.byref(Np), C.byref(Bp))
-    Mp, Np, Bp = Mp.value, Np.value, Bp.value
-    if Bp < 64:
+    if rank != 0:
         return None
-    g = torch.Generator(device="cuda").manual_seed(0)
-    K = torch.rand((Mp, Np), dtype=torch.float64, device="cuda", generator=g) - 0.5
-    KT = K.t().contiguous()
-    z = torch.rand((Np, Bp), dtype=torch.float64, device="cuda", generator=g) - 0.5
-    y = torch.rand((Mp, Bp), dtype=torch.float64, device="cuda", generator=g) - 0.5
-    tiles = (Np // 64) * ((Bp + 127) // 128)
-    P = max(1, min(32, Mp // 256, (2 * 148) // tiles))          # same split as pdhg.cu:split_k_tc
-    out = torch.empty((max(P, 1), max(Mp, Np), Bp), dtype=torch.float64, device="cuda")
-    ms = {}
-    for name, (A, X, R, kd, ns) in {"K*zbar": (K, z, Mp, Np, 1), "K^T*y": (KT, y, Np, Mp, P)}.items():
-        a, b = C.c_float(), C.c_float()
-        check(lib.mbrf_tc_product_device(A.data_ptr(), R, kd, X.data_ptr(), Bp, nd, ns, out.data_ptr(), 20,
-                                         C.cast(C.byref(a), C.c_void_p), C.cast(C.byref(b), C.c_void_p), None))
-        ms[name] = (a.value, b.value)
-    torch.cuda.synchronize()
-    ops = 2.0 * Mp * Np * Bp * (nd * (nd + 1) // 2)              # int8 multiply-adds x2, per product
-    t = ms["K*zbar"][0] + ms["K^T*y"][0]
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    if "bf16_tflops" in peaks:
-        peak, src = 2.0 * float(peaks["bf16_tflops"]), "2 x MEASURED_PEAKS.json bf16_tflops (int8 issues at twice the bf16 rate; no int8 figure is recorded)"
-    else:
-        peak, src = 4500.0, "fallback: nominal dense int8 4.5 POP/s (B200_PROFILING.md: 2 x bf16 2.25 PFLOP/s)"
-    ach = 2 * ops / (t * 1e-3) / 1e12
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "solver_tc_traffic.json"))).get("dram_bytes_per_launch")
-    except (OSError, ValueError):
-        pass
-    return {"bound": "tensor", "kernel": "mbrf::tc::tc_i8_gemm_kernel<%d>" % nd, "achieved": ach, "peak": peak, "unit": "TOP/s (int8)",
-            "frac": ach / peak, "traffic": traffic, "peak_source": src,
-            "fp64_equivalent_tflops": 2 * 2.0 * Mp * Np * Bp / (t * 1e-3) / 1e12,
-            "kernel_ms": {k: v[0] for k, v in ms.items()}, "with_digit_planes_ms": {k: v[1] for k, v in ms.items()},
-            "shape": {"Mp": Mp, "Np": Np, "Bp": Bp, "digit_planes": nd, "split_k": P},
-            "note": "algorithmic work = 2*Mp*Np*Bp int8 MACs x2 per digit-plane product x 15 products x 2 GEMMs per iteration; the "
-                    "fp64 tensor path this replaced (mma.sync m8n8k4) ran the same two products in 0.139 + 0.148 ms"}
+    info = full["info"]
+    st = info[:, 0]
+    ok = st == 1
+    out = {"metric": "N=256 FIR pulse designs solved/sec", "value": total / sec, "unit": "designs/s", "designs": total,
+           "seconds": sec, "seconds_solve_only": sec_solve, "scaling": "strong",
+           "workload": "cfg4: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, %d obj in logspace(-2,4) x %d Peak in "
+                       "logspace(-4,-2) x %d f_add in linspace(0, 0.9 df_min/2); same grid at every GPU count" % (no, npk, nfa),
+           "method": "interior point (mbrf_fir_ipm_solve): structured normal matrix from Toeplitz/Hankel moments, batched "
+                     "double-double Cholesky", "batch": 512,
+           "status_counts": {"solved": int(ok.sum()), "infeasible_certificate": int((st == 2).sum()),
+                             "iteration_limit": int((st == 3).sum())},
+           "iterations_mean": float(info[:, 1].mean()), "iterations_max": float(info[:, 1].max()),
+           "max_violation_solved": float(info[ok, 4].max()) if ok.any() else None,
+           "max_rel_gap_solved": float((np.abs(info[ok, 2] - info[ok, 3]) / np.maximum(np.abs(info[ok, 2]), 1e-300)).max()) if ok.any() else None,
+           "gpu_launches_rank0": int(launches), "clocks": clocks,
+           "tolerances": {"feastol": fir.IPM_FEASTOL, "reltol": fir.IPM_RELTOL},
+           "note": "most of the grid is infeasible at N = 256 (Peak < ~1e-3, or band edges widened by more than ~0.15 df_min/2): those "
+                   "designs end with a Farkas certificate ('Failed', like CVX's Infeasible); all 4096 are counted in designs/s"}
+    # the step after the solve (fir_ap_cvx.m:185-202): x -> minimum-phase taps h = fmp2(r), batched on the GPU
+    if ok.any():
+        R = np.stack([fir._x_to_r(x, n) for x in full["x"][ok]])
+        fir.fmp2_batch(R[:8])
+        t2 = time.perf_counter()
+        fir.fmp2_batch(R)
+        dt = time.perf_counter() - t2
+        out["fmp2"] = {"designs": int(ok.sum()), "seconds": dt, "designs_per_s": float(ok.sum() / dt)}
+    return out
+
+
+def solver_roofline(lib, tf_peak):
+    """Roofline of the solver's dominant kernel, ipm::cholesky_kernel<dd> (42 % of a sweep, profiles/r2_ipm_launches_summary.txt):
+    the batched double-double Cholesky of the 512 x 512 normal matrices of a 512-design batch, timed alone with CUDA events
+    inside libmbrf.  FP64-pipe bound: algorithmic work = n^3/6 double-double multiply-subtracts per matrix, 15 FP64-pipe
+    instructions each (dd.cuh dd_fnma: 1 DMUL, 3 DFMA, 11 DADD); peak = the DFMA issue rate measured in this run."""
+    from multiband_rf_pulse_design_b200._lib import check
+    nv, B = 512, 512
+    ms = C.c_float()
+    check(lib.mbrf_ipm_cholesky_bench(nv, B, 1, 5, C.byref(ms)))
+    ms64 = C.c_float()
+    check(lib.mbrf_ipm_cholesky_bench(nv, B, 0, 5, C.byref(ms64)))
+    macs = nv ** 3 / 6.0 * B
+    ach = 2.0 * 15.0 * macs / (ms.value * 1e-3) / 1e12          # FP64-pipe instructions counted as 2 flops each, like a DFMA
+    return {"bound": "fp64", "kernel": "mbrf::ipm::cholesky_kernel<dd>", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s (FP64-pipe issue, 2 per instruction)",
+            "frac": ach / tf_peak, "traffic": None, "kernel_ms": ms.value, "shape": {"order": nv, "matrices": B},
+            "algorithmic": "n^3/6 double-double multiply-subtracts per matrix x 15 FP64 instructions",
+            "dd_gflops_equiv": 2.0 * macs / (ms.value * 1e-3) / 1e9, "fp64_variant_ms": ms64.value,
+            "peak_source": "FP64 FMA peak measured in this run (mbrf_measure_fp64_peak)"}
+
+
+def leg_cfg3(m, lib, hbm_peak):
+    """BASELINE config 3: fir_qp_cvx(256, f, a, d, 120, 1e6) (dzrf_mb.m:211-213), one design, on the reference grid
+    (oversamp 10, 2566 points) and on the 4096-point grid (oversamp 16).  Single designs stay on the first-order solver:
+    vectorised matrix-vector passes over K and K^T (no interior-point path for the disk rows of fir_qp_cvx).
+    HBM roofline per SURVEY.md 8(d): 2 * sizeof(K) algorithmic bytes per iteration."""
+    from multiband_rf_pulse_design_b200 import fir
+    out = {}
+    for tag, os_ in (("grid2566", 10), ("grid4096", 16)):
+        t1 = time.perf_counter()
+        _, st3, ex3 = fir.fir_qp_cvx(256, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 120, 1e6, return_info=True,
+                                     oversamp=os_, max_iter=400000)
+        sec = time.perf_counter() - t1
+        mrows = 2 * ex3["problem"]["w"].size + 2 * 256
+        kbytes = 8.0 * mrows * 512
+        it = float(ex3["info"][1])
+        gbs = 2.0 * kbytes * it / sec / 1e9
+        out[tag] = {"status": st3, "seconds": sec, "iterations": it, "objective": float(ex3["info"][2]), "dual_bound": float(ex3["info"][3]),
+                    "max_violation": float(ex3["info"][4]), "rows": int(mrows), "us_per_iteration": sec / max(it, 1) * 1e6,
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "algorithmic_bytes_per_iteration": 2.0 * kbytes,
+                                 "note": "whole call (assembly + solve) / iterations; K and K^T (%.0f MB together) stay in the 126 MB L2" % (2 * kbytes / 1e6)}}
+    out["workload"] = "cfg3: fir_qp_cvx min-energy/min-peak multiband FIR, N=256, dual-band H-1 spec, k=120, obj=1e6, single design"
+    return out
+
+
+def leg_cfg5(m, lib, rank, world, allgather_obj, barrier):
+    """BASELINE config 5: C-13 bSSFP duration search at 14 T -- the minimal order of the arbitrary-phase design
+    fir_ap(512, f, a, d, Peak=1e-3, min_order=1) (fir_ap.m:143-166, reached from dzrf_mb 'ap_minorder_cvx') and of the
+    linear-phase design fir_min_order_linprog(512, ...) (ss/fir_min_order_linprog.m), on the spec of bSSFP_pulse_lp_ap.m.
+    The arbitrary-phase search probes the next three levels of the reference's bisection tree at once (different orders =
+    different matrices); the probes of a round are spread over the GPUs, the tree is walked with the reference's decisions."""
+    from multiband_rf_pulse_design_b200 import fir
+    f, a, d, dt = c13_bssfp_spec()
+    lam, peak, n_top = 0.1, 1e-3, 512
+
+    def step(st, solved):                                                  # fir_ap.m:143-162
+        bot, top, mid = st
+        if solved:
+            top = mid
+        else:
+            bot = mid
+        return (bot, top, int(np.ceil((top + bot) / 2)) if top - bot > 1 else None)
+
+    barrier()
+    t0 = time.perf_counter()
+    cache, probes, rounds = {}, 0, 0
+    state = (2, n_top, int(np.ceil((n_top + 2) / 2)))
+    first = True
+    while state[2] is not None or first:
+        need = ([n_top] if first else []) + [q for q in fir._speculate(state, step, 3) if q not in cache]
+        first = False
+        mine = need[rank::world]
+        res = fir._solve_concurrently([(lambda q=q: fir.fir_ap_cvx(q, f, a, d, lam, peak, method="ipm")[1]) for q in mine])
+        merged = {}
+        for part in allgather_obj(dict(zip(mine, res))):
+            merged.update(part)
+        cache.update(merged)
+        probes += len(need)
+        rounds += 1
+        if cache.get(n_top) == "Failed":
+            break                                                          # "original parameters are too tight", fir_ap.m:52-54
+        for _ in range(3):
+            if state[2] is None:
+                break
+            state = step(state, cache[state[2]] != "Failed")
+    sec = time.perf_counter() - t0
+    out = None
+    if rank == 0:
+        out = {"workload": "cfg5: C-13 bSSFP spec at 14 T (bSSFP_pulse_lp_ap.m), order search of fir_ap(512, f, a, d, Peak=1e-3, min_order=1)",
+               "minimal_order_arbitrary_phase": int(state[1]), "probes_solved": probes, "rounds": rounds, "seconds": sec,
+               "instances_per_s": probes / sec, "duration_ms": float(state[1] * dt), "gpus": world}
+        t1 = time.perf_counter()
+        h, st = fir.fir_min_order_linprog(512, f, a, d, 0, 0, method="ipm")
+        out["linear_phase"] = {"call": "fir_min_order_linprog(512, f, a, d)", "status": st, "taps": int(len(h)), "seconds": time.perf_counter() - t1,
+                               "duration_ms": float(len(h) * dt)}
+    barrier()
+    return out
+
+
+def solver_cpu_baseline():
+    """CPU baseline of the solver path: CVX/SeDuMi/linprog are not installable offline, so the restated problem
+    of ONE design of the sweep goes to HiGHS (SciPy) on one host core -- the LP without the 2-D Peak cones.  Bounded sample."""
+    from oracle.fir_problems import build_fir_ap, solve_fir_ap_highs
+    pr = build_fir_ap(256, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 0.1, 1e-2)
+    t3 = time.perf_counter()
+    res, _ = solve_fir_ap_highs(pr, 0)
+    dt3 = time.perf_counter() - t3
+    return {"value": 1.0 / dt3, "unit": "designs/s", "cores": 1, "kind": "port", "seconds": dt3, "highs_status": int(res.status),
+            "objective": float(res.fun) if res.status == 0 else None,
+            "sample": "1 design of the sweep (obj=0.1, cones dropped), N=256, 7686-row grid: HiGHS via scipy.optimize.linprog on the "
+                      "restated LP (oracle/fir_problems.py); obj=1e4 / 1e5 take 400 / 760 s (tests/golden/fir_ap_weights_known.json)"}
 
 
 # ----------------------------------------------------------------------------
@@ -373,8 +435,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib = m.lib()
     check(lib.mbrf_set_device(local))
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")     # host-side barriers that leave the GPUs idle (an NCCL barrier spins on them)
 
     wl = make_workload(world)
     nt = wl["b1"].size
@@ -415,6 +479,18 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
+    def allgather_obj(o):
+        if world == 1:
+            return [o]
+        outl = [None] * world
+        dist.all_gather_object(outl, o, group=cpu_group)
+        return outl
+
     # ---- device-resident leg ---------------------------------------------------------------
     full = None
     for _ in range(args.warmup):
@@ -452,8 +528,10 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     launches = lib.mbrf_launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    ms_dev = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    ms_dev = sum(per_step) / args.steps
     ms_dev = max_over_ranks(ms_dev)
+    ms_dev_min, ms_dev_med = max_over_ranks(min(per_step)), max_over_ranks(statistics.median(per_step))
     value = world * steps_per_gpu / (ms_dev * 1e-3)
 
     # dominant kernel alone (prep + spin kernel, no gather) for the roofline, same stream, L2 flushed
@@ -470,68 +548,89 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / args.steps
 
-    # ---- end-to-end leg: the reference-facing call on pinned host buffers --------------------
-    h_out = [torch.empty(nlocal, dtype=torch.float64).pin_memory() for _ in range(3)]
-    h_out_np = tuple(t.numpy() for t in h_out)
-    h_b1 = wl["b1"].reshape(-1, 1)
-    h_gr = wl["gx"].reshape(-1, 1)
-    h_df = np.ascontiguousarray(wl["df"][rank * NF_PER_GPU:(rank + 1) * NF_PER_GPU]).reshape(-1, 1)
-    h_dp = wl["dx"].reshape(-1, 1)
-    h2d = 8 * (2 * nt + nt + nt + h_df.size + h_dp.size)   # b1 re/im, gradient, time steps, df, dp
-    d2h = 3 * 8 * nlocal
+    # ---- end-to-end leg: ONE reference-facing call for the whole job, host buffers ------------------
+    # What a MEX gateway does: blochC(b1,gr,tp,t1,t2,df,dp,mode) -> mbrf_bloch on rank 0, the result arrays freshly allocated
+    # PAGEABLE memory (mxCreateDoubleMatrix), all `world` GPUs used inside the call (mbrf_set_fanout: contiguous spin ranges,
+    # each device DMA-ing its slice into a pinned ring, host threads copying it out).  The other ranks idle at a host barrier.
+    e2e = None
+    host_barrier()
+    if rank == 0:
+        h_b1 = wl["b1"].reshape(-1, 1)
+        h_gr = wl["gx"].reshape(-1, 1)
+        h_df = np.ascontiguousarray(wl["df"]).reshape(-1, 1)          # all world * 1000 off-resonances
+        h_dp = wl["dx"].reshape(-1, 1)
+        ntot = nf * npos
+        h2d = 8 * (2 * nt + nt + nt + h_df.size + h_dp.size) * world   # the small inputs go to every device
+        d2h = 3 * 8 * ntot
+        check(lib.mbrf_set_fanout(world))
+        res = {}
+        pin = tuple(torch.empty(ntot, dtype=torch.float64).pin_memory().numpy() for _ in range(3))
+        for kind in ("pageable", "pinned"):
+            def step_e2e():
+                return m.blochC(h_b1, h_gr, wl["dt"], wl["t1"], wl["t2"], h_df, h_dp, 0, out=pin if kind == "pinned" else None)
+            for _ in range(max(3, args.warmup)):
+                last = step_e2e()
+            ts = []
+            for _ in range(args.steps):
+                t0 = time.perf_counter()
+                last = step_e2e()                            # synchronous: returns with the result in host memory
+                ts.append(time.perf_counter() - t0)
+            res[kind] = (sum(ts) / len(ts) * 1e3, min(ts) * 1e3, statistics.median(ts) * 1e3, last)
+        check(lib.mbrf_set_fanout(1))
+        # the e2e result must be the same numbers as the device-resident leg (rank 0's shard is the first nlocal spins)
+        chk = float(np.abs(res["pageable"][3][2].ravel(order="F")[:4096] - out[2][:4096].cpu().numpy()).max())
+        ms_e2e = res["pageable"][0]
+        e2e = {"value": world * steps_per_gpu / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e2e, "ms_min": res["pageable"][1], "ms_median": res["pageable"][2],
+               "call": "ONE blochC(b1,gr,tp,t1,t2,df,dp,0) -> mbrf_bloch (C ABI) for all %d spins, result in freshly allocated PAGEABLE "
+                       "arrays (what mxCreateDoubleMatrix gives a MEX gateway), fan-out over %d GPU(s) inside the call" % (ntot, world),
+               "check_vs_device_leg": chk,
+               "pinned_result_arrays": {"value": world * steps_per_gpu / (res["pinned"][0] * 1e-3), "ms_per_step": res["pinned"][0],
+                                        "ms_min": res["pinned"][1], "note": "same call with page-locked result arrays (a C / Python host can "
+                                        "supply them, MATLAB cannot): one GPU stores straight into them, several DMA their slices"}}
+        del pin, res
+    host_barrier()
 
-    def step_e2e():
-        m.blochC(h_b1, h_gr, wl["dt"], wl["t1"], wl["t2"], h_df, h_dp, 0, out=h_out_np)
+    # ---- forward SLR (abrx) on the same pulse: 10^6 positions per GPU x 512 samples, device-resident, sharded by
+    # contiguous position range (abrx.c:67-78) with the alpha/beta planes gathered on rank 0 like the Bloch planes ----------
+    from multiband_rf_pulse_design_b200.shard import abr_sharded
+    rf = np.load(os.path.join(ROOT, "tests", "golden", "pulses.npz"))["rf512_rad"] \
+        if os.path.exists(os.path.join(ROOT, "tests", "golden", "pulses.npz")) else wl["b1"] * (2 * np.pi * 1.0705 * wl["dt"] * 1e3)
+    ns, nx_local = rf.size, 1_000_000
+    nx = nx_local * world
+    d_rfr, d_rfi = T(rf.real), T(rf.imag)
+    d_g, d_x = T(np.full(ns, 2 * np.pi / ns)), T(np.linspace(-40, 40, nx))
+    ab = torch.empty((4, nx_local), dtype=torch.float64, device=dev)
+    ws2 = torch.empty(int(lib.mbrf_abr_workspace_bytes(ns)), dtype=torch.uint8, device=dev)
+    slr_args = dict(rfr=d_rfr.data_ptr(), rfi=d_rfi.data_ptr(), gx=d_g.data_ptr(), gy=None, ns=ns, x=d_x.data_ptr(), nx=nx, y=None, ny=1)
 
-    for _ in range(args.warmup):
-        step_e2e()
+    def step_slr():
+        return abr_sharded(lib, slr_args, nx, ab, ws2.data_ptr(), stream, 0, chunks=[0.85, 0.15])
+    for _ in range(3):
+        full_ab = step_slr()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()                                   # synchronous: returns with the result in host memory
-    torch.cuda.synchronize()
-    ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
-    ms_e2e = max_over_ranks(ms_e2e)
+    reps = 20
+    sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for k in range(reps):
+        flush.zero_()
+        sev[k][0].record(stream)
+        full_ab = step_slr()
+        sev[k][1].record(stream)
     barrier()
-    e2e_value = world * steps_per_gpu / (ms_e2e * 1e-3)
-    # the e2e result must be the same numbers as the device-resident leg
-    chk = float(np.abs(h_out_np[2][:4096] - out[2][:4096].cpu().numpy()).max())
-
-    # ---- forward SLR (abrx) on the same pulse: 10^6 positions x 512 samples, device-resident -------------
+    ms_slr = max_over_ranks(sum(a.elapsed_time(b) for a, b in sev) / reps)
     slr = None
     if rank == 0:
-        rf = np.load(os.path.join(ROOT, "tests", "golden", "pulses.npz"))["rf512_rad"] \
-            if os.path.exists(os.path.join(ROOT, "tests", "golden", "pulses.npz")) else wl["b1"] * (2 * np.pi * 1.0705 * wl["dt"] * 1e3)
-        ns, nx = rf.size, 1_000_000
-        d_rfr, d_rfi = T(rf.real), T(rf.imag)
-        d_g, d_x = T(np.full(ns, 2 * np.pi / ns)), T(np.linspace(-40, 40, nx))
-        ab = torch.empty((4, nx), dtype=torch.float64, device=dev)
-        ws2 = torch.empty(int(lib.mbrf_abr_workspace_bytes(ns)), dtype=torch.uint8, device=dev)
-
-        def step_slr():
-            check(lib.mbrf_abr_device(d_rfr.data_ptr(), d_rfi.data_ptr(), d_g.data_ptr(), None, ns, d_x.data_ptr(), nx,
-                                      None, 1, 0, 0, nx, ab[0].data_ptr(), ab[1].data_ptr(), ab[2].data_ptr(),
-                                      ab[3].data_ptr(), ws2.data_ptr(), stream.cuda_stream))
-        for _ in range(3):
-            step_slr()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        e0.record(stream)
-        for _ in range(reps):
-            step_slr()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms_slr = e0.elapsed_time(e1) / reps
-        unit = float((ab[0] ** 2 + ab[1] ** 2 + ab[2] ** 2 + ab[3] ** 2 - 1).abs().max().item())
+        unit = float((full_ab[0] ** 2 + full_ab[1] ** 2 + full_ab[2] ** 2 + full_ab[3] ** 2 - 1).abs().max().item())
         slr = {"metric": "SLR position-steps/sec", "value": nx * ns / (ms_slr * 1e-3), "unit": "position-steps/s",
-               "ms_per_call": ms_slr, "positions": nx, "samples": ns, "unitarity_max_err": unit,
-               "flops_per_position_step": 50, "call": "mbrf_abr_device (abrx convention), device-resident"}
+               "ms_per_call": ms_slr, "positions": nx, "samples": ns, "unitarity_max_err": unit, "n_gpus": world,
+               "flops_per_position_step": 50, "call": "mbrf_abr_device (abrx convention) per rank + gather of alpha/beta on rank 0, device-resident"}
+    full_ab = None
 
     # ---- second hot path: convex FIR design step (BASELINE metric "N=256 FIR pulse designs solved/sec") --------
-    solver = None
+    solver = cfg5 = None
     if not args.no_solver:
-        solver = solver_leg(args, m, lib, rank, world, max_over_ranks, barrier)
+        solver = leg_cfg4(args, m, lib, rank, world, dev, max_over_ranks, barrier)
+        cfg5 = leg_cfg5(m, lib, rank, world, allgather_obj, host_barrier)
 
     if rank != 0:
         if world > 1:
@@ -572,8 +671,14 @@ def run_ours(args):
     }
 
     if slr:
-        slr["roofline"] = {"bound": "fp64", "achieved": slr["value"] * 50 / 1e12, "peak": tf.value, "unit": "TFLOP/s",
-                           "frac": slr["value"] * 50 / 1e12 / tf.value}
+        slr["roofline"] = {"bound": "fp64", "achieved": slr["value"] * 50 / 1e12 / world, "peak": tf.value, "unit": "TFLOP/s per GPU",
+                           "frac": slr["value"] * 50 / 1e12 / world / tf.value}
+    if solver is not None:
+        solver["roofline"] = solver_roofline(lib, tf.value)
+        solver["single_design"] = leg_cfg3(m, lib, hbm_peak)
+        solver["order_search"] = cfg5
+        if world == 1 and not args.no_cpu_baseline:
+            solver["cpu_baseline"] = solver_cpu_baseline()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
     cpu = None
@@ -587,20 +692,26 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_dev, "ms_per_step_min": ms_dev_min, "ms_per_step_median": ms_dev_med,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "pulse": wl["src"], "spins_per_gpu": nlocal, "ntime": nt,
-                   "sharding": f"contiguous spin ranges over {world} GPU(s), one NCCL gather to rank 0 per step"
+                   "sharding": f"contiguous spin ranges over {world} GPU(s), one gather per step: batched NCCL send/recv straight into rank 0's preallocated [3, S] result"
                    if world > 1 else "single GPU", "l2": "flushed between timed iterations (256 MiB memset)", "gather_check_max_abs": gather_check},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e, "call": "blochC(b1,gr,tp,t1,t2,df,dp,0) -> mbrf_bloch (C ABI), pinned host buffers",
-                "check_vs_device_leg": chk},
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "solver": solver,
+        # short top-level copies of the second hot path's headline numbers (the full objects follow)
+        "solver_designs_per_s": solver["value"] if solver else None,
+        "solver_roofline_frac": solver["roofline"]["frac"] if solver else None,
+        "solver_cfg3_seconds": solver["single_design"]["grid4096"]["seconds"] if solver else None,
+        "solver_cfg3_hbm_frac": solver["single_design"]["grid4096"]["roofline"]["frac"] if solver else None,
+        "solver_cfg5_seconds": solver["order_search"]["seconds"] if solver and solver.get("order_search") else None,
+        "slr_position_steps_per_s": slr["value"] if slr else None,
         "slr": slr,
+        "solver": solver,
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
@@ -627,9 +738,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solver", action="store_true", help="skip the FIR-design leg")
-    ap.add_argument("--solver-designs", type=int, default=512, help="fir_ap_cvx designs per GPU in the solver leg")
-    ap.add_argument("--order-search", action="store_true",
-                    help="also time the arbitrary-phase order search from n=512 (BASELINE config 5 shape, ~16 s)")
+    ap.add_argument("--solver-grid", type=lambda v: tuple(int(x) for x in v.split(",")), default=(16, 16, 16),
+                    help="cfg4 sweep: numbers of obj, Peak and f_add values (default 16,16,16 = 4096 designs, BASELINE config 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:

@@ -44,6 +44,11 @@ int  mbrf_device_count(void);             /* >= 0, never fails */
 int  mbrf_set_device(int device);         /* device used by this host thread's later calls */
 int  mbrf_get_device(int *device);        /* the calling host thread's current device (worker threads inherit nothing) */
 int  mbrf_device_sm_count(int *sm_count); /* multiprocessors of the current device */
+/* Host-pointer entry points (mbrf_bloch, mbrf_blochsimfz, mbrf_abr) spread one call over `ndevices` GPUs of the box: contiguous
+ * spin / position ranges, one per device, results written into the caller's arrays (no collective).  0 = all devices; default 1,
+ * or the environment variable MBRF_FANOUT.  A MATLAB host is one process: this is how it uses more than one GPU. */
+int  mbrf_set_fanout(int ndevices);
+int  mbrf_get_fanout(void);
 /* counts kernel launches made by this library on the calling process (for bench `gpu_launches`) */
 unsigned long long mbrf_launch_count(void);
 
@@ -292,6 +297,9 @@ int mbrf_ipm_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
 /* 0: precision of the Newton systems (0 fp64, 1 double-double, 2 auto = double-double once mu < switch * mu0; default 2),
  * 1: that switch (default 1e-3), 2: refinement steps per solve (default 1), 3: trace the first `value` designs on stderr */
 int mbrf_ipm_set_option(int which, double value);
+/* Diagnostic: the batched Cholesky of the interior-point solver alone -- B matrices of order nv, double-double (use_dd) or
+ * fp64, timed with CUDA events over `reps` launches (mean ms per launch): the kernel bench.py's solver roofline is quoted on. */
+int mbrf_ipm_cholesky_bench(int nv, int B, int use_dd, int reps, float *ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched minimum-phase spectral factorisation: hmp = fmp2(h) of fir_ap_cvx.m:262-283 (with fftc :253-255 and

@@ -40,6 +40,8 @@ SIGNATURES = {
     "mbrf_set_device": (_i, [_i]),
     "mbrf_get_device": (_i, [c_int_p]),
     "mbrf_device_sm_count": (_i, [c_int_p]),
+    "mbrf_set_fanout": (_i, [_i]),
+    "mbrf_get_fanout": (_i, []),
     "mbrf_launch_count": (C.c_ulonglong, []),
     "mbrf_measure_fp64_peak": (_i, [c_double_p, c_double_p]),
     "mbrf_blochsimfz": (_i, [_dp, _dp, _dp, _dp, _dp, _dp, _i, _d, _d, _dp, _i, _dp, _dp, _dp, _i,
@@ -80,6 +82,7 @@ SIGNATURES = {
                                 _dp, _i, _d, _d, _d, _dp, _dp]),
     "mbrf_ipm_padded_sizes": (_i, [_i, _i, _i, c_int_p, c_int_p, c_int_p]),
     "mbrf_ipm_set_option": (_i, [_i, _d]),
+    "mbrf_ipm_cholesky_bench": (_i, [_i, _i, _i, _i, C.POINTER(C.c_float)]),
     "mbrf_fir_pdhg_solve": (_i, [_dp, _dp, _i, c_int_p, _dp, _dp, _i, _i, c_int_p, c_int_p, _i,
                                  _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _i, _i, _dp, _i, _i, _d, _d, _d,
                                  _dp, _dp, _dp]),

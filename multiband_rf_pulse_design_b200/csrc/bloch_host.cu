@@ -3,6 +3,7 @@
 // blochC.c:514-927).  They stage inputs through one pinned buffer, run the device path
 // of bloch.cu and bring the result back; there is no CPU computation of the physics.
 #include "common.h"
+#include "hostpipe.h"
 
 #include <cstdio>
 #include <cstring>
@@ -10,40 +11,6 @@
 
 namespace mbrf {
 namespace bloch {
-
-struct HostCtx {
-    DeviceScratch dev;
-    void *pinned = nullptr;
-    size_t pinned_bytes = 0;
-    cudaStream_t stream = nullptr;
-    int stream_device = -1;
-    ~HostCtx()
-    {
-        if (pinned) cudaFreeHost(pinned);
-        // streams die with the context
-    }
-    int reserve_pinned(size_t need)
-    {
-        if (pinned && pinned_bytes >= need) return MBRF_OK;
-        if (pinned) { cudaFreeHost(pinned); pinned = nullptr; pinned_bytes = 0; }
-        size_t want = need + need / 4 + 4096;
-        MBRF_CUDA(cudaMallocHost(&pinned, want));
-        pinned_bytes = want;
-        return MBRF_OK;
-    }
-    int get_stream(cudaStream_t *out)
-    {
-        int dev = 0;
-        MBRF_CUDA(cudaGetDevice(&dev));
-        if (!stream || stream_device != dev) {
-            MBRF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-            stream_device = dev;
-        }
-        *out = stream;
-        return MBRF_OK;
-    }
-};
-static thread_local HostCtx t_ctx;
 
 static bool all_zero(const double *v, long long n)
 {
@@ -53,18 +20,12 @@ static bool all_zero(const double *v, long long n)
     return true;
 }
 
-// If `p` is page-locked host memory the GPU can address, return its device alias, else NULL.
-static double *device_alias_if_pinned(double *p)
-{
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (at.type == cudaMemoryTypeHost && at.devicePointer) return (double *)at.devicePointer;
-    return nullptr;
-}
-
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // m0*: host, element i at [i*m0_stride], or all NULL for (0,0,1).  Outputs: host, [t + ntout*s].
+// The spins are spread over mbrf_set_fanout() devices and pipelined in chunks (hostpipe.h): pageable result arrays -- what
+// mxCreateDoubleMatrix hands a MEX gateway -- are filled from a pinned ring by host threads while the GPUs simulate the
+// next chunks; page-locked ones are written by the GPU directly.
 static int run_host(const double *b1r, const double *b1i, const double *gx, const double *gy, const double *gz,
                     const double *dt, int ntime, double t1, double t2, const double *df, int nf,
                     const double *dx, const double *dy, const double *dz, int npos, const double *m0x,
@@ -86,11 +47,7 @@ static int run_host(const double *b1r, const double *b1i, const double *gx, cons
     const bool any_yz = y_live || z_live;
     const bool use_x = x_live || any_yz;
 
-    HostCtx &cx = t_ctx;
-    cudaStream_t st;
-    if (int rc = cx.get_stream(&st)) return rc;
-
-    // ---- pack small inputs into one pinned block -> one H2D --------------------------------
+    // ---- the small inputs, packed into one block -> one H2D per device ----------------------
     const size_t nt = (size_t)ntime;
     size_t off = 0;
     auto take = [&](size_t n_doubles) { size_t o = off; off += align_up(n_doubles * sizeof(double), 64); return o; };
@@ -99,83 +56,43 @@ static int run_host(const double *b1r, const double *b1i, const double *gx, cons
     const size_t o_df = take((size_t)nf);
     const size_t o_dx = take((size_t)npos), o_dy = (any_yz && dy) ? take((size_t)npos) : 0,
                  o_dz = (any_yz && dz) ? take((size_t)npos) : 0;
-    const size_t in_bytes = off;
 
-    // outputs are produced in chunks of spins so that mode 2/3 (ntout = ntime) cannot exhaust HBM
-    const size_t out_budget = (size_t)3 << 30;  // bytes of device output per chunk
-    long long chunk = nspins;
-    if ((size_t)nspins * (size_t)ntout * 24 > out_budget) {
-        chunk = (long long)(out_budget / ((size_t)ntout * 24));
-        if (chunk < 1) chunk = 1;
-    }
     const bool have_m0 = m0x && m0y && m0z;
-    const size_t m0_bytes = have_m0 ? align_up((size_t)chunk * 8, 64) * 3 : 0;
-    if (int rc = cx.reserve_pinned(in_bytes + m0_bytes)) return rc;
-
-    double *zero_copy[3] = {nullptr, nullptr, nullptr};
-    if (ntout == 1 && chunk == nspins) {
-        // page-locked result arrays: let the kernel store straight into them over PCIe
-        zero_copy[0] = device_alias_if_pinned(mx);
-        zero_copy[1] = device_alias_if_pinned(my);
-        zero_copy[2] = device_alias_if_pinned(mz);
-        if (!(zero_copy[0] && zero_copy[1] && zero_copy[2])) zero_copy[0] = zero_copy[1] = zero_copy[2] = nullptr;
-    }
-    const size_t out_bytes = zero_copy[0] ? 0 : align_up((size_t)chunk * (size_t)ntout * 8, 256) * 3;
-    const size_t ws_bytes = align_up(mbrf_bloch_workspace_bytes(ntime), 256);
-    if (int rc = cx.dev.reserve(align_up(in_bytes, 256) + align_up(m0_bytes, 256) + ws_bytes + out_bytes)) return rc;
-
-    char *hp = (char *)cx.pinned;
-    char *dp = (char *)cx.dev.ptr;
-    memcpy(hp + o_b1r, b1r, nt * 8);
-    if (b1i) memcpy(hp + o_b1i, b1i, nt * 8);
-    memcpy(hp + o_dt, dt, nt * 8);
-    if (use_x && gx) memcpy(hp + o_gx, gx, nt * 8);
-    if (y_live) memcpy(hp + o_gy, gy, nt * 8);
-    if (z_live) memcpy(hp + o_gz, gz, nt * 8);
-    memcpy(hp + o_df, df, (size_t)nf * 8);
-    memcpy(hp + o_dx, dx, (size_t)npos * 8);
-    if (any_yz && dy) memcpy(hp + o_dy, dy, (size_t)npos * 8);
-    if (any_yz && dz) memcpy(hp + o_dz, dz, (size_t)npos * 8);
-    MBRF_CUDA(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
-
-    auto dptr = [&](size_t o) { return (const double *)(dp + o); };
-    char *d_m0 = dp + align_up(in_bytes, 256);
-    char *d_ws = d_m0 + align_up(m0_bytes, 256);
-    char *d_out = d_ws + ws_bytes;
-    const size_t comp_out = out_bytes / 3, comp_m0 = m0_bytes / 3;
-
-    for (long long s0 = 0; s0 < nspins; s0 += chunk) {
-        const long long n = (nspins - s0 < chunk) ? nspins - s0 : chunk;
-        const double *dm0[3] = {nullptr, nullptr, nullptr};
-        if (have_m0) {
-            double *h = (double *)(hp + in_bytes);
-            const size_t cs = comp_m0 / 8;
-            // the previous chunk's H2D of this staging area has completed (stream synced below)
-            for (long long i = 0; i < n; ++i) {
-                h[i] = m0x[(s0 + i) * m0_stride];
-                h[cs + i] = m0y[(s0 + i) * m0_stride];
-                h[2 * cs + i] = m0z[(s0 + i) * m0_stride];
-            }
-            MBRF_CUDA(cudaMemcpyAsync(d_m0, h, m0_bytes, cudaMemcpyHostToDevice, st));
-            for (int c = 0; c < 3; ++c) dm0[c] = (const double *)(d_m0 + c * comp_m0);
-        }
-        double *dout[3];
-        for (int c = 0; c < 3; ++c) dout[c] = zero_copy[0] ? zero_copy[c] : (double *)(d_out + c * comp_out);
-        int rc = mbrf_bloch_device(dptr(o_b1r), b1i ? dptr(o_b1i) : nullptr, (use_x && gx) ? dptr(o_gx) : nullptr,
-                                   y_live ? dptr(o_gy) : nullptr, z_live ? dptr(o_gz) : nullptr, dptr(o_dt), ntime,
-                                   t1, t2, dptr(o_df), nf, dptr(o_dx), (any_yz && dy) ? dptr(o_dy) : nullptr,
-                                   (any_yz && dz) ? dptr(o_dz) : nullptr, npos, s0, n, dm0[0], dm0[1], dm0[2], 1,
-                                   dout[0], dout[1], dout[2], mode, gamma, d_ws, st);
-        if (rc) return rc;
-        if (!zero_copy[0]) {
-            double *hout[3] = {mx, my, mz};
-            for (int c = 0; c < 3; ++c)
-                MBRF_CUDA(cudaMemcpyAsync(hout[c] + (size_t)s0 * ntout, dout[c], (size_t)n * ntout * 8,
-                                          cudaMemcpyDeviceToHost, st));
-        }
-        MBRF_CUDA(cudaStreamSynchronize(st));
-    }
-    return MBRF_OK;
+    const double *m0[3] = {m0x, m0y, m0z};
+    double *outs[3] = {mx, my, mz};
+    hostpipe::Desc d;
+    d.in_bytes = off;
+    d.pack = [&](char *hp) {
+        memcpy(hp + o_b1r, b1r, nt * 8);
+        if (b1i) memcpy(hp + o_b1i, b1i, nt * 8);
+        memcpy(hp + o_dt, dt, nt * 8);
+        if (use_x && gx) memcpy(hp + o_gx, gx, nt * 8);
+        if (y_live) memcpy(hp + o_gy, gy, nt * 8);
+        if (z_live) memcpy(hp + o_gz, gz, nt * 8);
+        memcpy(hp + o_df, df, (size_t)nf * 8);
+        memcpy(hp + o_dx, dx, (size_t)npos * 8);
+        if (any_yz && dy) memcpy(hp + o_dy, dy, (size_t)npos * 8);
+        if (any_yz && dz) memcpy(hp + o_dz, dz, (size_t)npos * 8);
+    };
+    d.ws_bytes = mbrf_bloch_workspace_bytes(ntime);
+    d.ncomp = 3;
+    d.host_out = outs;
+    d.item_doubles = (size_t)ntout;
+    d.items = nspins;
+    d.ncomp_in = have_m0 ? 3 : 0;
+    d.host_in = m0;
+    d.in_stride = m0_stride;
+    d.launch = [&](cudaStream_t st, const char *dp, char *d_ws, long long s0, long long n, const double *const *dm0,
+                   double *const *dout) -> int {
+        auto dptr = [&](size_t o) { return (const double *)(dp + o); };
+        return mbrf_bloch_device(dptr(o_b1r), b1i ? dptr(o_b1i) : nullptr, (use_x && gx) ? dptr(o_gx) : nullptr,
+                                 y_live ? dptr(o_gy) : nullptr, z_live ? dptr(o_gz) : nullptr, dptr(o_dt), ntime, t1, t2,
+                                 dptr(o_df), nf, dptr(o_dx), (any_yz && dy) ? dptr(o_dy) : nullptr,
+                                 (any_yz && dz) ? dptr(o_dz) : nullptr, npos, s0, n, dm0 ? dm0[0] : nullptr,
+                                 dm0 ? dm0[1] : nullptr, dm0 ? dm0[2] : nullptr, 1, dout[0], dout[1], dout[2], mode, gamma,
+                                 d_ws, st);
+    };
+    return hostpipe::run(d);
 }
 
 }  // namespace bloch

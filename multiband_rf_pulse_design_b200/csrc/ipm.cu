@@ -1127,6 +1127,19 @@ __global__ void add_rows_kernel(double *__restrict__ a, const double *__restrict
     if (i < n) a[i] += d[i];
 }
 
+// SPD test matrices for mbrf_ipm_cholesky_bench: H = G G' / n + I with a fixed pseudo-random lower-triangular pattern
+template <typename T>
+__global__ void spd_fill_kernel(T *Hall, int n, int B)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * n * n) return;
+    const int b = (int)(idx / ((long long)n * n)), r = (int)((idx / n) % n), c = (int)(idx % n);
+    unsigned h = (unsigned)(r * 2654435761u) ^ (unsigned)(c * 40503u) ^ (unsigned)(b * 97u);
+    h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+    const double v = r == c ? (double)n : ((double)(h & 0xffff) / 65536.0 - 0.5);     // diagonally dominant: SPD
+    Hall[idx] = Num<T>::from(c <= r ? v : 0.0);
+}
+
 static int g_precision = 2;          // 0 fp64, 1 double-double, 2 auto (double-double once mu is small)
 static double g_dd_switch = 1e-3;    // auto: double-double when min over live designs of mu / mu0 falls below this
 static int g_refine = 1;
@@ -1149,6 +1162,51 @@ int mbrf_ipm_set_option(int which, double value)
     case 3: g_verbose = (int)value; break;
     default: return MBRF_EINVAL;
     }
+    return MBRF_OK;
+}
+
+/* Times the batched factorisation alone (CUDA events on its stream): `B` matrices of order nv (rounded up to the panel
+ * width), double-double (use_dd != 0) or fp64, `reps` launches; *ms = mean per launch.  bench.py's solver roofline. */
+int mbrf_ipm_cholesky_bench(int nv, int B, int use_dd, int reps, float *ms)
+{
+    if (int rc = require_device()) return rc;
+    if (nv < 1 || B < 1 || reps < 1 || !ms) return MBRF_EINVAL;
+    P p;
+    memset(&p, 0, sizeof p);
+    p.NV = nv; p.NVp = up(nv, PANEL); p.B = B; p.Bp = B;
+    const size_t tsz = use_dd ? sizeof(dd) : sizeof(double), hb = (size_t)B * p.NVp * p.NVp * tsz;
+    char *buf = nullptr;
+    MBRF_CUDA(cudaMalloc(&buf, 2 * hb + (size_t)B * sizeof(Ctl)));
+    p.ctl = (Ctl *)(buf + 2 * hb);
+    MBRF_CUDA(cudaMemset(p.ctl, 0, (size_t)B * sizeof(Ctl)));
+    const long long ne = (long long)B * p.NVp * p.NVp;
+    if (use_dd) spd_fill_kernel<dd><<<(unsigned)((ne + 255) / 256), 256>>>((dd *)buf, p.NVp, B);
+    else spd_fill_kernel<double><<<(unsigned)((ne + 255) / 256), 256>>>((double *)buf, p.NVp, B);
+    MBRF_LAUNCH_CHECK();
+    const size_t sm = (size_t)(PANEL * (PANEL + 1) + 256 * (PANEL + 1)) * tsz;
+    if (use_dd) MBRF_CUDA(cudaFuncSetAttribute(cholesky_kernel<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    else MBRF_CUDA(cudaFuncSetAttribute(cholesky_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    cudaEvent_t e0, e1;
+    MBRF_CUDA(cudaEventCreate(&e0));
+    MBRF_CUDA(cudaEventCreate(&e1));
+    float total = 0.f;
+    for (int r = 0; r <= reps; ++r) {                            // first pass: warm-up
+        MBRF_CUDA(cudaMemcpyAsync(buf + hb, buf, hb, cudaMemcpyDeviceToDevice, 0));
+        MBRF_CUDA(cudaEventRecord(e0, 0));
+        if (use_dd) cholesky_kernel<dd><<<B, 256, sm>>>(p, (dd *)(buf + hb));
+        else cholesky_kernel<double><<<B, 256, sm>>>(p, (double *)(buf + hb));
+        MBRF_LAUNCH_CHECK();
+        MBRF_CUDA(cudaEventRecord(e1, 0));
+        MBRF_CUDA(cudaEventSynchronize(e1));
+        float t = 0.f;
+        MBRF_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        if (r) total += t;
+    }
+    std::vector<Ctl> h((size_t)B);
+    MBRF_CUDA(cudaMemcpy(h.data(), p.ctl, (size_t)B * sizeof(Ctl), cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    for (int b = 0; b < B; ++b) if (h[(size_t)b].chol_fail != 0.0) { set_error("cholesky bench: pivot failure"); return MBRF_ECUDA; }
+    *ms = total / reps;
     return MBRF_OK;
 }
 

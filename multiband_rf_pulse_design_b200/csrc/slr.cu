@@ -12,6 +12,7 @@
 // u = 0 value of the same polynomials.  Update (abrx.c:103-111):
 //        a <- al*a - be*conj(b)        b <- al*b + be*conj(a)
 #include "common.h"
+#include "hostpipe.h"
 #include "rot_coeffs.cuh"
 #include <cstring>
 
@@ -197,15 +198,6 @@ static int launch(K kernel, const Params &p, int spt, cudaStream_t stream)
     return MBRF_OK;
 }
 
-struct HostCtx {
-    DeviceScratch dev;
-    void *pinned = nullptr;
-    size_t pinned_bytes = 0;
-    cudaStream_t stream = nullptr;
-    int stream_device = -1;
-    ~HostCtx() { if (pinned) cudaFreeHost(pinned); }
-};
-static thread_local HostCtx t_ctx;
 
 }  // namespace slr
 }  // namespace mbrf
@@ -268,47 +260,33 @@ int mbrf_abr(const double *rfr, const double *rfi, const double *gx, const doubl
     const long long npos = (long long)nx * ny;
     if (npos == 0) return MBRF_OK;
     if (!rfr || !gx || !x || !alpha_r || !alpha_i || !beta_r || !beta_i) { set_error("abr: NULL required pointer"); return MBRF_EINVAL; }
-    HostCtx &cx = t_ctx;
-    int dev = 0;
-    MBRF_CUDA(cudaGetDevice(&dev));
-    if (!cx.stream || cx.stream_device != dev) {
-        MBRF_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
-        cx.stream_device = dev;
-    }
-    cudaStream_t st = cx.stream;
+    // positions spread over mbrf_set_fanout() devices, chunks pipelined through a pinned ring (hostpipe.h)
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t nsb = up((size_t)ns * 8), nxb = up((size_t)nx * 8), nyb = up((size_t)ny * 8);
-    const size_t in_bytes = nsb * 4 + nxb + nyb;
-    const size_t wsb = up(mbrf_abr_workspace_bytes(ns));
-    const size_t outb = up((size_t)npos * 8);
-    if (!cx.pinned || cx.pinned_bytes < in_bytes) {
-        if (cx.pinned) cudaFreeHost(cx.pinned);
-        cx.pinned = nullptr;
-        MBRF_CUDA(cudaMallocHost(&cx.pinned, in_bytes + in_bytes / 4));
-        cx.pinned_bytes = in_bytes + in_bytes / 4;
-    }
-    if (int rc = cx.dev.reserve(in_bytes + wsb + 4 * outb)) return rc;
-    char *hp = (char *)cx.pinned, *dp = (char *)cx.dev.ptr;
-    memcpy(hp, rfr, (size_t)ns * 8);
-    if (rfi) memcpy(hp + nsb, rfi, (size_t)ns * 8);
-    memcpy(hp + 2 * nsb, gx, (size_t)ns * 8);
-    if (gy) memcpy(hp + 3 * nsb, gy, (size_t)ns * 8);
-    memcpy(hp + 4 * nsb, x, (size_t)nx * 8);
-    if (y) memcpy(hp + 4 * nsb + nxb, y, (size_t)ny * 8);
-    MBRF_CUDA(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
-    double *d_out = (double *)(dp + in_bytes + wsb);
-    const size_t oc = outb / 8;
-    int rc = mbrf_abr_device((const double *)dp, rfi ? (const double *)(dp + nsb) : nullptr,
-                             (const double *)(dp + 2 * nsb), gy ? (const double *)(dp + 3 * nsb) : nullptr, ns,
-                             (const double *)(dp + 4 * nsb), nx, y ? (const double *)(dp + 4 * nsb + nxb) : nullptr,
-                             ny, convention, 0, npos, d_out, d_out + oc, d_out + 2 * oc, d_out + 3 * oc,
-                             dp + in_bytes, st);
-    if (rc) return rc;
     double *outs[4] = {alpha_r, alpha_i, beta_r, beta_i};
-    for (int c = 0; c < 4; ++c)
-        MBRF_CUDA(cudaMemcpyAsync(outs[c], d_out + c * oc, (size_t)npos * 8, cudaMemcpyDeviceToHost, st));
-    MBRF_CUDA(cudaStreamSynchronize(st));
-    return MBRF_OK;
+    hostpipe::Desc d;
+    d.in_bytes = nsb * 4 + nxb + nyb;
+    d.pack = [&](char *hp) {
+        memcpy(hp, rfr, (size_t)ns * 8);
+        if (rfi) memcpy(hp + nsb, rfi, (size_t)ns * 8);
+        memcpy(hp + 2 * nsb, gx, (size_t)ns * 8);
+        if (gy) memcpy(hp + 3 * nsb, gy, (size_t)ns * 8);
+        memcpy(hp + 4 * nsb, x, (size_t)nx * 8);
+        if (y) memcpy(hp + 4 * nsb + nxb, y, (size_t)ny * 8);
+    };
+    d.ws_bytes = mbrf_abr_workspace_bytes(ns);
+    d.ncomp = 4;
+    d.host_out = outs;
+    d.item_doubles = 1;
+    d.items = npos;
+    d.launch = [&](cudaStream_t st, const char *dp, char *d_ws, long long p0, long long n, const double *const *,
+                   double *const *dout) -> int {
+        return mbrf_abr_device((const double *)dp, rfi ? (const double *)(dp + nsb) : nullptr, (const double *)(dp + 2 * nsb),
+                               gy ? (const double *)(dp + 3 * nsb) : nullptr, ns, (const double *)(dp + 4 * nsb), nx,
+                               y ? (const double *)(dp + 4 * nsb + nxb) : nullptr, ny, convention, p0, n, dout[0], dout[1],
+                               dout[2], dout[3], d_ws, st);
+    };
+    return hostpipe::run(d);
 }
 
 }  // extern "C"

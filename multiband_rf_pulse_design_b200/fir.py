@@ -774,7 +774,7 @@ def assemble_fir_qp(n, f, a, d, k=100.0, oversamp=10):
                 radius=np.concatenate([D_band, np.full(wtran.size, 1 + d.max() * 5)]), nband=wband.size)   # :151,156
 
 
-def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, **solver_kw):
+def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, oversamp=10, **solver_kw):
     """[h, status] = fir_qp_cvx(n, f, a, d, k, obj, dbg) — fir_qp_cvx.m:1-243.
 
     Scalar `obj` (:145-166):
@@ -793,7 +793,7 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, **solver_kw):
         raise ValueError("invalid input of obj")                          # :193-195
     n = int(n)
     ob = [float(v) for v in np.ravel(obj)]
-    p = assemble_fir_qp(n, f, a, d, float(k))
+    p = assemble_fir_qp(n, f, a, d, float(k), oversamp=int(oversamp))    # oversamp = 10: fir_qp_cvx.m:35 (16 = the 4096-point grid)
     m, nb = p["w"].size, p["nband"]
     N, M = 2 * n, 2 * m + 2 * n
     w_row = np.concatenate([np.repeat(p["w"], 2), np.zeros(2 * n)])
@@ -831,6 +831,11 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, **solver_kw):
         hi[0:2 * m:2, 0] = p["radius"]
         blocks.disk_row0, blocks.disk_pairs = 0, m
         gw, lam = np.array([ob[0]]), np.array([1.0])
+    # the solver sees the objective divided by its largest weight: at the reference's obj = 1e6 (dzrf_mb.m:211-213) the
+    # problem is "minimise Peak" with the energy as a 1e-6 tie-break, and a first-order method needs O(1) weights
+    oscale = float(solver_kw.pop("objective_scale", 0.0)) or max(1.0, float(gw[0]), float(lam[0]))
+    gw, lam = gw / oscale, lam / oscale
+    one = one / oscale if minimax else one
     big = 2.0 * p["radius"].max() + 2.0 * np.abs(p["center"]).max() + (2.0 if minimax else 0.0)
     c = np.zeros((N, 1))
     bl, bu = np.full((N, 1), -big), np.full((N, 1), big)
@@ -847,6 +852,9 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, **solver_kw):
                                      _dp(hi), _dp(bl), _dp(bu), None, 1, None, C.byref(blocks), int(kw["max_iter"]),
                                      int(kw["check_every"]), float(kw["eps_pr"]), float(kw["eps_dr"]),
                                      float(kw["eps_gap"]), _dp(z), _dp(info), None))
+    info[0, 2] *= oscale                                                  # objective / dual value / bound in the caller's units
+    info[0, 3] *= oscale
+    info[0, 6] *= oscale
     ok = info[0, 0] == 1.0
     x = z[:, 0]
     h = x[:n] + 1j * x[n:] if ok else np.zeros(0)                         # :209

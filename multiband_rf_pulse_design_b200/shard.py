@@ -22,25 +22,62 @@ def shard_bounds(n: int, world: int) -> list[tuple[int, int]]:
     return out
 
 
-def gather_planes(local, counts, dst=0, group=None):
+_FULL = {}
+
+
+def _full_buffer(planes, total, like):
+    """The gathered result [planes, total] on the destination rank: allocated ONCE per shape and device and reused by every
+    later call (the caller consumes it before the next gather), so that no allocation sits inside a timed step."""
+    import torch
+    key = (planes, total, like.dtype, str(like.device))
+    buf = _FULL.get(key)
+    if buf is None:
+        if len(_FULL) > 8:
+            _FULL.clear()
+        buf = _FULL[key] = torch.empty((planes, total), dtype=like.dtype, device=like.device)
+    return buf
+
+
+def _peer(group, r):
+    import torch.distributed as dist
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def _exchange(ops):
+    """One batched point-to-point call (a single NCCL group launch on the GPU box)."""
+    import torch.distributed as dist
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+def gather_planes(local, counts, dst=0, group=None, full=None):
     """Gather per-rank result planes to `dst`.
 
-    local  : tensor [planes, max(counts)] on this rank (only the first counts[rank] columns are valid)
+    local  : tensor [planes, >= counts[rank]] on this rank (only the first counts[rank] columns are valid)
     counts : per-rank column counts
-    returns tensor [planes, sum(counts)] on rank `dst`, None elsewhere.
+    returns tensor [planes, sum(counts)] on rank `dst` (the reused buffer of _full_buffer unless `full` is given), None
+    elsewhere.  Every rank sends exactly its valid columns and `dst` receives them straight into their place of the final
+    layout: no padding, no list of receive buffers, no concatenation.
     """
-    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    width = max(counts)
-    if local.shape[1] != width:
-        raise ValueError(f"local must be padded to the widest shard ({width} columns)")
-    bufs = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
-    dist.gather(local, bufs, dst=dst, group=group)
-    if rank != dst:
-        return None
-    return torch.cat([b[:, :c] for b, c in zip(bufs, counts)], dim=1)
+    planes = local.shape[0]
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(int)
+    if local.shape[1] < counts[rank]:
+        raise ValueError(f"local has {local.shape[1]} columns, this rank's shard has {counts[rank]}")
+    ops = []
+    if rank == dst:
+        if full is None:
+            full = _full_buffer(planes, int(starts[-1]), local)
+        full[:, starts[rank]:starts[rank] + counts[rank]] = local[:, :counts[rank]]
+        for r in range(world):
+            if r != dst and counts[r]:
+                ops += [dist.P2POp(dist.irecv, full[p, starts[r]:starts[r] + counts[r]], _peer(group, r), group) for p in range(planes)]
+    elif counts[rank]:
+        ops = [dist.P2POp(dist.isend, local[p, :counts[rank]], _peer(group, dst), group) for p in range(planes)]
+    for w in _exchange(ops):
+        w.wait()
+    return full if rank == dst else None
 
 
 def piece_widths(width: int, chunks) -> list[int]:
@@ -63,12 +100,14 @@ def piece_widths(width: int, chunks) -> list[int]:
 
 
 def bloch_sharded(lib, dev_args: dict, nspins: int, out_local, workspace, stream, mode=0, gamma=6726.1,
-                  group=None, chunks=1):
+                  group=None, chunks=1, full=None):
     """Run this rank's spin range through mbrf_bloch_device and gather mx,my,mz on rank 0.
 
     dev_args holds device pointers / sizes: b1r,b1i,gx,gy,gz,dt,ntime,t1,t2,df,nf,dx,dy,dz,npos.
     out_local is a [3, max shard] float64 device tensor.  Mode 0/1 only (one value per spin).
-    stream: raw CUDA stream pointer, or a torch.cuda.Stream (needed for chunks > 1).
+    stream: a torch.cuda.Stream (a raw CUDA stream pointer is accepted on one GPU only: the gather must be ordered
+    behind the kernel, which needs the stream object).
+    full: optional preallocated [3, nspins] result on rank 0 (default: one reused buffer per shape).
     chunks > 1: the shard is simulated in that many pieces and piece k is gathered (NCCL, on a side stream) while piece
     k + 1 is being simulated, so that only the last piece's transfer is exposed: rank 0 receives (world - 1) x 24 bytes
     per spin over its NVLink ingress, 0.19 ms for 8 x 10^6 spins against 1.1 ms of simulation.
@@ -87,74 +126,135 @@ def bloch_sharded(lib, dev_args: dict, nspins: int, out_local, workspace, stream
                                     a["df"], a["nf"], a["dx"], a["dy"], a["dz"], a["npos"], first, count, None, None, None, 1,
                                     o0, o1, o2, mode, gamma, workspace, raw))
 
-    if world == 1 or chunks == 1 or not hasattr(stream, "cuda_stream"):
+    if world == 1:
         simulate(s0, cnt, out_local[0].data_ptr(), out_local[1].data_ptr(), out_local[2].data_ptr())
-        if world == 1:
-            return out_local[:, :cnt]
-        return gather_planes(out_local, [c for _, c in bounds], dst=0, group=group)
+        return out_local[:, :cnt]
+    if not hasattr(stream, "cuda_stream"):
+        raise TypeError("bloch_sharded on several GPUs needs a torch.cuda.Stream: the gather is ordered behind the kernel by an event")
 
     return pipelined_gather(lambda first, size, piece: simulate(s0 + first, size, piece[0].data_ptr(), piece[1].data_ptr(),
                                                                 piece[2].data_ptr()),
-                            out_local, bounds, chunks, stream=stream, group=group)
+                            out_local, bounds, chunks, stream=stream, group=group, full=full)
 
 
-def pipelined_gather(fill_piece, out_local, bounds, chunks, stream=None, group=None, dst=0):
-    """Produce this rank's shard piece by piece (fill_piece(first, size, piece[planes, width]) fills columns
-    [first, first + size) of the shard into `piece`) and gather piece k while piece k + 1 is produced.
-    On CUDA tensors the gathers run on a side stream behind an event of `stream` (a torch.cuda.Stream); on CPU tensors
-    (gloo, tests) the same sequence runs synchronously.  Returns [planes, sum(counts)] on rank `dst`, None elsewhere."""
+def abr_sharded(lib, dev_args: dict, npos: int, out_local, workspace, stream, convention=0, group=None, chunks=1, full=None):
+    """Forward SLR over this rank's contiguous range of the position index ix + iy*nx (abrx.c:67-78) through
+    mbrf_abr_device, alpha/beta planes (re, im, re, im) gathered on rank 0 exactly like the Bloch planes.
+    dev_args: device pointers / sizes rfr, rfi, gx, gy, ns, x, nx, y, ny.  out_local: [4, widest shard] float64."""
+    import torch.distributed as dist
+    from ._lib import check
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    bounds = shard_bounds(npos, world)
+    p0, cnt = bounds[rank]
+    a = dev_args
+    raw = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+
+    def run(first, count, piece):
+        check(lib.mbrf_abr_device(a["rfr"], a["rfi"], a["gx"], a["gy"], a["ns"], a["x"], a["nx"], a["y"], a["ny"], convention,
+                                  first, count, piece[0].data_ptr(), piece[1].data_ptr(), piece[2].data_ptr(),
+                                  piece[3].data_ptr(), workspace, raw))
+
+    if world == 1:
+        run(p0, cnt, out_local)
+        return out_local[:, :cnt]
+    if not hasattr(stream, "cuda_stream"):
+        raise TypeError("abr_sharded on several GPUs needs a torch.cuda.Stream")
+    return pipelined_gather(lambda first, size, piece: run(p0 + first, size, piece), out_local, bounds, chunks,
+                            stream=stream, group=group, full=full)
+
+
+def pipelined_gather(fill_piece, out_local, bounds, chunks, stream=None, group=None, dst=0, full=None):
+    """Produce this rank's shard piece by piece (fill_piece(first, size, piece) fills columns [first, first + size) of the
+    shard into the [planes, >= size] tensor view `piece`) and move piece k to rank `dst` while piece k + 1 is produced.
+
+    Rank `dst` produces its own pieces IN PLACE in the final [planes, total] buffer and posts, per piece, one batched
+    receive that lands every other rank's columns in their final place; the other ranks stage a piece in `out_local` and
+    send its valid columns.  No receive lists, no concatenation, no allocation per call (`full`, or the reused buffer of
+    _full_buffer).  On CUDA tensors the transfers run on a side stream behind an event of `stream` (a torch.cuda.Stream);
+    on CPU tensors (gloo, tests) the same sequence runs synchronously.  Returns [planes, total] on `dst`, None elsewhere."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     planes = out_local.shape[0]
-    cnt = bounds[rank][1]
+    s0, cnt = bounds[rank]
+    total = sum(c for _, c in bounds)
     width = max(c for _, c in bounds)
     widths = piece_widths(width, chunks)
     starts = [sum(widths[:k]) for k in range(len(widths))]
-    if out_local.numel() < planes * width:
-        raise ValueError("out_local too small: [planes, widest shard] needed")
-    flat = out_local.reshape(-1)
-    pieces = [flat[planes * o:planes * (o + w)].view(planes, w) for o, w in zip(starts, widths)]   # piece-major staging
     on_gpu = out_local.is_cuda
+    if rank == dst:
+        if full is None:
+            full = _full_buffer(planes, total, out_local)
+        elif tuple(full.shape) != (planes, total):
+            raise ValueError(f"full must be [{planes}, {total}]")
+    else:
+        if out_local.numel() < planes * width:
+            raise ValueError("out_local too small: [planes, widest shard] needed")
+        flat = out_local.reshape(-1)
     comm = _comm_stream(out_local.device) if on_gpu else None
-    recv, works = [], []
+    works = []
     for k, (o, w) in enumerate(zip(starts, widths)):
         size = max(0, min(w, cnt - o))
-        if size:
-            fill_piece(o, size, pieces[k])
-        bufs = None
+        ops = []
+        if rank == dst:
+            if size:
+                fill_piece(o, size, full[:, s0 + o:s0 + o + size])
+            for r, (b0, c) in enumerate(bounds):
+                sz = max(0, min(w, c - o))
+                if r != dst and sz:
+                    ops += [dist.P2POp(dist.irecv, full[p, b0 + o:b0 + o + sz], _peer(group, r), group) for p in range(planes)]
+        elif size:
+            piece = flat[planes * o:planes * (o + w)].view(planes, w)          # piece-major staging, rows contiguous
+            fill_piece(o, size, piece)
+            ops = [dist.P2POp(dist.isend, piece[p, :size], _peer(group, dst), group) for p in range(planes)]
         if on_gpu:
             ev = torch.cuda.Event()
             ev.record(stream)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev)
-                bufs = [torch.empty_like(pieces[k]) for _ in range(world)] if rank == dst else None
-                works.append(dist.gather(pieces[k], bufs, dst=dst, group=group, async_op=True))
+                works += _exchange(ops)
         else:
-            bufs = [torch.empty_like(pieces[k]) for _ in range(world)] if rank == dst else None
-            dist.gather(pieces[k], bufs, dst=dst, group=group)
-        recv.append(bufs)
+            for wk in _exchange(ops):
+                wk.wait()
+    if on_gpu:
+        with torch.cuda.stream(stream):
+            for wk in works:
+                wk.wait()
+    return full if rank == dst else None
 
-    def assemble():
-        # (receiving every plane and piece straight into its place -- one gather per plane and piece, no concatenation --
-        # was measured at 2 GPUs and is 0.03 ms slower: six collectives instead of two)
-        if rank != dst:
-            return None
-        cols = []
-        for r, (_, c) in enumerate(bounds):
-            for k, (o, w) in enumerate(zip(starts, widths)):
-                size = max(0, min(w, c - o))
-                if size:
-                    cols.append(recv[k][r][:, :size])
-        return torch.cat(cols, dim=1)
 
-    if not on_gpu:
-        return assemble()
-    with torch.cuda.stream(stream):
-        for wk in works:
-            wk.wait()
-        return assemble()
+def gather_sweep(res, n, ndesigns, group=None, dst=0, device=None):
+    """Final gather of a design sweep (x, objective, status of every instance to the calling rank).
+    res: this rank's dict(index, x [k, 2n-1], ripple_stop [k], info [k, 8]) from fir.fir_ap_cvx_sweep.
+    Returns the same dict for ALL `ndesigns` instances, ordered by instance index, on rank `dst`; None elsewhere.
+    One collective: every rank contributes a [ceil(ndesigns / world), 2n - 1 + 1 + 8 + 1] block (NCCL on `device`, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dict(res)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    rows, width = -(-ndesigns // world), 2 * n - 1 + 10
+    blk = np.full((rows, width), -1.0)
+    k = len(res["index"])
+    blk[:k, 0] = res["index"]
+    blk[:k, 1:2 * n] = res["x"]
+    blk[:k, 2 * n] = res["ripple_stop"]
+    blk[:k, 2 * n + 1:2 * n + 9] = res["info"]
+    t = torch.from_numpy(blk)
+    if device is not None:
+        t = t.to(device)
+    bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, bufs, dst=_peer(group, dst), group=group)
+    if rank != dst:
+        return None
+    allb = torch.cat(bufs).cpu().numpy()
+    allb = allb[allb[:, 0] >= 0]
+    allb = allb[np.argsort(allb[:, 0])]
+    if allb.shape[0] != ndesigns or not np.array_equal(allb[:, 0], np.arange(ndesigns)):
+        raise RuntimeError("sweep gather: the ranks' instances do not partition the sweep")
+    return dict(index=allb[:, 0].astype(int), x=allb[:, 1:2 * n], ripple_stop=allb[:, 2 * n], info=allb[:, 2 * n + 1:2 * n + 9])
 
 
 _COMM = {}
