@@ -462,9 +462,23 @@ def run_ours(args):
                     ntime=nt, t1=wl["t1"], t2=wl["t2"], df=df.data_ptr(), nf=nf, dx=dx.data_ptr(), dy=None, dz=None,
                     npos=npos)
 
+    # The gather of the path is fused into the kernel: rank 0 owns the final [3, S] result, every other rank
+    # maps it (CUDA IPC) and its kernel stores its slice straight into it over NVLink -- one kernel per rank, no transfer
+    # step; a 1-element all-reduce on the stream orders completion.  (The NCCL variant -- batched send/recv into the final
+    # layout, pipelined in two pieces -- stays available: bloch_sharded(..., chunks=[0.85, 0.15]) without `peer`.)
+    from multiband_rf_pulse_design_b200.shard import PeerResult
+    peer = PeerResult(lib, 3, nf * npos) if world > 1 else None
+    peer_t = peer.tensor() if peer is not None else None
+    tok = torch.zeros(1, device=dev)
+
     def step_device():
-        # this rank's contiguous spin range, then the one collective of the path: the final gather (NCCL/NVLink)
-        # (pipelined in two pieces: the first piece's transfer hides behind the simulation of the second)
+        r = bloch_sharded(lib, dev_args, nf * npos, out, ws.data_ptr(), stream, 0, m.GAMMA_C13, peer=peer)
+        if world > 1:
+            dist.all_reduce(tok)         # returns on this stream once every rank's kernel (and its remote stores) has finished
+            return peer_t
+        return r
+
+    def step_device_nccl():
         return bloch_sharded(lib, dev_args, nf * npos, out, ws.data_ptr(), stream, 0, m.GAMMA_C13, chunks=[0.85, 0.15])
 
     def barrier():
@@ -533,6 +547,21 @@ def run_ours(args):
     ms_dev = max_over_ranks(ms_dev)
     ms_dev_min, ms_dev_med = max_over_ranks(min(per_step)), max_over_ranks(statistics.median(per_step))
     value = world * steps_per_gpu / (ms_dev * 1e-3)
+
+    # the NCCL gather variant, for the record
+    ms_nccl = None
+    if world > 1:
+        for _ in range(3):
+            step_device_nccl()
+        barrier()
+        nev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(20, args.steps))]
+        for k in range(len(nev)):
+            flush.zero_()
+            nev[k][0].record(stream)
+            step_device_nccl()
+            nev[k][1].record(stream)
+        barrier()
+        ms_nccl = max_over_ranks(sum(a.elapsed_time(b) for a, b in nev) / len(nev))
 
     # dominant kernel alone (prep + spin kernel, no gather) for the roofline, same stream, L2 flushed
     barrier()
@@ -604,8 +633,15 @@ def run_ours(args):
     ws2 = torch.empty(int(lib.mbrf_abr_workspace_bytes(ns)), dtype=torch.uint8, device=dev)
     slr_args = dict(rfr=d_rfr.data_ptr(), rfi=d_rfi.data_ptr(), gx=d_g.data_ptr(), gy=None, ns=ns, x=d_x.data_ptr(), nx=nx, y=None, ny=1)
 
+    peer_ab = PeerResult(lib, 4, nx) if world > 1 else None
+    peer_ab_t = peer_ab.tensor() if peer_ab is not None else None
+
     def step_slr():
-        return abr_sharded(lib, slr_args, nx, ab, ws2.data_ptr(), stream, 0, chunks=[0.85, 0.15])
+        r = abr_sharded(lib, slr_args, nx, ab, ws2.data_ptr(), stream, 0, peer=peer_ab)
+        if world > 1:
+            dist.all_reduce(tok)
+            return peer_ab_t
+        return r
     for _ in range(3):
         full_ab = step_slr()
     barrier()
@@ -623,7 +659,7 @@ def run_ours(args):
         unit = float((full_ab[0] ** 2 + full_ab[1] ** 2 + full_ab[2] ** 2 + full_ab[3] ** 2 - 1).abs().max().item())
         slr = {"metric": "SLR position-steps/sec", "value": nx * ns / (ms_slr * 1e-3), "unit": "position-steps/s",
                "ms_per_call": ms_slr, "positions": nx, "samples": ns, "unitarity_max_err": unit, "n_gpus": world,
-               "flops_per_position_step": 50, "call": "mbrf_abr_device (abrx convention) per rank + gather of alpha/beta on rank 0, device-resident"}
+               "flops_per_position_step": 50, "call": "mbrf_abr_device (abrx convention) per rank, alpha/beta planes stored straight into rank 0's peer-mapped result, device-resident"}
     full_ab = None
 
     # ---- second hot path: convex FIR design step (BASELINE metric "N=256 FIR pulse designs solved/sec") --------
@@ -696,7 +732,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "pulse": wl["src"], "spins_per_gpu": nlocal, "ntime": nt,
-                   "sharding": f"contiguous spin ranges over {world} GPU(s), one gather per step: batched NCCL send/recv straight into rank 0's preallocated [3, S] result"
+                   "sharding": f"contiguous spin ranges over {world} GPU(s); every rank's kernel stores its slice straight into rank 0's [3, S] result "
+                               f"over NVLink (peer-mapped, CUDA IPC), completion ordered by a 1-element all-reduce; NCCL send/recv gather variant: {ms_nccl} ms per step"
                    if world > 1 else "single GPU", "l2": "flushed between timed iterations (256 MiB memset)", "gather_check_max_abs": gather_check},
         "e2e": e2e,
         "gpu_launches": int(launches),

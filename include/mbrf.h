@@ -49,6 +49,14 @@ int  mbrf_device_sm_count(int *sm_count); /* multiprocessors of the current devi
  * or the environment variable MBRF_FANOUT.  A MATLAB host is one process: this is how it uses more than one GPU. */
 int  mbrf_set_fanout(int ndevices);
 int  mbrf_get_fanout(void);
+/* Peer-mapped result buffer of a sharded run (one process per GPU): the destination rank allocates [planes x S] doubles and
+ * exports a 64-byte CUDA IPC handle; the other ranks open it and hand pointers into it to mbrf_bloch_device / mbrf_abr_device as
+ * output arrays, so every kernel stores its slice straight into the destination GPU over NVLink -- the "one gather at the end"
+ * of SURVEY.md 8(e) without a transfer step.  The caller orders completion (a barrier / 1-element all-reduce on the stream). */
+int  mbrf_peer_alloc(unsigned long long bytes, void **dptr, unsigned char handle[64]);
+int  mbrf_peer_open(const unsigned char handle[64], void **dptr);
+int  mbrf_peer_close(void *dptr);   /* a pointer from mbrf_peer_open */
+int  mbrf_peer_free(void *dptr);    /* a pointer from mbrf_peer_alloc */
 /* counts kernel launches made by this library on the calling process (for bench `gpu_launches`) */
 unsigned long long mbrf_launch_count(void);
 

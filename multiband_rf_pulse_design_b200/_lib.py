@@ -42,6 +42,10 @@ SIGNATURES = {
     "mbrf_device_sm_count": (_i, [c_int_p]),
     "mbrf_set_fanout": (_i, [_i]),
     "mbrf_get_fanout": (_i, []),
+    "mbrf_peer_alloc": (_i, [C.c_ulonglong, C.POINTER(C.c_void_p), C.c_char_p]),
+    "mbrf_peer_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mbrf_peer_close": (_i, [_vp]),
+    "mbrf_peer_free": (_i, [_vp]),
     "mbrf_launch_count": (C.c_ulonglong, []),
     "mbrf_measure_fp64_peak": (_i, [c_double_p, c_double_p]),
     "mbrf_blochsimfz": (_i, [_dp, _dp, _dp, _dp, _dp, _dp, _i, _d, _d, _dp, _i, _dp, _dp, _dp, _i,

@@ -110,6 +110,53 @@ int mbrf_device_sm_count(int *out)
 
 unsigned long long mbrf_launch_count(void) { return mbrf::g_launches.load(); }
 
+/* ---- peer-mapped result buffers: the gather of a sharded run without a collective ------------------------------------
+ * The destination rank allocates the final [planes x S] result once and exports a CUDA IPC handle; every other rank (one
+ * process per GPU) opens it and passes pointers INTO it as the output arrays of mbrf_bloch_device / mbrf_abr_device: the
+ * kernels store their slice straight into the destination GPU's memory over NVLink (24 B per spin after 512 steps of
+ * arithmetic: the link is idle), so "compute then gather" is one kernel per rank and no transfer step exists. */
+int mbrf_peer_alloc(unsigned long long bytes, void **dptr, unsigned char handle[64])
+{
+    if (!dptr || !handle || bytes == 0) return MBRF_EINVAL;
+    if (int rc = mbrf::require_device()) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    MBRF_CUDA(cudaMalloc(dptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dptr);
+        *dptr = nullptr;
+        mbrf::set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return MBRF_ECUDA;
+    }
+    memcpy(handle, &h, 64);
+    return MBRF_OK;
+}
+
+int mbrf_peer_open(const unsigned char handle[64], void **dptr)
+{
+    if (!dptr || !handle) return MBRF_EINVAL;
+    if (int rc = mbrf::require_device()) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    MBRF_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MBRF_OK;
+}
+
+int mbrf_peer_close(void *dptr)
+{
+    if (!dptr) return MBRF_OK;
+    MBRF_CUDA(cudaIpcCloseMemHandle(dptr));
+    return MBRF_OK;
+}
+
+int mbrf_peer_free(void *dptr)
+{
+    if (!dptr) return MBRF_OK;
+    MBRF_CUDA(cudaFree(dptr));
+    return MBRF_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------

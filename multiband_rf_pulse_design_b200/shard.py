@@ -80,6 +80,54 @@ def gather_planes(local, counts, dst=0, group=None, full=None):
     return full if rank == dst else None
 
 
+class PeerResult:
+    """The final [planes, total] float64 result of a sharded run, living on rank `dst`'s GPU and mapped into every other
+    rank's address space (CUDA IPC, include/mbrf.h mbrf_peer_*).  Every rank's kernel stores its slice straight into it over
+    NVLink; nothing is transferred afterwards.  Collective constructor (all ranks of `group`); `exchange` is a callable
+    that all-gathers a picklable object (default: torch.distributed.all_gather_object on `group`)."""
+
+    def __init__(self, lib, planes, total, group=None, dst=0, exchange=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from ._lib import check
+        self.lib, self.planes, self.total, self.dst = lib, planes, total, dst
+        self.rank = dist.get_rank(group)
+        world = dist.get_world_size(group)
+        self.owner = self.rank == dst
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        if self.owner:
+            check(lib.mbrf_peer_alloc(planes * total * 8, C.byref(ptr), handle))
+        if exchange is None:
+            def exchange(o):
+                outl = [None] * world
+                dist.all_gather_object(outl, o, group=group)
+                return outl
+        handles = exchange(handle.raw if self.owner else None)
+        if not self.owner:
+            check(lib.mbrf_peer_open(handles[dst], C.byref(ptr)))
+        self.base = ptr.value
+
+    def plane_ptr(self, p, col0=0):
+        return self.base + (p * self.total + col0) * 8
+
+    def tensor(self):
+        """[planes, total] torch view of the buffer (owner rank only)."""
+        import torch
+        if not self.owner:
+            return None
+        holder = type("_Buf", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (self.planes, self.total), "typestr": "<f8", "data": (self.base, False),
+                                           "version": 2, "strides": None}
+        self._holder = holder
+        return torch.as_tensor(holder, device="cuda")
+
+    def close(self):
+        if self.base:
+            (self.lib.mbrf_peer_free if self.owner else self.lib.mbrf_peer_close)(self.base)
+            self.base = 0
+
+
 def piece_widths(width: int, chunks) -> list[int]:
     """Padded widths of the pieces a shard of `width` columns is cut into for the pipelined gather: `chunks` is a number
     of equal pieces or a list of fractions (e.g. [0.85, 0.15]: a large piece whose transfer hides behind the simulation of
@@ -100,7 +148,7 @@ def piece_widths(width: int, chunks) -> list[int]:
 
 
 def bloch_sharded(lib, dev_args: dict, nspins: int, out_local, workspace, stream, mode=0, gamma=6726.1,
-                  group=None, chunks=1, full=None):
+                  group=None, chunks=1, full=None, peer=None):
     """Run this rank's spin range through mbrf_bloch_device and gather mx,my,mz on rank 0.
 
     dev_args holds device pointers / sizes: b1r,b1i,gx,gy,gz,dt,ntime,t1,t2,df,nf,dx,dy,dz,npos.
@@ -108,6 +156,8 @@ def bloch_sharded(lib, dev_args: dict, nspins: int, out_local, workspace, stream
     stream: a torch.cuda.Stream (a raw CUDA stream pointer is accepted on one GPU only: the gather must be ordered
     behind the kernel, which needs the stream object).
     full: optional preallocated [3, nspins] result on rank 0 (default: one reused buffer per shape).
+    peer: a PeerResult([3, nspins]) -- the ranks' kernels then store straight into rank 0's buffer (no gather step at all);
+    returns None, the result is peer.tensor() on rank 0 once the caller has ordered completion (barrier / all-reduce).
     chunks > 1: the shard is simulated in that many pieces and piece k is gathered (NCCL, on a side stream) while piece
     k + 1 is being simulated, so that only the last piece's transfer is exposed: rank 0 receives (world - 1) x 24 bytes
     per spin over its NVLink ingress, 0.19 ms for 8 x 10^6 spins against 1.1 ms of simulation.
@@ -129,6 +179,10 @@ def bloch_sharded(lib, dev_args: dict, nspins: int, out_local, workspace, stream
     if world == 1:
         simulate(s0, cnt, out_local[0].data_ptr(), out_local[1].data_ptr(), out_local[2].data_ptr())
         return out_local[:, :cnt]
+    if peer is not None:
+        # one kernel per rank, storing straight into rank 0's result over NVLink (PeerResult); the caller orders completion
+        simulate(s0, cnt, peer.plane_ptr(0, s0), peer.plane_ptr(1, s0), peer.plane_ptr(2, s0))
+        return None
     if not hasattr(stream, "cuda_stream"):
         raise TypeError("bloch_sharded on several GPUs needs a torch.cuda.Stream: the gather is ordered behind the kernel by an event")
 
@@ -137,7 +191,8 @@ def bloch_sharded(lib, dev_args: dict, nspins: int, out_local, workspace, stream
                             out_local, bounds, chunks, stream=stream, group=group, full=full)
 
 
-def abr_sharded(lib, dev_args: dict, npos: int, out_local, workspace, stream, convention=0, group=None, chunks=1, full=None):
+def abr_sharded(lib, dev_args: dict, npos: int, out_local, workspace, stream, convention=0, group=None, chunks=1, full=None,
+                peer=None):
     """Forward SLR over this rank's contiguous range of the position index ix + iy*nx (abrx.c:67-78) through
     mbrf_abr_device, alpha/beta planes (re, im, re, im) gathered on rank 0 exactly like the Bloch planes.
     dev_args: device pointers / sizes rfr, rfi, gx, gy, ns, x, nx, y, ny.  out_local: [4, widest shard] float64."""
@@ -158,6 +213,11 @@ def abr_sharded(lib, dev_args: dict, npos: int, out_local, workspace, stream, co
     if world == 1:
         run(p0, cnt, out_local)
         return out_local[:, :cnt]
+    if peer is not None:
+        check(lib.mbrf_abr_device(a["rfr"], a["rfi"], a["gx"], a["gy"], a["ns"], a["x"], a["nx"], a["y"], a["ny"], convention,
+                                  p0, cnt, peer.plane_ptr(0, p0), peer.plane_ptr(1, p0), peer.plane_ptr(2, p0),
+                                  peer.plane_ptr(3, p0), workspace, raw))
+        return None
     if not hasattr(stream, "cuda_stream"):
         raise TypeError("abr_sharded on several GPUs needs a torch.cuda.Stream")
     return pipelined_gather(lambda first, size, piece: run(p0 + first, size, piece), out_local, bounds, chunks,
