@@ -289,7 +289,7 @@ int mbrf_pdhg_solve_device(const double *K, const double *KT, int Mp, int Np, in
  * weight vectors of the batch) and factorised by a batched Cholesky, in double-double once the complementarity gap is small.
  *   Column frequencies col_kappa must be multiples of 1/2 (all the reference's matrices: fir_ap_cvx.m:100 k = 1..n-1,
  *   ss/fir_linprog.m:195-217 k or k + 1/2).  bl / bu may be NULL (no bounds); infinite entries mean "no bound".
- *   feastol (relative primal / dual residual, default 1e-7), reltol (relative gap, default 2e-6), abstol (default 1e-12).
+ *   feastol (relative primal residual, default 1e-7; the dual residual gets 100 x feastol), reltol (relative gap, default 2e-6), abstol (default 1e-12).
  *   A design whose last iterations lose feasibility again (fp64 cone scalings at the boundary) ends with its best iterate if that was
  *   within 10x of the tolerances (CVX's "Inaccurate/Solved", accepted as 'Solved' by fir_ap_cvx.m:176-182).
  *   info_out [B x 8] as mbrf_fir_pdhg_solve: status 1 optimal, 2 primal infeasible (a Farkas certificate was found),

@@ -332,9 +332,46 @@ def _speculate(state, step, depth):
 # --------------------------------------------------------------------------------------------
 # public mirrors
 # --------------------------------------------------------------------------------------------
+class UndecidedProbe(UserWarning):
+    """A feasibility probe of a bisection ended at the solver's iteration limit twice: neither solved nor certified
+    infeasible.  The search treats it as 'Failed' (as the reference treats every non-'Solved' CVX status, fir_ap.m:86,149)
+    but says so, because a wrong 'Failed' moves the bisection to a longer filter / narrower band than necessary."""
+
+
+def _retry_kw(solver_kw):
+    """More effort for a probe that hit the iteration limit (status 3): three times the iterations."""
+    kw = dict(solver_kw)
+    if (kw.get("method") or DEFAULT_METHOD) == "ipm":
+        kw["ipm_max_iter"] = 3 * int(kw.get("ipm_max_iter") or IPM_MAX_ITER)
+    else:
+        kw["max_iter"] = 4 * int(kw.get("max_iter") or MAX_ITER)
+    return kw
+
+
+def fir_ap_cvx_decided(n, f_list, a, d, obj_list, peak_list, **solver_kw):
+    """fir_ap_cvx_batch for the bisections: designs that end at the iteration limit (status 3 -- NOT a certificate of
+    infeasibility, unlike status 2) are solved again with more iterations before their 'Failed' is believed; if the limit is
+    hit again an UndecidedProbe warning is raised.  Returns (h_list, status_list, code_list)."""
+    import warnings
+    hs, st, ex = fir_ap_cvx_batch(n, f_list, a, d, obj_list, peak_list, return_info=True, **solver_kw)
+    code = ex["info"][:, 0].astype(int)
+    again = np.nonzero(code == 3)[0]
+    if again.size:
+        pick = lambda v: [v[i] for i in again] if isinstance(v, (list, tuple)) and np.ndim(v[0]) else v   # noqa: E731
+        h2, s2, e2 = fir_ap_cvx_batch(n, [f_list[i] for i in again], pick(a), pick(d), [obj_list[i] for i in again],
+                                      [peak_list[i] for i in again], return_info=True, **_retry_kw(solver_kw))
+        for k, i in enumerate(again):
+            hs[i], st[i], code[i] = h2[k], s2[k], int(e2["info"][k, 0])
+        if (code[again] == 3).any():
+            warnings.warn(f"{int((code[again] == 3).sum())} feasibility probe(s) at n = {n} stayed undecided at the iteration "
+                          "limit and are treated as 'Failed'", UndecidedProbe, stacklevel=2)
+    return hs, st, list(code)
+
+
 def fir_ap_cvx_batch(n, f_list, a, d, obj_list, peak_list, return_info=False, **solver_kw):
     """Batched fir_ap_cvx: designs i = 0..B-1 with band edges f_list[i], trade-off obj_list[i], Peak peak_list[i]
-    (a, d shared or per-design lists).  Returns (h_list, status_list[, info]); h is None where 'Failed'."""
+    (a, d shared or per-design lists).  Returns (h_list, status_list[, info]); h is None where 'Failed'.
+    info["info"][:, 0] keeps what the string cannot: 1 solved, 2 infeasible (certificate), 3 iteration limit (undecided)."""
     B = len(f_list)
     a_list = a if isinstance(a, (list, tuple)) and np.ndim(a[0]) else [a] * B
     d_list = d if isinstance(d, (list, tuple)) and np.ndim(d[0]) else [d] * B
@@ -372,7 +409,12 @@ def fir_ap(n, f, a, d, Peak=1e-3, min_order=0, min_tran=0, min_peak=0, dbg=0, **
     f = np.asarray(f, float).ravel()
     lam, df_thre = 0.1, 0.0005                                            # fir_ap.m:45-46
     n_op, f_op = int(n), f.copy()
-    h1, status1 = fir_ap_cvx(n, f, a, d, lam, Peak, **solver_kw)          # :51
+    def solve1(nn, ff):
+        """one fir_ap_cvx probe whose 'Failed' is only believed after a retry (fir_ap_cvx_decided)"""
+        hq, sq, _ = fir_ap_cvx_decided(int(nn), [ff], a, d, [lam], [Peak], **solver_kw)
+        return (hq[0] if hq[0] is not None else np.zeros(0)), sq[0]
+
+    h1, status1 = solve1(n, f)                                            # :51
     if status1 == "Failed":
         raise RuntimeError("original parameters are too tight")          # :52-54
     h, status = h1, status1
@@ -394,8 +436,8 @@ def fir_ap(n, f, a, d, Peak=1e-3, min_order=0, min_tran=0, min_peak=0, dbg=0, **
         while True:
             span = top - bot
             nodes = {j: bot + span * j / 8 for j in range(1, 8)}
-            hs, sts = fir_ap_cvx_batch(n, [widen(nodes[j]) for j in range(1, 8)], a, d, [lam] * 7, [Peak] * 7,
-                                       **solver_kw)
+            hs, sts, _ = fir_ap_cvx_decided(n, [widen(nodes[j]) for j in range(1, 8)], a, d, [lam] * 7, [Peak] * 7,
+                                            **solver_kw)
             res = {j: (hs[j - 1], sts[j - 1]) for j in range(1, 8)}
             lo_j, hi_j, done = 0, 8, False
             for _ in range(3):
@@ -414,7 +456,7 @@ def fir_ap(n, f, a, d, Peak=1e-3, min_order=0, min_tran=0, min_peak=0, dbg=0, **
         if not (0 < min_tran <= 1):
             raise ValueError("invalid input of min_tran")                 # :131-133
         fa = bot * min_tran                                               # :110
-        h0, st0 = fir_ap_cvx(n, widen(fa), a, d, lam, Peak, **solver_kw)  # :116
+        h0, st0 = solve1(n, widen(fa))                                    # :116
         if st0 == "Failed":
             fa = bot                                                      # :117-121
         else:
@@ -438,7 +480,7 @@ def fir_ap(n, f, a, d, Peak=1e-3, min_order=0, min_tran=0, min_peak=0, dbg=0, **
         cache = {}
         while state[2] is not None:
             need = [q for q in _speculate(state, step, 3) if q not in cache]
-            res = _solve_concurrently([(lambda q=q: fir_ap_cvx(q, f, a, d, lam, Peak, **solver_kw)) for q in need])
+            res = _solve_concurrently([(lambda q=q: solve1(q, f)) for q in need])
             cache.update(dict(zip(need, res)))
             for _ in range(3):
                 if state[2] is None:
@@ -452,7 +494,7 @@ def fir_ap(n, f, a, d, Peak=1e-3, min_order=0, min_tran=0, min_peak=0, dbg=0, **
             n_op = n_top                                                  # :164-166
         elif 0 < min_order < 1:
             n_new = int(np.ceil(n * (1 - min_order) + n_top * min_order)) # :169-173
-            h, status = fir_ap_cvx(n_new, f, a, d, lam, Peak, **solver_kw)
+            h, status = solve1(n_new, f)
             n_op = n_new
         else:
             raise ValueError("invalid input of min_order")                # :174-176
@@ -639,7 +681,7 @@ def fir_linprog(n, f, a, d, h0=None, dbg=0, return_info=False, **solver_kw):
     n = int(n)
     p = assemble_fir_linprog(n, f, a, d)
     if p is None:
-        return np.zeros(0), "Failed"                                      # :68-72
+        return (np.zeros(0), "Failed", dict(info=None)) if return_info else (np.zeros(0), "Failed")   # :68-72
     M, N = p["w"].size, p["col_type"].size
     c = _lp_objective(p)
     arr = lambda v: np.ascontiguousarray(v, dtype=np.float64)            # noqa: E731
@@ -670,6 +712,19 @@ def fir_linprog(n, f, a, d, h0=None, dbg=0, return_info=False, **solver_kw):
     st = "Solved" if ok else "Failed"
     if return_info:
         return h, st, dict(x=z[:, 0].copy(), info=info[0].copy(), problem=p, c=c)
+    return h, st
+
+
+def _fir_linprog_decided(n, f, a, d, h0=None, dbg=0, **solver_kw):
+    """fir_linprog as a bisection probe: an iteration-limit ending (status 3) is retried with more iterations, see
+    fir_ap_cvx_decided."""
+    import warnings
+    h, st, ex = fir_linprog(n, f, a, d, h0, dbg, return_info=True, **solver_kw)
+    if isinstance(ex, dict) and ex.get("info") is not None and int(ex["info"][0]) == 3:
+        h, st, ex = fir_linprog(n, f, a, d, h0, dbg, return_info=True, **_retry_kw(solver_kw))
+        if int(ex["info"][0]) == 3:
+            warnings.warn(f"fir_linprog probe at n = {n} stayed undecided at the iteration limit and is treated as 'Failed'",
+                          UndecidedProbe, stacklevel=2)
     return h, st
 
 
@@ -729,7 +784,7 @@ def _min_order_search(n, f, a, d, even_odd, solve, pick_longer):
 
 def fir_min_order_linprog(n, f, a, d, even_odd=0, dbg=0, **solver_kw):
     """[h, status] = fir_min_order_linprog(n, f, a, d, even_odd, dbg) — ss/fir_min_order_linprog.m:54-234."""
-    return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: fir_linprog(nt, f, a, d, hw, dbg, **solver_kw),
+    return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: _fir_linprog_decided(nt, f, a, d, hw, dbg, **solver_kw),
                              pick_longer=False)
 
 
@@ -740,7 +795,7 @@ def fir_min_order(n, f, a, d, even_odd=0, a_min=None, dbg=0, **solver_kw):
     be reproduced; per BASELINE.json's north star the search is re-expressed as LP feasibility: the same
     bisection (and the same 'longer of odd/even' selection, :222-226) with fir_linprog probes.  a_min is
     fir_pm's minimum-amplitude option and has no LP counterpart; it is accepted and ignored."""
-    return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: fir_linprog(nt, f, a, d, hw, dbg, **solver_kw),
+    return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: _fir_linprog_decided(nt, f, a, d, hw, dbg, **solver_kw),
                              pick_longer=True)
 
 
@@ -835,7 +890,8 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, oversamp=10, 
     # problem is "minimise Peak" with the energy as a 1e-6 tie-break, and a first-order method needs O(1) weights
     oscale = float(solver_kw.pop("objective_scale", 0.0)) or max(1.0, float(gw[0]), float(lam[0]))
     gw, lam = gw / oscale, lam / oscale
-    one = one / oscale if minimax else one
+    if minimax:
+        one /= oscale                                                     # in place: blocks.group2_w already points at it
     big = 2.0 * p["radius"].max() + 2.0 * np.abs(p["center"]).max() + (2.0 if minimax else 0.0)
     c = np.zeros((N, 1))
     bl, bu = np.full((N, 1), -big), np.full((N, 1), big)
@@ -854,7 +910,8 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, oversamp=10, 
                                      float(kw["eps_gap"]), _dp(z), _dp(info), None))
     info[0, 2] *= oscale                                                  # objective / dual value / bound in the caller's units
     info[0, 3] *= oscale
-    info[0, 6] *= oscale
+    if abs(info[0, 6]) < 1e300:
+        info[0, 6] *= oscale
     ok = info[0, 0] == 1.0
     x = z[:, 0]
     h = x[:n] + 1j * x[n:] if ok else np.zeros(0)                         # :209
