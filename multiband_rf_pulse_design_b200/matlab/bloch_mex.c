@@ -56,5 +56,9 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
                    mxGetPr(plhs[0]), mxGetPr(plhs[1]), mxGetPr(plhs[2]), dims, MBRF_GAMMA) != MBRF_OK)
         mexErrMsgTxt(mbrf_last_error());
 
-    for (i = 0; i < 3; i++) mxSetDimensions(plhs[i], dims, dims[3]);                     /* blochC.c:880-904 */
+    {   /* blochC.c:880-904; mxSetDimensions takes mwSize (size_t on 64-bit MATLAB / Octave), not int */
+        mwSize d[3];
+        d[0] = (mwSize)dims[0]; d[1] = (mwSize)dims[1]; d[2] = (mwSize)dims[2];
+        for (i = 0; i < 3; i++) mxSetDimensions(plhs[i], d, (mwSize)dims[3]);
+    }
 }

@@ -70,12 +70,21 @@ static inline mxArray *mxCreateString(const char *s)
     return a;
 }
 
-static inline int mxSetDimensions(mxArray *a, const int *dims, int ndim)
+/* The real API is  int mxSetDimensions(mxArray *, const mwSize *dims, mwSize ndim)  with mwSize = size_t on 64-bit MATLAB
+ * and 64-bit-index Octave.  The reference's 1990s sources pass an `int` array (blochC.c:885-903) -- they are compiled with
+ * -DMEX_STUB_INT_DIMS (oracle/Makefile) so that the stub reads what they write; everything else (our gateways) compiles
+ * against the real signature, so a gateway that passes an int array does not compile cleanly here either. */
+#ifdef MEX_STUB_INT_DIMS
+typedef int mex_stub_dim_t;
+#else
+typedef mwSize mex_stub_dim_t;
+#endif
+static inline int mxSetDimensions(mxArray *a, const mex_stub_dim_t *dims, mex_stub_dim_t ndim)
 {
     int i; size_t tail = 1;
-    a->ndim = ndim;
-    for (i = 0; i < 3; i++) a->dims[i] = i < ndim ? dims[i] : 1;
-    for (i = 1; i < ndim; i++) tail *= (size_t)dims[i];
+    a->ndim = (int)ndim;
+    for (i = 0; i < 3; i++) a->dims[i] = i < (int)ndim ? (int)dims[i] : 1;
+    for (i = 1; i < (int)ndim; i++) tail *= (size_t)dims[i];
     a->m = (size_t)dims[0]; a->n = tail;
     return 0;
 }

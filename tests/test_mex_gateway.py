@@ -16,7 +16,7 @@ MEX = os.path.join(ROOT, "multiband_rf_pulse_design_b200", "matlab")
 @pytest.fixture(scope="module")
 def gateways(mbrf):
     subprocess.check_call(["make", "-s", "-C", MEX, "check"])
-    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "b2a", "ab2rf", "fmp2")}
+    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "fir_solve", "b2a", "ab2rf", "fmp2")}
 
 
 def test_gateways_link_and_report_errors_like_the_reference(gateways, oracle, mbrf):
@@ -97,6 +97,128 @@ def test_fir_pdhg_gateway_solves_like_the_python_mirror(gateways, oracle, mbrf):
     assert k["outer_obj"] * (1 - 1e-4) <= info[2, 0] <= k["inner_obj"] * (1 + 1e-4)   # x1 + obj*ripple_stop
     out, err = oracle.mex_call(gateways["fir_pdhg"], 2, w_row)
     assert out is None and err.startswith("Usage:")
+
+
+E = np.zeros((0, 0))        # MATLAB []
+
+
+@pytest.mark.gpu
+def test_fir_solve_gateway_interior_point_like_fir_ap_cvx_batch_m(gateways, oracle, mbrf):
+    """fir_solve_mex (method 1 = interior point) with the arguments matlab/fir_ap_cvx_batch.m builds for ONE design
+    (dim-by-B matrices, 1-based rows, the 9-entry blocks vector): the optimum of the HiGHS-bracketed golden."""
+    import json
+    from multiband_rf_pulse_design_b200 import fir
+    k = json.load(open(os.path.join(ROOT, "tests", "golden", "fir_ap_known.json")))["lowpass_n24_obj10"]
+    n, obj, peak = k["n"], k["obj"], k["peak"]
+    p = fir.assemble_fir_ap(n, k["f"], k["a"], k["d"], obj, peak)
+    allw = np.unique(p["w"])                                        # fir_ap_cvx_batch.m: union grid, ismember positions
+    pos = np.searchsorted(allw, p["w"])
+    M1 = allw.size
+    srows = np.unique(pos[p["stop"]])
+    M, N = M1 + srows.size, 2 * n - 1
+    lo = np.full((M, 1), -np.inf); hi = np.full((M, 1), np.inf)
+    np.maximum.at(lo[:, 0], pos, p["lo"]); np.minimum.at(hi[:, 0], pos, p["hi"])
+    hi[M1:, 0] = 0.0
+    w_row = np.concatenate([allw, allw[srows]])
+    col_type = np.concatenate([[0], np.ones(n - 1), 2 * np.ones(n - 1)])
+    col_kappa = np.concatenate([[0], np.arange(1, n), np.arange(1, n)])
+    col_amp = np.concatenate([[1], 2 * np.ones(2 * n - 2)])
+    c = np.zeros((N, 1)); c[0] = 1
+    bl = np.full((N, 1), -np.inf); bu = np.full((N, 1), np.inf)
+    bl[0], bu[0] = -n * peak, n * peak
+    rho = ((n - np.arange(2, n + 1) + 1) * peak).reshape(-1, 1)
+    blocks = np.array([M1 + 1, srows.size, 0, 0, 0, 0, 0, 0, 0], float)
+    block_w = np.array([[obj], [0], [0], [0]], float)
+    args = [1.0, w_row, E, E, col_type, col_kappa, col_amp, E, np.arange(2, n + 1, dtype=float), np.arange(n + 1, 2 * n, dtype=float),
+            c, lo, hi, bl, bu, rho, E, np.array([100, 1e-7, 2e-6, 1e-12]), blocks, block_w]
+    outs, err = oracle.mex_call(gateways["fir_solve"], 2, *args)
+    assert err is None, err
+    z, info = outs
+    assert z.shape == (N, 1) and info.shape == (8, 1) and info[0, 0] == 1.0
+    assert k["outer_obj"] * (1 - 1e-4) <= info[2, 0] <= k["inner_obj"] * (1 + 1e-4)
+    # the first-order solver through the same gateway and the same arguments
+    args[0] = 0.0
+    args[16] = np.array([n * peak + obj * p["hi"][p["stop"]].max()])
+    args[17] = np.array([200000, 64, 8e-7, 1e-4, 5e-5])
+    (z2, info2), err = oracle.mex_call(gateways["fir_solve"], 2, *args)
+    assert err is None and info2[0, 0] == 1.0 and abs(info2[2, 0] - info[2, 0]) <= 2e-4 * info[2, 0]
+    # misuse is reported through mexErrMsgTxt
+    bad = list(args); bad[0] = 1.0; bad[2] = np.zeros(M)           # a row phase with the interior-point solver
+    out, err = oracle.mex_call(gateways["fir_solve"], 2, *bad)
+    assert out is None and "interior-point solver takes" in err
+    out, err = oracle.mex_call(gateways["fir_solve"], 2, *args[:5])
+    assert out is None and err.startswith("Usage:")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["qp_n16_obj1", "mm_n16_a"])
+def test_fir_solve_gateway_like_fir_qp_cvx_m(gateways, oracle, case):
+    """fir_solve_mex (method 0) with the arguments matlab/fir_qp_cvx.m builds -- row phases / scales, explicit identity
+    entries, the blocks vector, 4-by-B weights, objective scaling -- for the scalar-obj form and the minimax form:
+    the SciPy trust-constr known answers of tests/golden (the same the Python mirror is held to)."""
+    import json
+    minimax = case.startswith("mm")
+    k = json.load(open(os.path.join(ROOT, "tests", "golden", "fir_qp_minimax_known.json" if minimax else "fir_qp_known.json")))[case]
+    n, kk, obj = k["n"], k["k"], np.atleast_1d(np.asarray(k["obj"], float))
+    f = np.asarray(k["f"], float) * np.pi; a = np.asarray(k["a"], float); d = np.asarray(k["d"], float)
+    w = np.sort(np.concatenate([np.linspace(-np.pi, np.pi, n * 10), f]))                    # fir_qp_cvx.m:35-38
+    inband = np.zeros(w.size, bool); Mb, Db, bidx = [], [], []
+    for b in range(len(f) // 2):
+        e0, e1 = f[2 * b], f[2 * b + 1]
+        sel = np.nonzero((w >= e0) & (w <= e1))[0]
+        amp = np.full(sel.size, a[2 * b]) if e0 == e1 else a[2 * b] + (a[2 * b + 1] - a[2 * b]) * (w[sel] - e0) / (e1 - e0)
+        bidx.append(sel); Mb.append(amp); Db.append(np.full(sel.size, d[b])); inband[sel] = True
+    bidx, Mb, Db = map(np.concatenate, (bidx, Mb, Db))
+    wband, wtran = w[bidx], w[~inband]
+    Hd = Mb * np.exp(1j * (kk * wband ** 2 - wband * (n - 1) / 2))
+    wall = np.concatenate([wband, wtran]); m, nb = wall.size, wband.size
+    centre = np.concatenate([Hd, np.zeros(wtran.size)]); radius = np.concatenate([Db, np.full(wtran.size, 1 + 5 * d.max())])
+    N, M = 2 * n, 2 * m + 2 * n
+    w_row = np.concatenate([np.repeat(wall, 2), np.zeros(2 * n)])
+    row_phase = np.concatenate([np.tile([0, np.pi / 2], m), np.zeros(2 * n)])
+    row_scale = np.concatenate([np.ones(2 * m), np.zeros(2 * n)])
+    col_type = np.concatenate([np.ones(n), 2 * np.ones(n)]); col_kappa = np.concatenate([np.arange(n), np.arange(n)]).astype(float)
+    entries = np.column_stack([2 * m + np.arange(1, 2 * n + 1), np.column_stack([np.arange(1, n + 1), n + np.arange(1, n + 1)]).ravel(),
+                               np.ones(2 * n)]).astype(float)
+    lo = np.full((M, 1), -np.inf); hi = np.full((M, 1), np.inf)
+    blocks = np.zeros(9)
+    if minimax:
+        row_scale[0:2 * nb:2] = 1 / Db; row_scale[1:2 * nb:2] = 1 / Db
+        lo[0:2 * nb:2, 0] = Hd.real / Db; lo[1:2 * nb:2, 0] = Hd.imag / Db
+        lo[2 * nb:2 * m, 0] = 0; hi[2 * nb:2 * m:2, 0] = 1.1
+        blocks[[7, 8]] = [1, nb]; blocks[[2, 3]] = [2 * nb + 1, m - nb]
+        gw, lam, g2 = obj[1], obj[0], 1.0
+    else:
+        lo[0:2 * m:2, 0] = centre.real; lo[1:2 * m:2, 0] = centre.imag; hi[0:2 * m:2, 0] = radius
+        blocks[[2, 3]] = [1, m]
+        gw, lam, g2 = obj[0], 1.0, 0.0
+    big = 2 * radius.max() + 2 * np.abs(centre).max() + 2 * minimax
+    blocks[[4, 5]] = [2 * m + 1, n]; blocks[6] = N
+    oscale = max(1.0, gw, lam)
+    block_w = np.array([[0.0], [gw], [lam], [g2]]) / oscale
+    outs, err = oracle.mex_call(gateways["fir_solve"], 2, 0.0, w_row, row_phase, row_scale, col_type, col_kappa, np.ones(N), entries,
+                                E, E, np.zeros((N, 1)), lo, hi, np.full((N, 1), -big), np.full((N, 1), big), E, E,
+                                np.array([400000, 64, 8e-7, 1e-4, 5e-5]), blocks, block_w)
+    assert err is None, err
+    z, info = outs
+    assert info[0, 0] == 1.0
+    assert abs(info[2, 0] * oscale - k["objective"]) <= 1e-4 * k["objective"]
+
+
+@pytest.mark.gpu
+def test_fir_solve_gateway_like_fir_linprog_m(gateways, oracle):
+    """fir_solve_mex (method 1) with the arguments matlab/fir_linprog.m builds (no bounds, no pairs, no blocks: all [])
+    for a complex even-length linear-phase design: the HiGHS optimum."""
+    import json
+    from multiband_rf_pulse_design_b200 import fir
+    k = json.load(open(os.path.join(ROOT, "tests", "golden", "fir_lp_known.json")))["lp_cplx_even_n40"]
+    p = fir.assemble_fir_linprog(k["n"], k["f"], k["a"], k["d"])
+    c = fir._lp_objective(p).reshape(-1, 1)
+    outs, err = oracle.mex_call(gateways["fir_solve"], 2, 1.0, p["w"], E, E, p["col_type"].astype(float), p["col_kappa"], p["col_amp"], E,
+                                E, E, c, p["lo"].reshape(-1, 1), p["hi"].reshape(-1, 1), E, E, E, E, np.array([100, 1e-7, 2e-6, 1e-12]), E, E)
+    assert err is None, err
+    z, info = outs
+    assert info[0, 0] == 1.0 and abs(info[2, 0] - k["obj"]) <= 1e-4 * abs(k["obj"])
 
 
 def test_postprocessing_gateways_usage_errors(gateways, oracle):
