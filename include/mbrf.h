@@ -303,7 +303,8 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
                        double *info_out);
 int mbrf_ipm_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
 /* 0: precision of the Newton systems (0 fp64, 1 double-double, 2 auto = double-double once mu < switch * mu0; default 2),
- * 1: that switch (default 1e-3), 2: refinement steps per solve (default 1), 3: trace the first `value` designs on stderr */
+ * 1: that switch (default 1e-3), 2: refinement steps per solve in the double-double phase (default 1), 3: trace the first `value`
+ * designs on stderr, 4: refinement steps per solve in the fp64 phase (default 0) */
 int mbrf_ipm_set_option(int which, double value);
 /* Diagnostic: the batched Cholesky of the interior-point solver alone -- B matrices of order nv, double-double (use_dd) or
  * fp64, timed with CUDA events over `reps` launches (mean ms per launch): the kernel bench.py's solver roofline is quoted on. */

@@ -98,6 +98,18 @@ DD_FN dd dd_fnma(dd a, dd b, dd c)
     s.lo = DD_ADD(s.lo, DD_SUB(c.lo, p.lo));
     return quick_two_sum(s.hi, s.lo);
 }
+// the same inside a long accumulation: the sum is kept UN-normalised (hi exact partial sums, lo the collected errors) and
+// renormalised once at the end (dd_renorm) -- 12 instead of 15 FP64 instructions per term
+DD_FN dd dd_fnma_acc(dd a, dd b, dd c)
+{
+    const double p = DD_MUL(a.hi, b.hi);
+    double e = DD_FMA(a.hi, b.hi, -p);
+    e = DD_FMA(a.hi, b.lo, e);
+    e = DD_FMA(a.lo, b.hi, e);
+    const dd s = two_sum(c.hi, -p);
+    return dd{s.hi, DD_ADD(c.lo, DD_SUB(s.lo, e))};
+}
+DD_FN dd dd_renorm(dd a) { return two_sum(a.hi, a.lo); }
 DD_FN dd dd_div(dd a, dd b)
 {
     const double q1 = DD_DIV(a.hi, b.hi);
@@ -129,6 +141,8 @@ template <> struct Num<double> {
     static DD_FN double mul(double a, double b) { return a * b; }
     static DD_FN double mul_d(double a, double b) { return a * b; }
     static DD_FN double fnma(double a, double b, double c) { return DD_FMA(-a, b, c); }
+    static DD_FN double fnma_acc(double a, double b, double c) { return DD_FMA(-a, b, c); }
+    static DD_FN double renorm(double a) { return a; }
     static DD_FN double div(double a, double b) { return a / b; }
     static DD_FN double sqrt_(double a) { return sqrt(a); }
     static DD_FN double neg(double a) { return -a; }
@@ -144,6 +158,8 @@ template <> struct Num<dd> {
     static DD_FN dd mul(dd a, dd b) { return dd_mul(a, b); }
     static DD_FN dd mul_d(dd a, double b) { return dd_mul_d(a, b); }
     static DD_FN dd fnma(dd a, dd b, dd c) { return dd_fnma(a, b, c); }
+    static DD_FN dd fnma_acc(dd a, dd b, dd c) { return dd_fnma_acc(a, b, c); }
+    static DD_FN dd renorm(dd a) { return dd_renorm(a); }
     static DD_FN dd div(dd a, dd b) { return dd_div(a, b); }
     static DD_FN dd sqrt_(dd a) { return dd_sqrt(a); }
     static DD_FN dd neg(dd a) { return dd_neg(a); }

@@ -67,6 +67,7 @@ struct Ctl {                 // per-design scalars (device)
     double status;           // 0 running, 1 optimal, 2 primal infeasible (certificate), 3 iteration limit / numerical failure, 4 unbounded
     double iters, chol_fail;
     double merit_best, tau_best, t_best, pcost_best, dcost_best, dres_best, improved, use_best;   // best iterate seen (see SC_PRE)
+    double merit_ref, iter_ref;      // stall detection: the last iteration at which the merit had halved
 };
 
 struct P {                   // everything the kernels need, passed by value
@@ -676,10 +677,16 @@ __global__ void scalars_kernel(P p, int phase, int r, int iter)
             ct.merit_best = merit; ct.tau_best = tau; ct.t_best = ct.t; ct.pcost_best = ct.pcost; ct.dcost_best = ct.dcost;
             ct.dres_best = ct.dres; ct.improved = 1.0;
         }
+        // progress = the optimality merit OR the quality of the emerging infeasibility certificate halves
+        const double infm = hz < 0.0 ? sqrt(acc[A_GTZ2 * Bp + b] + gtzt * gtzt) / (-hz) / p.feastol : INFINITY;
+        const double prog = fmin(merit, infm);
+        if (iter == 0 || prog < 0.5 * ct.merit_ref) { ct.merit_ref = prog; ct.iter_ref = iter; }
+        const bool stalled = iter - ct.iter_ref > 30.0;       // no halving of the merit in 30 iterations: a design at the edge of
+                                                              // feasibility that neither converges nor yields a certificate
         if (merit <= 1.0) st = 1;
         else if (hz < 0.0 && sqrt(acc[A_GTZ2 * Bp + b] + gtzt * gtzt) / (-hz) <= p.feastol) st = 2;
         else if (cx < 0.0 && sqrt(acc[A_GXS2 * Bp + b]) / (-cx) <= p.feastol) st = 4;
-        else if (iter >= p.max_iter || ct.chol_fail > 2.0 || merit == INFINITY || (ct.merit_best <= 10.0 && merit > 1e3 * ct.merit_best)) {
+        else if (iter >= p.max_iter || stalled || ct.chol_fail > 2.0 || merit == INFINITY || (ct.merit_best <= 10.0 && merit > 1e3 * ct.merit_best)) {
             st = 3;
             if (ct.merit_best <= 10.0) { st = 1; ct.use_best = 1.0; }
         }
@@ -934,8 +941,9 @@ assemble_kernel(P p, const T *__restrict__ MC, const T *__restrict__ MS, const T
 // ------------------------------------------------------------------------------------------------------------------
 // batched Cholesky, one CTA of 256 threads per design: right-looking, 32-wide panels, 64 x 64 trailing tiles
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int CHOL_THREADS = 512;   // 16 warps: 4 per scheduler keep the FP64 pipe issuing through the long dd dependency chains
 template <typename T>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
 cholesky_kernel(P p, T *__restrict__ Hall)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -943,14 +951,14 @@ cholesky_kernel(P p, T *__restrict__ Hall)
     if (b >= p.B || p.ctl[b].status != 0.0) return;
     T *H = Hall + (size_t)b * p.NVp * p.NVp;
     const int n = p.NVp, tid = threadIdx.x;
-    constexpr int LDS_ = PANEL + 1;
+    constexpr int LDS_ = PANEL + 1, NT = CHOL_THREADS;
     T *Ld = reinterpret_cast<T *>(smem_raw);                 // [PANEL][PANEL+1] diagonal block
     T *Xs = Ld + PANEL * LDS_;                               // [256][PANEL+1] panel rows / [2][PANEL][TILE] update tiles
     __shared__ int fail;
     if (tid == 0) fail = 0;
     for (int k0 = 0; k0 < n; k0 += PANEL) {
         // ---- diagonal block ----
-        for (int e = tid; e < PANEL * PANEL; e += 256) {
+        for (int e = tid; e < PANEL * PANEL; e += NT) {
             const int r = e / PANEL, c = e % PANEL;
             Ld[r * LDS_ + c] = c <= r ? H[(size_t)(k0 + r) * n + k0 + c] : Num<T>::zero();
         }
@@ -965,81 +973,106 @@ cholesky_kernel(P p, T *__restrict__ Hall)
             if (tid > j && tid < PANEL) Ld[tid * LDS_ + j] = Num<T>::div(Ld[tid * LDS_ + j], Ld[j * LDS_ + j]);
             __syncthreads();
             // trailing part of the block: entries (r, c), j < c <= r < PANEL
-            for (int e = tid; e < PANEL * PANEL; e += 256) {
+            for (int e = tid; e < PANEL * PANEL; e += NT) {
                 const int r = e / PANEL, c = e % PANEL;
                 if (c > j && c <= r) Ld[r * LDS_ + c] = Num<T>::fnma(Ld[r * LDS_ + j], Ld[c * LDS_ + j], Ld[r * LDS_ + c]);
             }
             __syncthreads();
         }
-        for (int e = tid; e < PANEL * PANEL; e += 256) {
+        for (int e = tid; e < PANEL * PANEL; e += NT) {
             const int r = e / PANEL, c = e % PANEL;
             if (c <= r) H[(size_t)(k0 + r) * n + k0 + c] = Ld[r * LDS_ + c];
         }
         const int rows = n - k0 - PANEL;
         if (rows <= 0) break;
-        // ---- panel: X L11' = A21, one thread per row, 256 rows per pass ----
+        // ---- panel: X L11' = A21.  Two threads per row (256 rows per pass): the pair splits every inner sum in halves ----
         for (int r0 = 0; r0 < rows; r0 += 256) {
             const int nr = min(256, rows - r0);
             __syncthreads();
-            for (int e = tid; e < nr * PANEL; e += 256) {
+            for (int e = tid; e < nr * PANEL; e += NT) {
                 const int r = e / PANEL, c = e % PANEL;
                 Xs[r * LDS_ + c] = H[(size_t)(k0 + PANEL + r0 + r) * n + k0 + c];
             }
             __syncthreads();
-            if (tid < nr) {
-                T *xr = Xs + tid * LDS_;
+            {
+                const int row = tid >> 1, half = tid & 1;
+                T *xr = Xs + (row < nr ? row : 0) * LDS_;
                 for (int j = 0; j < PANEL; ++j) {
-                    T s = xr[j];
-                    for (int l = 0; l < j; ++l) s = Num<T>::fnma(xr[l], Ld[j * LDS_ + l], s);
-                    xr[j] = Num<T>::div(s, Ld[j * LDS_ + j]);
+                    // partial sums over l = half, half + 2, ... < j, combined through a shuffle of the pair
+                    T s = Num<T>::zero();
+                    if (row < nr)
+                        for (int l = half; l < j; l += 2) s = Num<T>::fnma_acc(xr[l], Ld[j * LDS_ + l], s);
+                    s = Num<T>::renorm(s);
+                    T o;
+                    if constexpr (sizeof(T) == sizeof(dd)) {
+                        o.hi = __shfl_xor_sync(0xffffffffu, s.hi, 1);
+                        o.lo = __shfl_xor_sync(0xffffffffu, s.lo, 1);
+                    } else {
+                        o = __shfl_xor_sync(0xffffffffu, s, 1);
+                    }
+                    if (row < nr && half == 0) xr[j] = Num<T>::div(Num<T>::add(xr[j], Num<T>::add(s, o)), Ld[j * LDS_ + j]);
+                    __syncwarp();
                 }
             }
             __syncthreads();
-            for (int e = tid; e < nr * PANEL; e += 256) {
+            for (int e = tid; e < nr * PANEL; e += NT) {
                 const int r = e / PANEL, c = e % PANEL;
                 H[(size_t)(k0 + PANEL + r0 + r) * n + k0 + c] = Xs[r * LDS_ + c];
             }
         }
         __syncthreads();
-        // ---- trailing update: A22[I][J] -= P[I] P[J]', tiles of 64 x 64, thread = 4 x 4 outputs ----
+        // ---- trailing update: A22[I][J] -= P[I] P[J]', tiles of 64 x 64, thread = 4 x 2 outputs ----
         T *Pi = Xs, *Pj = Xs + PANEL * TILE;                 // k-major: [PANEL][TILE]
         const int base = k0 + PANEL;
         const int nt = (rows + TILE - 1) / TILE;
-        const int ty = tid >> 4, tx = tid & 15;
+        const int ty = tid >> 5, tx = tid & 31;              // a warp shares its 4 rows (broadcast), lane tx owns columns tx and tx + 32 (conflict-free 16-byte loads)
         for (int ti = 0; ti < nt; ++ti)
             for (int tj = 0; tj <= ti; ++tj) {
                 __syncthreads();
-                for (int e = tid; e < TILE * PANEL; e += 256) {
+                for (int e = tid; e < TILE * PANEL; e += NT) {
                     const int r = e / PANEL, c = e % PANEL;
                     const int gi = base + ti * TILE + r, gj = base + tj * TILE + r;
                     Pi[c * TILE + r] = gi < n ? H[(size_t)gi * n + k0 + c] : Num<T>::zero();
                     Pj[c * TILE + r] = gj < n ? H[(size_t)gj * n + k0 + c] : Num<T>::zero();
                 }
                 __syncthreads();
-                T acc[4][4];
+                T acc[4][2];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int gi = base + ti * TILE + ty * 4 + i, gj = base + tj * TILE + tx * 4 + j;
+                    for (int j = 0; j < 2; ++j) {
+                        const int gi = base + ti * TILE + ty * 4 + i, gj = base + tj * TILE + tx + 32 * j;
                         acc[i][j] = (gi < n && gj <= gi) ? H[(size_t)gi * n + gj] : Num<T>::zero();
                     }
-#pragma unroll 4
-                for (int k = 0; k < PANEL; ++k) {
-                    T a[4], bb[4];
+                // on a diagonal tile the warps whose rows lie in its upper half own no entry of the columns tx + 32 (above the diagonal)
+                const bool upper_half_of_diag = ti == tj && ty < 8;
+                if (upper_half_of_diag) {
+#pragma unroll 8
+                    for (int k = 0; k < PANEL; ++k) {
+                        const T b0 = Pj[k * TILE + tx];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { a[i] = Pi[k * TILE + ty * 4 + i]; bb[i] = Pj[k * TILE + tx * 4 + i]; }
+                        for (int i = 0; i < 4; ++i) acc[i][0] = Num<T>::fnma_acc(Pi[k * TILE + ty * 4 + i], b0, acc[i][0]);
+                    }
+                } else {
+#pragma unroll 8
+                    for (int k = 0; k < PANEL; ++k) {
+                        T a[4], bb[2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                        for (int i = 0; i < 4; ++i) a[i] = Pi[k * TILE + ty * 4 + i];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] = Num<T>::fnma(a[i], bb[j], acc[i][j]);
+                        for (int j = 0; j < 2; ++j) bb[j] = Pj[k * TILE + tx + 32 * j];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) acc[i][j] = Num<T>::fnma_acc(a[i], bb[j], acc[i][j]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int gi = base + ti * TILE + ty * 4 + i, gj = base + tj * TILE + tx * 4 + j;
-                        if (gi < n && gj <= gi) H[(size_t)gi * n + gj] = acc[i][j];
+                    for (int j = 0; j < 2; ++j) {
+                        const int gi = base + ti * TILE + ty * 4 + i, gj = base + tj * TILE + tx + 32 * j;
+                        if (gi < n && gj <= gi) H[(size_t)gi * n + gj] = Num<T>::renorm(acc[i][j]);
                     }
             }
         __syncthreads();
@@ -1149,7 +1182,7 @@ __global__ void spd_fill_kernel(T *Hall, int n, int B)
 
 static int g_precision = 2;          // 0 fp64, 1 double-double, 2 auto (double-double once mu is small)
 static double g_dd_switch = 1e-3;    // auto: double-double when min over live designs of mu / mu0 falls below this
-static int g_refine = 1;
+static int g_refine = 1, g_refine_fp64 = 0;
 static int g_verbose = 0;
 
 }  // namespace ipm
@@ -1167,6 +1200,7 @@ int mbrf_ipm_set_option(int which, double value)
     case 1: if (!(value > 0)) return MBRF_EINVAL; g_dd_switch = value; break;
     case 2: if (value < 0 || value > 4) return MBRF_EINVAL; g_refine = (int)value; break;
     case 3: g_verbose = (int)value; break;
+    case 4: if (value < 0 || value > 4) return MBRF_EINVAL; g_refine_fp64 = (int)value; break;
     default: return MBRF_EINVAL;
     }
     return MBRF_OK;
@@ -1200,8 +1234,8 @@ int mbrf_ipm_cholesky_bench(int nv, int B, int use_dd, int reps, float *ms)
     for (int r = 0; r <= reps; ++r) {                            // first pass: warm-up
         MBRF_CUDA(cudaMemcpyAsync(buf + hb, buf, hb, cudaMemcpyDeviceToDevice, 0));
         MBRF_CUDA(cudaEventRecord(e0, 0));
-        if (use_dd) cholesky_kernel<dd><<<B, 256, sm>>>(p, (dd *)(buf + hb));
-        else cholesky_kernel<double><<<B, 256, sm>>>(p, (double *)(buf + hb));
+        if (use_dd) cholesky_kernel<dd><<<B, CHOL_THREADS, sm>>>(p, (dd *)(buf + hb));
+        else cholesky_kernel<double><<<B, CHOL_THREADS, sm>>>(p, (double *)(buf + hb));
         MBRF_LAUNCH_CHECK();
         MBRF_CUDA(cudaEventRecord(e1, 0));
         MBRF_CUDA(cudaEventSynchronize(e1));
@@ -1473,7 +1507,7 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
             if (p.ns) { moments_kernel<dd><<<gb, 256, 0, st>>>(p, p.DS, p.srow0, p.srow0 + p.ns, nlagB, (dd *)dBC, (dd *)dBS); MBRF_LAUNCH_CHECK(); }
             assemble_kernel<dd><<<dim3(B, ay), 256, 0, st>>>(p, (dd *)dMC, (dd *)dMS, (dd *)dBC, (dd *)dBS, nsplit_hint, nlagM, nlagB, (dd *)dH);
             MBRF_LAUNCH_CHECK();
-            cholesky_kernel<dd><<<B, 256, sm_chol_dd, st>>>(p, (dd *)dH);
+            cholesky_kernel<dd><<<B, CHOL_THREADS, sm_chol_dd, st>>>(p, (dd *)dH);
             MBRF_LAUNCH_CHECK();
         } else {
             moments_kernel<double><<<gm, 256, 0, st>>>(p, p.D, 0, M, nlagM, (double *)dMC, (double *)dMS);
@@ -1481,7 +1515,7 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
             if (p.ns) { moments_kernel<double><<<gb, 256, 0, st>>>(p, p.DS, p.srow0, p.srow0 + p.ns, nlagB, (double *)dBC, (double *)dBS); MBRF_LAUNCH_CHECK(); }
             assemble_kernel<double><<<dim3(B, ay), 256, 0, st>>>(p, (double *)dMC, (double *)dMS, (double *)dBC, (double *)dBS, nsplit_hint, nlagM, nlagB, (double *)dH);
             MBRF_LAUNCH_CHECK();
-            cholesky_kernel<double><<<B, 256, sm_chol_d, st>>>(p, (double *)dH);
+            cholesky_kernel<double><<<B, CHOL_THREADS, sm_chol_d, st>>>(p, (double *)dH);
             MBRF_LAUNCH_CHECK();
         }
         return MBRF_OK;
@@ -1499,7 +1533,9 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
         scal(SC_RHST, r, 0); MBRF_LAUNCH_CHECK();
         if (int rc = trsolve(p.RHS[r], p.RHST[r], p.UX[r], p.UT[r], 0)) return rc;
         if (int rc = gemm_K(p.UX[r], p.GUX[r])) return rc;
-        for (int k = 0; k < g_refine; ++k) {
+        // the refinement step matters once the weights spread (the double-double phase); the early fp64 iterations only need a
+        // direction that makes progress
+        for (int k = 0; k < (use_dd ? g_refine : g_refine_fp64); ++k) {
             rows(PH_REFINE, r); MBRF_LAUNCH_CHECK();
             if (int rc = gemm_KT(p.YR, p.KTQ)) return rc;
             cols(PC_REFINE, r); MBRF_LAUNCH_CHECK();
