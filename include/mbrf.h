@@ -126,7 +126,8 @@ int mbrf_bloch(const double *b1r, const double *b1i, int ntime,
  *   m0x,m0y,m0z   : initial magnetisation indexed by LOCAL spin (s - spin0) with stride
  *                   m0_stride doubles, or all NULL for (0,0,1).
  *   mx,my,mz      : outputs indexed [t + ntout*(s - spin0)].
- *   workspace     : device scratch of mbrf_bloch_workspace_bytes(ntime) bytes.
+ *   workspace     : device scratch of mbrf_bloch_workspace_bytes(ntime) bytes, 16-byte aligned (the kernels stream it with
+ *                   cp.async.bulk); a misaligned pointer is MBRF_EINVAL.  The same holds for mbrf_abr_device.
  */
 unsigned long long mbrf_bloch_workspace_bytes(int ntime);
 int mbrf_bloch_device(const double *b1real, const double *b1imag,

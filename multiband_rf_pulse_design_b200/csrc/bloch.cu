@@ -531,6 +531,7 @@ int mbrf_bloch_device(const double *b1real, const double *b1imag, const double *
     }
     if ((m0x || m0y || m0z) && !(m0x && m0y && m0z)) { set_error("bloch: m0x,m0y,m0z must be all set or all NULL"); return MBRF_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (((uintptr_t)workspace & 15) != 0) { set_error("bloch: workspace must be 16-byte aligned (TMA bulk copies)"); return MBRF_EINVAL; }
     double *ws = (double *)workspace;
     if (ntime == 0) {
         // no samples: modes 0/2 leave M untouched (mode 2 has zero outputs); steady state of nothing is 0/0
@@ -571,6 +572,7 @@ int mbrf_bloch_scale_sweep_device(const double *b1real, const double *b1imag, co
         return MBRF_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (((uintptr_t)workspace & 15) != 0) { set_error("bloch: workspace must be 16-byte aligned (TMA bulk copies)"); return MBRF_EINVAL; }
     double *ws = (double *)workspace;
     if (int rc = run_prep(b1real, b1imag, nullptr, nullptr, nullptr, tsteps, ntime, t1, t2, gamma, ws, st)) return rc;
     Params p;

@@ -149,6 +149,7 @@ static int solve_impl(const double *w_row, const double *row_phase, const double
     int dev = 0;
     MBRF_CUDA(cudaGetDevice(&dev));
     if (!cx.stream || cx.stream_device != dev) {
+        if (cx.stream) { cudaSetDevice(cx.stream_device); cudaStreamDestroy(cx.stream); cudaSetDevice(dev); cx.stream = nullptr; }
         MBRF_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
         cx.stream_device = dev;
     }

@@ -122,10 +122,8 @@ int mbrf_fmp2_batch_device(const double *r_re, const double *r_im, int n, int B,
     twiddle_kernel<<<(N / 2 + 255) / 256, 256, 0, st>>>(tw, N / 2);
     MBRF_LAUNCH_CHECK();
     const size_t smem = (size_t)N * sizeof(double2);
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
+    if (smem > 48 * 1024) {        // set on every call: the attribute is per device, a cache per process would miss a device change
         MBRF_CUDA(cudaFuncSetAttribute(fmp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
     }
     fmp2_kernel<<<B, THREADS, smem, st>>>(r_re, r_im, n, lg, tw, h_re, h_im);
     MBRF_LAUNCH_CHECK();

@@ -1305,7 +1305,7 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
     int dev = 0;
     MBRF_CUDA(cudaGetDevice(&dev));
     if (!stream || stream_dev != dev) {
-        if (stream) cudaStreamDestroy(stream);
+        if (stream) { cudaSetDevice(stream_dev); cudaStreamDestroy(stream); cudaSetDevice(dev); stream = nullptr; }
         MBRF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         stream_dev = dev;
     }

@@ -220,11 +220,9 @@ int mbrf_b2a_batch(const double *b_re, const double *b_im, int n, int B, double 
     twiddle_kernel<<<(L / 2 + 255) / 256, 256>>>(tw, L / 2);
     MBRF_LAUNCH_CHECK();
     const size_t smem = (size_t)L * sizeof(double2);
-    static size_t attr_set = 0;
-    if (smem > 40 * 1024 && smem > attr_set) {
+    if (smem > 40 * 1024) {        // set on every call: the attribute is per device
         MBRF_CUDA(cudaFuncSetAttribute(b2a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MBRF_CUDA(cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
     }
     DftPlan pl;
     pl.N = N; pl.lgL = lg; pl.tw = tw; pl.chirp = nullptr; pl.Bhat = nullptr;
@@ -261,10 +259,8 @@ int mbrf_ab2rf_batch(const double *a_re, const double *a_im, const double *b_re,
     MBRF_CUDA(cudaMemcpyAsync(p[2], b_re, nb, cudaMemcpyHostToDevice, 0));
     if (b_im) MBRF_CUDA(cudaMemcpyAsync(p[3], b_im, nb, cudaMemcpyHostToDevice, 0));
     const size_t smem = (size_t)4 * n * sizeof(double2);
-    static size_t attr_set = 0;
-    if (smem > 40 * 1024 && smem > attr_set) {
+    if (smem > 40 * 1024) {        // set on every call: the attribute is per device
         MBRF_CUDA(cudaFuncSetAttribute(ab2rf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
     }
     ab2rf_kernel<<<B, THREADS, smem>>>(p[0], a_im ? p[1] : nullptr, p[2], b_im ? p[3] : nullptr, n, p[4], p[5]);
     MBRF_LAUNCH_CHECK();

@@ -849,7 +849,8 @@ __global__ void control_kernel(Problem p, int max_iter)
     const int k = p.halpern == 1 ? 0 : (err[0] < err[1] ? 0 : 1);   // Halpern mode 1: the PDHG output T(z, y) is the candidate
     c.use_avg = k == 0 ? 1.0 : 0.0;
     if (c.status == 0.0) {
-        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = p.nn > 0 ? -DBL_MAX : fmax(rig[0], rig[1]);
+        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = p.nn > 0 ? -DBL_MAX : (p.halpern ? rig[0] : fmax(rig[0], rig[1]));   // Halpern: candidate 1 is the reflected
+                                                              // iterate, which can leave the blocks' dual sets -- no valid bound
         c.tmax = p.ng > 0 ? p.acc[(size_t)k * NACC * p.Bp + A_GMAX * p.Bp + b] : tm[k];
         const bool solved = pr[k] <= p.eps_pr && dr[k] <= p.eps_dr &&
                             fabs(po[k] - du[k]) <= p.eps_gap * fmax(fabs(po[k]), 1e-12);
@@ -972,15 +973,7 @@ static size_t tc_bytes(int Mp, int Np, int Bp)
     const size_t mxd = (size_t)(Mp > Np ? Mp : Np);
     return (size_t)tc::MAX_ND * (2 * (size_t)Mp * Np + (size_t)Bp * mxd) + ((size_t)Mp + Np + 3 * (size_t)Bp) * 8 + 4 * 256;
 }
-static int sm_count()
-{
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
-    }
-    return n;
-}
+using ::mbrf::sm_count;       // per-device cache (common.cu)
 static int split_k_tc(int Mp, int Np, int Bp)
 {
     const int tiles = (Np / tc::TN) * ((Bp + tc::TM - 1) / tc::TM);
@@ -999,11 +992,8 @@ static int tc_product_nd(const TcState &t, const double *X, int kdim, int Bp, co
                          const double *sa, int R, double *C, int P, long long slab, double *mx, bool have_max,
                          double *zero_other, cudaStream_t st, bool gemm_only = false)
 {
-    static bool attr = false;
-    if (!attr) {
-        MBRF_CUDA(cudaFuncSetAttribute(tc::tc_i8_gemm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(ND)));
-        attr = true;
-    }
+    // per device (the attribute is), not per process: a host thread may move to another GPU (mbrf_set_device)
+    MBRF_CUDA(cudaFuncSetAttribute(tc::tc_i8_gemm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(ND)));
     if (!have_max) {
         MBRF_CUDA(cudaMemsetAsync(mx, 0, (size_t)Bp * 8, st));
         int gy = kdim / 64;

@@ -25,7 +25,7 @@ constexpr int NBUF = 2;
 constexpr int BLOCK = 128;
 constexpr int WS_HEADER = 8;
 enum { E_RFR = 0, E_RFI, E_C, E_GX, E_GY };
-enum { B_C = 0, B_GX, B_GY };
+enum { B_C = 0, B_GX, B_GY, B_VARG };   // header: bounds of |rf|^2, |gx|, |gy|; B_VARG != 0 when the gradient varies over the pulse
 
 __global__ void slr_prep_kernel(const double *__restrict__ rfr, const double *__restrict__ rfi,
                                 const double *__restrict__ gx, const double *__restrict__ gy, int ns,
@@ -48,6 +48,7 @@ __global__ void slr_prep_kernel(const double *__restrict__ rfr, const double *__
     amax(ws + B_C, e[E_C]);
     amax(ws + B_GX, e[E_GX]);
     amax(ws + B_GY, e[E_GY]);
+    if (gx[k] != gx[0] || (gy && gy[k] != gy[0])) amax(ws + B_VARG, 1.0);
 }
 
 struct Params {
@@ -62,18 +63,25 @@ struct Params {
 
 struct State {
     double x, y;
+    double cg, cg2;   // constant-gradient case (the default g = 2 pi / N of abr.m:25 / abrm.m:28): x*gx + y*gy and its square
     double a0, a1, b0, b1;
     bool degenerate;  // some sample had phi == 0 (abrm.m has no guard there: 0/0)
 };
 
-template <bool HAVE_Y, int TIER, bool TRACK_ZERO>
+template <bool HAVE_Y, int TIER, bool TRACK_ZERO, bool CONSTG>
 __device__ __forceinline__ void slr_step(const double *__restrict__ e, State &s)
 {
     const double2 rf = *reinterpret_cast<const double2 *>(e + E_RFR);
     const double2 cg2 = *reinterpret_cast<const double2 *>(e + E_C);  // c, gx
-    double cg = s.x * cg2.y;                                          // abrx.c:88
-    if (HAVE_Y) cg = fma(s.y, e[E_GY], cg);                           // abrx.c:89
-    const double u = fma(cg, cg, cg2.x);                              // abrx.c:93, squared
+    double cg, u;
+    if (CONSTG) {
+        cg = s.cg;
+        u = s.cg2 + cg2.x;
+    } else {
+        cg = s.x * cg2.y;                                             // abrx.c:88
+        if (HAVE_Y) cg = fma(s.y, e[E_GY], cg);                       // abrx.c:89
+        u = fma(cg, cg, cg2.x);                                       // abrx.c:93, squared
+    }
     if (TRACK_ZERO) s.degenerate |= (u == 0.0);
     double w, s2;
     rot_coeffs<TIER>(u, w, s2);
@@ -89,12 +97,20 @@ __device__ __forceinline__ void slr_step(const double *__restrict__ e, State &s)
 }
 
 template <bool HAVE_Y, int SPT, int TIER, bool TRACK_ZERO>
-__device__ __forceinline__ void run_tile(const double *__restrict__ tile, int n, State (&st)[SPT])
+__device__ __forceinline__ void run_tile(const double *__restrict__ tile, int n, State (&st)[SPT], bool constg)
 {
-#pragma unroll 2
-    for (int i = 0; i < n; ++i) {
+    if (constg) {
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
 #pragma unroll
-        for (int j = 0; j < SPT; ++j) slr_step<HAVE_Y, TIER, TRACK_ZERO>(tile + i * SD, st[j]);
+            for (int j = 0; j < SPT; ++j) slr_step<HAVE_Y, TIER, TRACK_ZERO, true>(tile + i * SD, st[j]);
+        }
+    } else {
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < SPT; ++j) slr_step<HAVE_Y, TIER, TRACK_ZERO, false>(tile + i * SD, st[j]);
+        }
     }
 }
 
@@ -131,6 +147,8 @@ __global__ void __launch_bounds__(BLOCK) slr_kernel(const Params p)
             if (k < total) issue(k);
     }
     const double bc = p.ws[B_C], bgx = p.ws[B_GX], bgy = p.ws[B_GY];
+    const bool constg = p.ns > 0 && p.ws[B_VARG] == 0.0;
+    const double g0x = p.ns > 0 ? tab[E_GX] : 0.0, g0y = p.ns > 0 ? tab[E_GY] : 0.0;
     // abrm(rf,g,x,y) == (a_abrx(-x,-y), conj(b_abrx(-x,-y)))  (abrm.m:51-55 vs abrx.c:100-109)
     const double sign = p.convention == MBRF_SLR_ABRM ? -1.0 : 1.0;
 
@@ -150,6 +168,8 @@ __global__ void __launch_bounds__(BLOCK) slr_kernel(const Params p)
             st[j].y = (HAVE_Y && p.y) ? sign * p.y[iy] : 0.0;
             st[j].a0 = 1.0; st[j].a1 = 0.0; st[j].b0 = 0.0; st[j].b1 = 0.0;  // abrx.c:71
             st[j].degenerate = false;
+            st[j].cg = HAVE_Y ? fma(st[j].y, g0y, st[j].x * g0x) : st[j].x * g0x;   // same operations as the per-step form
+            st[j].cg2 = st[j].cg * st[j].cg;
             const double cgb = fabs(st[j].x) * bgx + fabs(st[j].y) * bgy;
             const double ub = fma(cgb, cgb, bc);
             const int tj = rot_tier(ub);
@@ -161,11 +181,11 @@ __global__ void __launch_bounds__(BLOCK) slr_kernel(const Params p)
             const double *tile = tiles[k % NBUF];
             mbar_wait(&full[k % NBUF], (k / NBUF) & 1u);
             switch (tier) {
-            case TIER_TINY: run_tile<HAVE_Y, SPT, TIER_TINY, TRACK_ZERO>(tile, n, st); break;
-            case TIER_SMALL: run_tile<HAVE_Y, SPT, TIER_SMALL, TRACK_ZERO>(tile, n, st); break;
-            case TIER_MED: run_tile<HAVE_Y, SPT, TIER_MED, TRACK_ZERO>(tile, n, st); break;
-            case TIER_BIG: run_tile<HAVE_Y, SPT, TIER_BIG, TRACK_ZERO>(tile, n, st); break;
-            default: run_tile<HAVE_Y, SPT, TIER_ANY, TRACK_ZERO>(tile, n, st); break;
+            case TIER_TINY: run_tile<HAVE_Y, SPT, TIER_TINY, TRACK_ZERO>(tile, n, st, constg); break;
+            case TIER_SMALL: run_tile<HAVE_Y, SPT, TIER_SMALL, TRACK_ZERO>(tile, n, st, constg); break;
+            case TIER_MED: run_tile<HAVE_Y, SPT, TIER_MED, TRACK_ZERO>(tile, n, st, constg); break;
+            case TIER_BIG: run_tile<HAVE_Y, SPT, TIER_BIG, TRACK_ZERO>(tile, n, st, constg); break;
+            default: run_tile<HAVE_Y, SPT, TIER_ANY, TRACK_ZERO>(tile, n, st, constg); break;
             }
             __syncthreads();
             if (tid == 0 && k + NBUF < total) issue(k + NBUF);
@@ -230,6 +250,7 @@ int mbrf_abr_device(const double *rfr, const double *rfi, const double *gx, cons
         set_error("abr: NULL required pointer");
         return MBRF_EINVAL;
     }
+    if (((uintptr_t)workspace & 15) != 0) { set_error("abr: workspace must be 16-byte aligned (TMA bulk copies)"); return MBRF_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     double *ws = (double *)workspace;
     MBRF_CUDA(cudaMemsetAsync(ws, 0, WS_HEADER * sizeof(double), st));
