@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py — Bloch hot path on B200 (BASELINE.json metric "Bloch spin-steps/sec").
+"""bench.py — Bloch hot path on B200 (BASELINE.json metric "Bloch spin-steps/sec"), with the forward-SLR and the
+convex-FIR-design paths reported in the same JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -7,14 +8,18 @@ Workload (`config.workload`): BASELINE configs[1] — a 512-sample excitation pu
 over 10^6 spins per GPU (1000 off-resonances x 1000 positions with a 0.05 G/cm x-gradient,
 T1 = T2 = 1000 s, mode 0, 13C gamma), i.e. 5.12e8 spin-steps per step per GPU.  At N GPUs the
 job is 1000*N off-resonances x 1000 positions, sharded by contiguous spin range
-(s = p + npos*f, blochC.c:468-473) with one NCCL gather of mx/my/mz to rank 0 per step.
+(s = p + npos*f, blochC.c:468-473); the final gather is fused into the kernels: every rank stores
+its slice straight into rank 0's peer-mapped result over NVLink.
 
 One JSON line is printed by rank 0:
-  value        device-resident throughput (inputs already in HBM, mbrf_bloch_device + gather),
-               timed with CUDA events on the launching stream, max over ranks
-  e2e          the same metric through the reference-facing call  blochC(b1,gr,tp,t1,t2,df,dp,mode)
-               (C ABI mbrf_bloch) with pinned HOST buffers; H2D of the inputs and the result
-               landing in host memory are inside the timed region
+  value        device-resident throughput (inputs already in HBM, one mbrf_bloch_device per rank writing
+               into rank 0's result), timed with CUDA events on the launching stream, max over ranks
+  e2e          the same metric through ONE reference-facing call  blochC(b1,gr,tp,t1,t2,df,dp,mode)
+               (C ABI mbrf_bloch) on rank 0 for the whole job: HOST buffers, the result arrays freshly
+               allocated PAGEABLE memory as a MEX gateway gets them, all N GPUs used inside the call
+               (mbrf_set_fanout); H2D, D2H and the host-side copies are inside the timed region
+  solver_*     short copies of the second hot path's numbers: BASELINE config 4 (4096 fir_ap_cvx designs, the same
+               grid at every N), config 3 (fir_qp_cvx, one design), config 5 (C-13 order search); details under "solver"
   roofline     FP64-pipe roofline of the dominant kernel (76 algorithmic flops per
                spin-step; the path is FP64-bound, 56 B of HBM traffic per spin) against the FP64
                FMA peak measured in this run by a DFMA-only kernel; `hbm` shows why it is not HBM-bound
@@ -261,8 +266,12 @@ def leg_cfg4(args, m, lib, rank, world, dev, max_over_ranks, barrier):
         sampler.start()
     l0 = lib.mbrf_launch_count()
     t0 = time.perf_counter()
-    r = fir.fir_ap_cvx_sweep(n, f, H1_DUALBAND["a"], H1_DUALBAND["d"], objs, peaks, fadds, rank=rank, world=world, batch=512,
-                             method="ipm")
+    # two batches in flight per GPU (two host threads, two streams): the per-design kernels of a batch leave SMs idle once
+    # most of its designs have finished, the other batch fills them (measured: 182 -> 242 designs/s on 1024 designs)
+    local = -(-total // world)
+    batch = 512 if local > 512 else max(64, -(-local // 2 // 64) * 64)
+    r = fir.fir_ap_cvx_sweep(n, f, H1_DUALBAND["a"], H1_DUALBAND["d"], objs, peaks, fadds, rank=rank, world=world, batch=batch,
+                             method="ipm", concurrent_batches=2)
     t_solve = time.perf_counter() - t0
     full = gather_sweep(r, n, total, device=dev if world > 1 else None)
     t1 = time.perf_counter()
@@ -281,7 +290,7 @@ def leg_cfg4(args, m, lib, rank, world, dev, max_over_ranks, barrier):
            "workload": "cfg4: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, %d obj in logspace(-2,4) x %d Peak in "
                        "logspace(-4,-2) x %d f_add in linspace(0, 0.9 df_min/2); same grid at every GPU count" % (no, npk, nfa),
            "method": "interior point (mbrf_fir_ipm_solve): structured normal matrix from Toeplitz/Hankel moments, batched "
-                     "double-double Cholesky", "batch": 512,
+                     "double-double Cholesky", "batch": batch, "concurrent_batches": 2,
            "status_counts": {"solved": int(ok.sum()), "infeasible_certificate": int((st == 2).sum()),
                              "iteration_limit": int((st == 3).sum())},
            "iterations_mean": float(info[:, 1].mean()), "iterations_max": float(info[:, 1].max()),
@@ -332,7 +341,7 @@ def leg_cfg3(m, lib, hbm_peak):
     for tag, os_ in (("grid2566", 10), ("grid4096", 16)):
         t1 = time.perf_counter()
         _, st3, ex3 = fir.fir_qp_cvx(256, H1_DUALBAND["f"], H1_DUALBAND["a"], H1_DUALBAND["d"], 120, 1e6, return_info=True,
-                                     oversamp=os_, max_iter=400000)
+                                     oversamp=os_, max_iter=1500000)
         sec = time.perf_counter() - t1
         mrows = 2 * ex3["problem"]["w"].size + 2 * 256
         kbytes = 8.0 * mrows * 512
@@ -711,7 +720,7 @@ def run_ours(args):
                            "frac": slr["value"] * 50 / 1e12 / world / tf.value}
     if solver is not None:
         solver["roofline"] = solver_roofline(lib, tf.value)
-        solver["single_design"] = leg_cfg3(m, lib, hbm_peak)
+        solver["single_design"] = leg_cfg3(m, lib, hbm_peak) if not args.skip_single_design else None
         solver["order_search"] = cfg5
         if world == 1 and not args.no_cpu_baseline:
             solver["cpu_baseline"] = solver_cpu_baseline()
@@ -743,8 +752,8 @@ def run_ours(args):
         # short top-level copies of the second hot path's headline numbers (the full objects follow)
         "solver_designs_per_s": solver["value"] if solver else None,
         "solver_roofline_frac": solver["roofline"]["frac"] if solver else None,
-        "solver_cfg3_seconds": solver["single_design"]["grid4096"]["seconds"] if solver else None,
-        "solver_cfg3_hbm_frac": solver["single_design"]["grid4096"]["roofline"]["frac"] if solver else None,
+        "solver_cfg3_seconds": solver["single_design"]["grid4096"]["seconds"] if solver and solver.get("single_design") else None,
+        "solver_cfg3_hbm_frac": solver["single_design"]["grid4096"]["roofline"]["frac"] if solver and solver.get("single_design") else None,
         "solver_cfg5_seconds": solver["order_search"]["seconds"] if solver and solver.get("order_search") else None,
         "slr_position_steps_per_s": slr["value"] if slr else None,
         "slr": slr,
@@ -777,6 +786,8 @@ def main():
     ap.add_argument("--no-solver", action="store_true", help="skip the FIR-design leg")
     ap.add_argument("--solver-grid", type=lambda v: tuple(int(x) for x in v.split(",")), default=(16, 16, 16),
                     help="cfg4 sweep: numbers of obj, Peak and f_add values (default 16,16,16 = 4096 designs, BASELINE config 4)")
+    ap.add_argument("--skip-single-design", action="store_true",
+                    help="skip cfg3 (a million small launches: only for runs under a profiler)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:

@@ -532,9 +532,9 @@ def fir_ap_cvx_sweep(n, f, a, d, objs, peaks, f_adds, rank=0, world=1, batch=512
     Returns dict(index, x, ripple_stop, info) for the local designs."""
     fl, ol, pl = sweep_grid(f, objs, peaks, f_adds)
     mine = np.arange(rank, len(fl), world)
-    xs, ts, infos = [], [], []
-    for b0 in range(0, mine.size, batch):
-        ids = mine[b0:b0 + batch]
+    concurrent = int(solver_kw.pop("concurrent_batches", 0) or 0)
+
+    def solve_batch(ids):
         designs = [assemble_fir_ap(n, fl[i], a, d, ol[i], pl[i]) for i in ids]
         stride = seed_stride
         if stride == "auto":                            # seeds about 0.1 decades of the weight apart; coarser sweeps run cold
@@ -544,10 +544,28 @@ def fir_ap_cvx_sweep(n, f, a, d, objs, peaks, f_adds, rank=0, world=1, batch=512
             if stride < 8:
                 stride = 0
         if stride and stride > 1 and len(designs) > 2 * stride:
-            x, t, info = _solve_seeded(n, designs, [np.asarray(fl[i]).tobytes() for i in ids], [pl[i] for i in ids],
-                                       [ol[i] for i in ids], int(stride), **solver_kw)
-        else:
-            x, t, info = _solve_batch_ap(n, designs, **solver_kw)
+            return _solve_seeded(n, designs, [np.asarray(fl[i]).tobytes() for i in ids], [pl[i] for i in ids],
+                                 [ol[i] for i in ids], int(stride), **solver_kw)
+        return _solve_batch_ap(n, designs, **solver_kw)
+
+    chunks = [mine[b0:b0 + batch] for b0 in range(0, mine.size, batch)]
+    if concurrent > 1 and len(chunks) > 1 and (solver_kw.get("method") or DEFAULT_METHOD) == "ipm":
+        # interior point: the per-design kernels (Cholesky, triangular solves) of a batch leave SMs idle once most of its designs
+        # have finished; a second batch on another host thread / stream fills them
+        from concurrent.futures import ThreadPoolExecutor
+        import ctypes as _C
+        dev = _C.c_int(0)
+        check(lib().mbrf_get_device(_C.byref(dev)))
+
+        def run(ids):
+            check(lib().mbrf_set_device(dev.value))
+            return solve_batch(ids)
+        with ThreadPoolExecutor(max_workers=concurrent) as ex:
+            results = list(ex.map(run, chunks))
+    else:
+        results = [solve_batch(ids) for ids in chunks]
+    xs, ts, infos = [], [], []
+    for x, t, info in results:
         xs.append(x); ts.append(t); infos.append(info)
     cat = lambda v, w: np.concatenate(v) if v else np.zeros((0, w))   # noqa: E731
     return dict(index=mine, x=cat(xs, 2 * n - 1), ripple_stop=np.concatenate(ts) if ts else np.zeros(0),

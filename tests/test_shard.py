@@ -80,6 +80,45 @@ def _worker_pieces(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
+def _worker_sweep(rank, world, port, ndesigns, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multiband_rf_pulse_design_b200.shard import gather_sweep
+    n = 5
+    mine = np.arange(rank, ndesigns, world)                 # fir_ap_cvx_sweep: instance i -> rank i mod world
+    res = dict(index=mine, x=np.outer(mine + 1.0, np.arange(1, 2 * n)), ripple_stop=mine * 0.5,
+               info=np.tile(mine[:, None].astype(float), (1, 8)))
+    full = gather_sweep(res, n, ndesigns)
+    if rank == 0:
+        ids = np.arange(ndesigns)
+        ok = (np.array_equal(full["index"], ids) and np.array_equal(full["x"], np.outer(ids + 1.0, np.arange(1, 2 * n)))
+              and np.array_equal(full["ripple_stop"], ids * 0.5) and np.array_equal(full["info"][:, 3], ids.astype(float)))
+        q.put(bool(ok))
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ndesigns", [7, 16])
+def test_sweep_gather_world2_gloo(ndesigns):
+    """the final gather of a design sweep (x, ripple_stop, status rows of every instance to rank 0), ragged shares"""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker_sweep, args=(r, 2, port, ndesigns, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
+
+
 def test_piece_widths():
     from multiband_rf_pulse_design_b200.shard import piece_widths
     for width in (1, 7, 1000, 10 ** 6):

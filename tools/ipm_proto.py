@@ -15,6 +15,10 @@ import numpy as np
 import scipy.linalg as sla
 
 REG = 0.0
+STEP = 0.99       # fraction of the way to the boundary
+SIGPOW = 3        # sigma = (1 - alpha_aff)^SIGPOW
+INIT = "e"        # "e": x = 0, s = z = e;  "ls": least-squares start shifted into the cone (CVXOPT)
+NCORR = 0         # extra Gondzio centrality correctors
 
 
 def _soc_step(u, du):
@@ -160,6 +164,20 @@ def conelp(c, G, h, cone: Cone, feastol=1e-9, abstol=1e-10, reltol=1e-9, maxit=1
     z = cone.e()
     tau = kap = 1.0
     e = cone.e()
+    if INIT == "ls":
+        # CVXOPT's start: x = argmin ||G x - h||, s = h - G x shifted into the cone; z = argmin ||z|| s.t. G'z + c = 0, shifted
+        GtG = G.T @ G
+        cf0 = sla.cho_factor(GtG + 1e-12 * np.trace(GtG) / nv * np.eye(nv))
+        x = sla.cho_solve(cf0, G.T @ h)
+        s = h - G @ x
+        z = -G @ sla.cho_solve(cf0, c)
+        def shift(v):
+            m_ = v[:cone.nl].min() if cone.nl else np.inf
+            for i in range(len(cone.q)):
+                a_, b_ = cone.off[i], cone.off[i + 1]
+                m_ = min(m_, v[a_] - np.linalg.norm(v[a_ + 1:b_]))
+            return v + (1.0 - m_) * e if m_ < 0 else (v + e if m_ < 1e-8 else v)
+        s, z = shift(s), shift(z)
     nrm_h, nrm_c = max(1.0, np.linalg.norm(h)), max(1.0, np.linalg.norm(c))
     status = "maxit"
     hist = []
@@ -177,7 +195,7 @@ def conelp(c, G, h, cone: Cone, feastol=1e-9, abstol=1e-10, reltol=1e-9, maxit=1
             print(f"{it:3d} pcost {pcost:+.10e} dcost {dcost:+.10e} gap {gap:.2e} pres {pres:.1e} dres {dres:.1e} "
                   f"tau {tau:.2e} kap {kap:.2e} mu {mu:.2e}")
         hist.append((pcost, dcost, gap, pres, dres))
-        if pres <= feastol and dres <= feastol and (gap <= abstol or relgap <= reltol):
+        if pres <= feastol and dres <= 100 * feastol and (gap <= abstol or relgap <= reltol):
             status = "optimal"
             break
         hz = h @ z
@@ -233,11 +251,11 @@ def conelp(c, G, h, cone: Cone, feastol=1e-9, abstol=1e-10, reltol=1e-9, maxit=1
 
         Dx, Dz, dtau, Ds, Dk = direction(-rx, -rz, -rt, -cone.prod(lam, lam), -kap * tau)
         al = min(1.0, maxstep(Ds, Dz, dtau, Dk))
-        sig = (1 - al) ** 3
+        sig = (1 - al) ** SIGPOW
         ds_c = -cone.prod(lam, lam) - cone.prod(cone.Wmul(Ds, inv=True), cone.Wmul(Dz)) + sig * mu * e
         dk_c = -kap * tau - Dk * dtau + sig * mu
         Dx, Dz, dtau, Ds, Dk = direction(-(1 - sig) * rx, -(1 - sig) * rz, -(1 - sig) * rt, ds_c, dk_c)
-        al = min(1.0, 0.99 * maxstep(Ds, Dz, dtau, Dk))
+        al = min(1.0, STEP * maxstep(Ds, Dz, dtau, Dk))
         x += al * Dx
         s += al * Ds
         z += al * Dz
