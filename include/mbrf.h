@@ -332,6 +332,21 @@ int mbrf_b2a_batch(const double *b_re, const double *b_im, int n, int B, double 
 int mbrf_ab2rf_batch(const double *a_re, const double *a_im, const double *b_re, const double *b_im, int n, int B,
                      double *rf_re, double *rf_im);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched zero flipping: the loop of fir_flip_zero.m:66-99 (called by fir_ap.m:199-208, fir_qp.m:136-146, dzrf_mb.m:225).
+ * Z = roots(h) (nroots = N-1 zeros, split planes, z_im NULL = all real) and the passband zeros idx_pb (0-based indices into
+ * Z, fir_flip_zero.m:28) stay the caller's work, as does the choice of flip patterns mask [nmask x n_pb] (row-major,
+ * 1 = reflect that passband zero about the unit circle, :112-117; MATLAB's n_pb-by-Num `mask` is exactly this layout).
+ * Per pattern the polynomial is expanded in the order of Z like poly() (:70), scaled by hsum / sum (hsum = sum(h), :71),
+ * and its power sum|h|^2 and peak max|h| are recorded (:74-75); the pattern with the smallest peak (first one on ties, as
+ * min(), :96) is returned: best (0-based), h [N].  Optional outputs (may be NULL): peak [nmask], power [nmask],
+ * h_all [nmask x N] (the reference's h_array).  Host pointers.  N <= mbrf_flip_zero_max_taps().
+ * ------------------------------------------------------------------------------------------------ */
+int mbrf_flip_zero_max_taps(void);
+int mbrf_flip_zero_batch(const double *z_re, const double *z_im, int nroots, const int *idx_pb, int n_pb,
+                         const unsigned char *mask, int nmask, double hsum_re, double hsum_im, int *best, double *h_re,
+                         double *h_im, double *peak, double *power, double *h_all_re, double *h_all_im);
+
 #ifdef __cplusplus
 }
 #endif

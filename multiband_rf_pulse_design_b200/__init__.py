@@ -8,7 +8,9 @@ behaviour) over the C ABI in ``include/mbrf.h`` / ``libmbrf.so``:
     abrx, abrm, abr                  <- rf_tools/mex5/abrx.c, rf_tools/abrm.m, rf_tools/abr.m
     b2a, ab2rf, b2rf                 <- rf_tools/b2a.m, rf_tools/ab2rf.m (batched inverse SLR, dzrf_mb.m:239-240)
     fmp2                             <- fir_ap_cvx.m:253-304 (batched spectral factorisation)
-    fir_ap_cvx, fir_ap               <- fir_ap_cvx.m, fir_ap.m (solve = batched restarted PDHG on the GPU)
+    fir_ap_cvx, fir_ap               <- fir_ap_cvx.m, fir_ap.m (solve = batched interior point / restarted PDHG on the GPU)
+    fir_flip_zero                    <- fir_flip_zero.m (all flip patterns expanded in one launch)
+    fir_qprog_phs, fir_min_order_qprog_phs <- ss/fir_qprog_phs.m, ss/fir_min_order_qprog_phs.m
 
 There is no CPU fallback: importing works anywhere, computing needs the built library
 and a CUDA device.
@@ -18,7 +20,8 @@ from .bloch import bloch, blochC, blochH, blochsimfz, GAMMA_C13, GAMMA_H1  # noq
 from .slr import ab2rf, abr, abrm, abrx, b2a, b2rf  # noqa: F401
 from .fir import (fir_ap, fir_ap_cvx, fir_ap_cvx_batch, fir_linprog, fir_min_order,  # noqa: F401
                   fir_min_order_linprog, fir_qp_cvx, fmp2)
+from .fir_post import fir_flip_zero, fir_min_order_qprog_phs, fir_qprog_phs  # noqa: F401
 
 __all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "b2a", "ab2rf", "b2rf", "fir_ap", "fir_ap_cvx",
-           "fir_ap_cvx_batch", "fir_linprog", "fir_min_order", "fir_min_order_linprog", "fir_qp_cvx", "fmp2", "lib", "MbrfError",
+           "fir_ap_cvx_batch", "fir_flip_zero", "fir_qprog_phs", "fir_min_order_qprog_phs", "fir_linprog", "fir_min_order", "fir_min_order_linprog", "fir_qp_cvx", "fmp2", "lib", "MbrfError",
            "library_path", "GAMMA_C13", "GAMMA_H1"]

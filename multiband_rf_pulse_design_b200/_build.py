@@ -12,7 +12,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmbrf.so")
-SOURCES = ["common.cu", "hostpipe.cu", "bloch.cu", "bloch_host.cu", "slr.cu", "pdhg.cu", "ipm.cu", "fir.cu", "fmp.cu", "islr.cu"]
+SOURCES = ["common.cu", "hostpipe.cu", "bloch.cu", "bloch_host.cu", "slr.cu", "pdhg.cu", "ipm.cu", "fir.cu", "fmp.cu", "islr.cu", "flipzero.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",

@@ -87,6 +87,9 @@ SIGNATURES = {
     "mbrf_ipm_padded_sizes": (_i, [_i, _i, _i, c_int_p, c_int_p, c_int_p]),
     "mbrf_ipm_set_option": (_i, [_i, _d]),
     "mbrf_ipm_cholesky_bench": (_i, [_i, _i, _i, _i, C.POINTER(C.c_float)]),
+    "mbrf_flip_zero_max_taps": (_i, []),
+    "mbrf_flip_zero_batch": (_i, [_dp, _dp, _i, c_int_p, _i, C.POINTER(C.c_ubyte), _i, _d, _d, c_int_p, _dp, _dp, _dp, _dp, _dp,
+                                  _dp]),
     "mbrf_fir_pdhg_solve": (_i, [_dp, _dp, _i, c_int_p, _dp, _dp, _i, _i, c_int_p, c_int_p, _i,
                                  _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _i, _i, _dp, _i, _i, _d, _d, _d,
                                  _dp, _dp, _dp]),

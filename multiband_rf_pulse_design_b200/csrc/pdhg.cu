@@ -89,7 +89,7 @@ struct Problem {
     double beta_suff, beta_nec, beta_art, omega_theta, min_since;   // restart rule constants (PDLP defaults 0.2, 0.8, 0.36, 0.5)
 };
 
-enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, A_GMAX, A_ZZ, A_ZV, A_VV, A_GMAX2, NACC };
+enum { A_PR = 0, A_DR, A_POBJ, A_GZ, A_HS, A_DZ2, A_DY2, A_RIGX, A_TMAX, A_GMAX, A_ZZ, A_ZV, A_VV, A_GMAX2, A_RIGN, A_GG, A_RR, NACC };
 
 __device__ __forceinline__ void atomic_max_pos(double *addr, double v)
 {
@@ -756,6 +756,7 @@ __global__ void col_metrics_kernel(Problem p, int cand)
     const double inv = cand == 0 ? 1.0 / fmax(p.ctl[b].cnt, 1.0) : 1.0;
     const double *zv = cand == 0 ? p.zs : p.z;
     double pobj = 0.0, gz = 0.0, dr = 0.0, dz2 = 0.0, rigx = 0.0, s_zz = 0.0, s_zv = 0.0, s_vv = 0.0;
+    double rign = 0.0, s_gg = 0.0, s_rr = 0.0;   // norm-term coordinates: box bound, ||g||^2, radius^2 of a ball around the box
     for (int j = blockIdx.y; j < p.Np; j += gridDim.y) {
         const int pr = p.pair_of[j];
         if (pr >= 0 && p.pair_j[pr] == j) continue;
@@ -767,7 +768,10 @@ __global__ void col_metrics_kernel(Problem p, int cand)
             gz = fma(g, z, gz);
             const double d = z - p.z0[o];
             dz2 = fma(d, d, dz2);
-            rigx += g > 0.0 ? g * p.bl[o] : (g < 0.0 ? g * p.bu[o] : 0.0);
+            const double bl = p.bl[o], bu = p.bu[o];
+            rign += g > 0.0 ? g * bl : (g < 0.0 ? g * bu : 0.0);
+            s_gg = fma(g, g, s_gg);
+            s_rr += fmax(bl * bl, bu * bu);
         } else if (pr < 0) {
             const double bl = p.bl[o], bu = p.bu[o];
             const double t = fmin(fmax(z - g, bl), bu);
@@ -801,6 +805,9 @@ __global__ void col_metrics_kernel(Problem p, int cand)
         atomicAdd(acc + A_ZZ * p.Bp + b, s_zz);
         atomicAdd(acc + A_ZV * p.Bp + b, s_zv);
         atomicAdd(acc + A_VV * p.Bp + b, s_vv);
+        atomicAdd(acc + A_RIGN * p.Bp + b, rign);
+        atomicAdd(acc + A_GG * p.Bp + b, s_gg);
+        atomicAdd(acc + A_RR * p.Bp + b, s_rr);
     }
 }
 
@@ -841,6 +848,13 @@ __global__ void control_kernel(Problem p, int max_iter)
             dr[k] = fmax(a[A_DR * p.Bp + b], sqrt(fmax(zz - 2.0 * sh * zv + sh * sh * vv, 0.0)));
         }
         rig[k] = -a[A_HS * p.Bp + b] + a[A_RIGX * p.Bp + b];
+        if (p.nn > 0) {
+            // min over the box of lam*||z|| + g.z over the norm-term coordinates: >= the box minimum of g.z alone (lam*||z|| >= 0)
+            // and >= -R*max(0, ||g|| - lam) with R the radius of a ball around the box ((lam - ||g||)*||z|| by Cauchy-Schwarz)
+            const double gn = sqrt(fmax(a[A_GG * p.Bp + b], 0.0)), R = sqrt(fmax(a[A_RR * p.Bp + b], 0.0));
+            const double ball = gn > p.lam[b] ? -R * (gn - p.lam[b]) : 0.0;
+            rig[k] += fmax(a[A_RIGN * p.Bp + b], R < DBL_MAX ? ball : -DBL_MAX);
+        }
         dz[k] = sqrt(a[A_DZ2 * p.Bp + b]);
         dy[k] = sqrt(a[A_DY2 * p.Bp + b]);
         err[k] = fmax(fmax(pr[k], dr[k]), fabs(po[k] - du[k]));
@@ -849,7 +863,7 @@ __global__ void control_kernel(Problem p, int max_iter)
     const int k = p.halpern == 1 ? 0 : (err[0] < err[1] ? 0 : 1);   // Halpern mode 1: the PDHG output T(z, y) is the candidate
     c.use_avg = k == 0 ? 1.0 : 0.0;
     if (c.status == 0.0) {
-        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = p.nn > 0 ? -DBL_MAX : (p.halpern ? rig[0] : fmax(rig[0], rig[1]));   // Halpern: candidate 1 is the reflected
+        c.obj = po[k]; c.dual = du[k]; c.pr = pr[k]; c.dr = dr[k]; c.rigorous = p.halpern ? rig[0] : fmax(rig[0], rig[1]);   // Halpern: candidate 1 is the reflected
                                                               // iterate, which can leave the blocks' dual sets -- no valid bound
         c.tmax = p.ng > 0 ? p.acc[(size_t)k * NACC * p.Bp + A_GMAX * p.Bp + b] : tm[k];
         const bool solved = pr[k] <= p.eps_pr && dr[k] <= p.eps_dr &&

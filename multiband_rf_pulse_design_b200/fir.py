@@ -402,10 +402,17 @@ def fir_ap(n, f, a, d, Peak=1e-3, min_order=0, min_tran=0, min_peak=0, dbg=0, **
 
     Each bisection step of the reference is one serial fir_ap_cvx solve; here every step probes a whole
     bracket of candidates in ONE batch (k-ary search), which needs fewer rounds and fills the GPU.
-    min_peak (fir_flip_zero) is not part of the accelerated path and raises if requested.
+    min_peak: the result goes through fir_flip_zero (fir_ap.m:199-208), all flip patterns expanded in one GPU launch.
     """
-    if min_peak:
-        raise NotImplementedError("fir_flip_zero (min_peak) is outside the accelerated path (SURVEY.md 2.3 M9)")
+    h, status, n_op, f_op = _fir_ap_search(n, f, a, d, Peak, min_order, min_tran, dbg, **solver_kw)
+    if min_peak and len(h):                                               # fir_ap.m:199-208
+        from .fir_post import fir_flip_zero
+        h = fir_flip_zero(h, dbg)
+    return h, status, n_op, f_op
+
+
+def _fir_ap_search(n, f, a, d, Peak, min_order, min_tran, dbg, **solver_kw):
+    """fir_ap.m:45-176: the transition-width and order bisections."""
     f = np.asarray(f, float).ravel()
     lam, df_thre = 0.1, 0.0005                                            # fir_ap.m:45-46
     n_op, f_op = int(n), f.copy()

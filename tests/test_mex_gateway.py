@@ -16,7 +16,7 @@ MEX = os.path.join(ROOT, "multiband_rf_pulse_design_b200", "matlab")
 @pytest.fixture(scope="module")
 def gateways(mbrf):
     subprocess.check_call(["make", "-s", "-C", MEX, "check"])
-    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "fir_solve", "b2a", "ab2rf", "fmp2")}
+    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "fir_solve", "b2a", "ab2rf", "fmp2", "flip_zero")}
 
 
 def test_gateways_link_and_report_errors_like_the_reference(gateways, oracle, mbrf):
@@ -254,3 +254,52 @@ def test_postprocessing_gateways_vs_restatements(gateways, oracle):
     (hm,), err = oracle.mex_call(gateways["fmp2"], 1, r)
     assert err is None and hm.size == 33
     assert np.abs(hm.ravel() - fmp2_reference(r)).max() < 1e-10
+
+
+def test_flip_zero_gateway_usage_errors(gateways, oracle):
+    out, err = oracle.mex_call(gateways["flip_zero"], 1, np.ones(4), np.ones(2))
+    assert out is None and err.startswith("Usage: [h_new, best, peak, power] = flip_zero_mex")
+    out, err = oracle.mex_call(gateways["flip_zero"], 1, np.ones(4), np.array([1.0, 2.0]), np.zeros((3, 4)), 1.0)
+    assert out is None and err == "flip_zero_mex: mask must have one row per passband zero"
+
+
+@pytest.mark.gpu
+def test_flip_zero_gateway_like_fir_flip_zero_m(gateways, oracle):
+    """flip_zero_mex with the arguments matlab/fir_flip_zero.m builds (complex Z, 1-based idx_pb, N_z-by-Num mask) against the
+    restatement of fir_flip_zero.m:66-99."""
+    from oracle import fir_post as O
+    from test_fir_post import _filter, flip_zero_check
+    h = _filter(18, 7, seed=9)
+    o = O.flip_zero_reference(h)
+    outs, err = oracle.mex_call(gateways["flip_zero"], 4, o["Z"], (o["idx_pb"] + 1).astype(float), o["mask"].astype(float), h.sum())
+    assert err is None, err
+    h_new, best, peak, power = outs
+    assert h_new.shape == (h.size, 1) and peak.shape == (1, 128)
+    flip_zero_check(h, o["Z"], o["idx_pb"], o["mask"].T, dict(h_new=h_new.ravel(), best=int(best.ravel()[0]) - 1, peak=peak.ravel(),
+                                                             power=power.ravel()))
+
+
+@pytest.mark.gpu
+def test_fir_solve_gateway_like_fir_qprog_phs_m(gateways, oracle):
+    """fir_solve_mex (method 0) with the arguments matlab/fir_qprog_phs.m builds (a phase per row, no scales / entries / pairs,
+    the norm term over all of x, obj_upper = amax): the minimiser of the CPU QP (oracle/fir_post.py, SciPy SLSQP)."""
+    from multiband_rf_pulse_design_b200 import fir_post as P
+    from oracle import fir_post as O
+    from test_fir_post import SPEC
+    n = 17
+    p = P.assemble_fir_qprog_phs(n, SPEC["f"], SPEC["a"], SPEC["d"])
+    N = 2 * n
+    fin = np.concatenate([p["hi"][np.isfinite(p["hi"])], p["lo"][np.isfinite(p["lo"])]])
+    big = 2 * np.sqrt(n) * max(1.0, np.abs(fin).max())
+    blocks = np.zeros(9); blocks[6] = N
+    outs, err = oracle.mex_call(gateways["fir_solve"], 2, 0.0, p["w"], p["phase"], E, np.concatenate([np.ones(n), 2 * np.ones(n)]),
+                                np.concatenate([p["q"], p["q"]]), np.ones(N), E, E, E, np.zeros((N, 1)), p["lo"].reshape(-1, 1),
+                                p["hi"].reshape(-1, 1), np.full((N, 1), -big), np.full((N, 1), big), E, np.array([p["amax"] * (1 + 1e-9)]),
+                                np.array([400000, 64, 8e-7, 1e-5, 2e-5]), blocks, np.array([[0.0], [0.0], [1.0], [0.0]]))
+    assert err is None, err
+    z, info = outs
+    assert info[0, 0] == 1.0
+    o = O.build_fir_qprog_phs(n, SPEC["f"], SPEC["a"], SPEC["d"])
+    r = O.solve_fir_qprog_phs_reference(o)
+    assert r.success and (o["A"] @ z[:, 0] - o["B"]).max() < 1e-6
+    assert abs(np.linalg.norm(z[:, 0]) - np.linalg.norm(r.x)) < 1e-4 * np.linalg.norm(r.x)
