@@ -302,6 +302,29 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
                        const double *bl, const double *bu, const double *rho, int B, int simplex_row0, int simplex_rows,
                        const double *simplex_w, int max_iter, double feastol, double reltol, double abstol, double *z_out,
                        double *info_out);
+/*
+ * fir_ap_cvx as ONE call, specification in -> taps out (device-side problem assembly).  Replaces
+ * fir_ap_cvx.m:44-202 for B designs of one order n: grid (:44-48), band masks and interpolated bounds (:51-82), squared /
+ * floored power bounds (:103-120), stop rows (:125), peak radii (:166-168), the solve (:160-169) and h = fmp2(r) (:185-202).
+ * The union of the designs' grids is built on the host (one sorted vector); every per-design quantity is computed by kernels
+ * straight into the solver's arrays (bit-identical to the host assembly of the Python mirror), the batch is solved by the
+ * interior-point method of mbrf_fir_ipm_solve, and the spectral factors are taken on the device from the solutions.
+ *   f [B x 2 nband] band edges as the reference takes them (fractions of pi), a [B x 2 nband], d [B x nband], obj [B], peak [B];
+ *   oversamp: 15 (fir_ap_cvx.m:45);  max_iter / feastol / reltol / abstol as mbrf_fir_ipm_solve (0 = defaults).
+ *   x_out [B x (2n-1)] solutions (may be NULL), h_re / h_im [B x n] minimum-phase taps (both NULL = skip; rows of designs that
+ *   did not end with status 1 are meaningless), info_out [B x 8] as mbrf_fir_ipm_solve, rows_out[2] (may be NULL): grid rows
+ *   of the union and rows of the stop block.  Host pointers, row-major, design index slowest.
+ */
+int mbrf_fir_ap_solve(int n, int nband, const double *f, const double *a, const double *d, const double *obj, const double *peak,
+                      int B, int oversamp, int max_iter, double feastol, double reltol, double abstol, double *x_out, double *h_re,
+                      double *h_im, double *info_out, int *rows_out);
+/* The assembly alone: the arrays mbrf_fir_ap_solve hands to its solver, in the layout of mbrf_fir_ipm_solve / mbrf_fir_pdhg_solve
+ * ([dim x B], design index fastest): w_row [M], lo / hi [M x B], c / bl / bu [(2n-1) x B], rho [(n-1) x B], ct [B] (the stop-band
+ * weights), M = rows_out[0] + rows_out[1] (grid rows of the union + rows of the stop block, which starts at rows_out[0]).
+ * Call with lo_out == NULL first to learn rows_out and size the arrays. */
+int mbrf_fir_ap_assemble(int n, int nband, const double *f, const double *a, const double *d, const double *obj, const double *peak,
+                         int B, int oversamp, int *rows_out, double *w_row_out, double *lo_out, double *hi_out, double *c_out,
+                         double *bl_out, double *bu_out, double *rho_out, double *ct_out);
 int mbrf_ipm_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
 /* 0: precision of the Newton systems (0 fp64, 1 double-double, 2 auto = double-double once mu < switch * mu0; default 2),
  * 1: that switch (default 1e-3), 2: refinement steps per solve in the double-double phase (default 1), 3: trace the first `value`

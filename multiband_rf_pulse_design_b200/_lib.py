@@ -84,6 +84,8 @@ SIGNATURES = {
                                   _i, _i, _d, _d, _d, _dp, _dp, _dp]),
     "mbrf_fir_ipm_solve": (_i, [_dp, _i, c_int_p, _dp, _dp, _i, c_int_p, c_int_p, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _i, _i,
                                 _dp, _i, _d, _d, _d, _dp, _dp]),
+    "mbrf_fir_ap_solve": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _i, _i, _i, _d, _d, _d, _dp, _dp, _dp, _dp, c_int_p]),
+    "mbrf_fir_ap_assemble": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _i, _i, c_int_p, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "mbrf_ipm_padded_sizes": (_i, [_i, _i, _i, c_int_p, c_int_p, c_int_p]),
     "mbrf_ipm_set_option": (_i, [_i, _d]),
     "mbrf_ipm_cholesky_bench": (_i, [_i, _i, _i, _i, C.POINTER(C.c_float)]),

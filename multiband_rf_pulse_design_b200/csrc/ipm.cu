@@ -34,12 +34,15 @@
 #include "common.h"
 #include "dd.cuh"
 #include "dgemm.cuh"
+#include "fir_assemble.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 namespace mbrf {
@@ -1185,6 +1188,15 @@ static double g_dd_switch = 1e-3;    // auto: double-double when min over live d
 static int g_refine = 1, g_refine_fp64 = 0;
 static int g_verbose = 0;
 
+// Device-side input / output of a solve (mbrf_fir_ap_solve): `fill` writes c, bl, bu, lo, hi, rho, ct of the padded problem
+// with kernels instead of an upload; `after` sees the solutions x [Np x Bp] (caller's units) and info [Bp x 8] on the device
+// before anything is copied back.  `extra_bytes` of device scratch beyond the solver's own are handed to both.
+struct Hooks {
+    std::function<int(const P &, void *, cudaStream_t)> fill;
+    std::function<int(const P &, const double *, const double *, void *, cudaStream_t)> after;
+    size_t extra_bytes = 0;
+};
+
 }  // namespace ipm
 }  // namespace mbrf
 
@@ -1259,18 +1271,23 @@ int mbrf_ipm_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp)
     return MBRF_OK;
 }
 
+}  // extern "C"
+
 /*
  * Host-pointer entry point: same problem description as mbrf_fir_pdhg_solve (include/mbrf.h) minus the explicit column.
  */
-int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const double *col_kappa, const double *col_amp, int N,
-                       const int *pair_i, const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
-                       const double *bl, const double *bu, const double *rho, int B, int simplex_row0, int simplex_rows,
-                       const double *simplex_w, int max_iter, double feastol, double reltol, double abstol, double *z_out,
-                       double *info_out)
+static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const double *col_kappa, const double *col_amp, int N,
+                          const int *pair_i, const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
+                          const double *bl, const double *bu, const double *rho, int B, int simplex_row0, int simplex_rows,
+                          const double *simplex_w, int max_iter, double feastol, double reltol, double abstol, double *z_out,
+                          double *info_out, const Hooks *hooks)
 {
     if (int rc = require_device()) return rc;
-    if (M <= 0 || N <= 0 || B <= 0 || !w_row || !col_type || !col_kappa || !col_amp || !c || !lo || !hi || !z_out || !info_out ||
-        npairs < 0 || (npairs && (!pair_i || !pair_j || !rho)) || simplex_rows < 0 || (simplex_rows && (!simplex_w || simplex_row0 < 0 || simplex_row0 + simplex_rows > M))) {
+    const bool dev_fill = hooks && hooks->fill;
+    if (M <= 0 || N <= 0 || B <= 0 || !w_row || !col_type || !col_kappa || !col_amp || (!dev_fill && (!c || !lo || !hi)) ||
+        (!z_out && !(hooks && hooks->after)) || !info_out ||
+        npairs < 0 || (npairs && (!pair_i || !pair_j || (!rho && !dev_fill))) || simplex_rows < 0 ||
+        (simplex_rows && ((!simplex_w && !dev_fill) || simplex_row0 < 0 || simplex_row0 + simplex_rows > M))) {
         set_error("fir_ipm_solve: bad arguments");
         return MBRF_EINVAL;
     }
@@ -1336,6 +1353,7 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
     need((size_t)B * NVp * NVp * tsz);                           // normal matrices
     need(16 * (size_t)Np * Bp * 8);                              // split-K slabs of K' y
     need(colsz + (size_t)Bp * 64);                               // z_out, info
+    need(hooks ? hooks->extra_bytes : 0);
     if (int rc = scratch.reserve(total + (1 << 20))) return rc;
     char *dptr = (char *)scratch.ptr;
     auto take = [&](size_t b) { char *q = dptr; dptr += al(b); return q; };
@@ -1381,6 +1399,7 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
     void *dH = take((size_t)B * NVp * NVp * tsz);
     double *dslab = (double *)take(16 * (size_t)Np * Bp * 8);
     double *dzout = (double *)take(colsz), *dinfo = (double *)take((size_t)Bp * 64);
+    void *dextra = hooks && hooks->extra_bytes ? take(hooks->extra_bytes) : nullptr;
 
     // ---- upload ----
     std::vector<double> h;
@@ -1410,15 +1429,19 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
         return MBRF_OK;
     };
     const double INF = INFINITY;
-    if (int rc = upload(c, dc, N, Np, 0.0, 0.0)) return rc;
-    if (int rc = upload(bl, dbl, N, Np, -INF, -INF)) return rc;
-    if (int rc = upload(bu, dbu, N, Np, INF, INF)) return rc;
-    if (int rc = upload(lo, dlo, M, Mp, -INF, -INF)) return rc;
-    if (int rc = upload(hi, dhi, M, Mp, INF, INF)) return rc;
-    if (npairs) if (int rc = upload(rho, drho, npairs, npairs, 1.0, 1.0)) return rc;
-    h.assign((size_t)Bp, 0.0);
-    if (simplex_rows) for (int b = 0; b < B; ++b) h[b] = simplex_w[b];
-    MBRF_CUDA(cudaMemcpyAsync(dct, h.data(), (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
+    if (dev_fill) {                                              // assembled on the device (mbrf_fir_ap_solve)
+        if (int rc = hooks->fill(p, dextra, st)) return rc;
+    } else {
+        if (int rc = upload(c, dc, N, Np, 0.0, 0.0)) return rc;
+        if (int rc = upload(bl, dbl, N, Np, -INF, -INF)) return rc;
+        if (int rc = upload(bu, dbu, N, Np, INF, INF)) return rc;
+        if (int rc = upload(lo, dlo, M, Mp, -INF, -INF)) return rc;
+        if (int rc = upload(hi, dhi, M, Mp, INF, INF)) return rc;
+        if (npairs) if (int rc = upload(rho, drho, npairs, npairs, 1.0, 1.0)) return rc;
+        h.assign((size_t)Bp, 0.0);
+        if (simplex_rows) for (int b = 0; b < B; ++b) h[b] = simplex_w[b];
+        MBRF_CUDA(cudaMemcpyAsync(dct, h.data(), (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
+    }
     MBRF_CUDA(cudaStreamSynchronize(st));
 
     // ---- matrix ----
@@ -1612,14 +1635,238 @@ int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const do
     disks(PH_METRICS, 0); MBRF_LAUNCH_CHECK();
     finish2_kernel<<<(B + 127) / 128, 128, 0, st>>>(p, dinfo);
     MBRF_LAUNCH_CHECK();
-    h.assign((size_t)Np * Bp, 0.0);
+    if (hooks && hooks->after)
+        if (int rc = hooks->after(p, dzout, dinfo, dextra, st)) return rc;
     std::vector<double> info((size_t)Bp * 8);
-    MBRF_CUDA(cudaMemcpyAsync(h.data(), dzout, (size_t)Np * Bp * 8, cudaMemcpyDeviceToHost, st));
+    if (z_out) {
+        h.assign((size_t)Np * Bp, 0.0);
+        MBRF_CUDA(cudaMemcpyAsync(h.data(), dzout, (size_t)Np * Bp * 8, cudaMemcpyDeviceToHost, st));
+    }
     MBRF_CUDA(cudaMemcpyAsync(info.data(), dinfo, (size_t)Bp * 64, cudaMemcpyDeviceToHost, st));
     MBRF_CUDA(cudaStreamSynchronize(st));
-    for (int j = 0; j < N; ++j)
-        for (int b = 0; b < B; ++b) z_out[(size_t)j * B + b] = h[(size_t)j * Bp + b];
+    if (z_out)
+        for (int j = 0; j < N; ++j)
+            for (int b = 0; b < B; ++b) z_out[(size_t)j * B + b] = h[(size_t)j * Bp + b];
     memcpy(info_out, info.data(), (size_t)B * 64);
+    return MBRF_OK;
+}
+
+namespace mbrf {
+namespace ipm {
+
+// Host part of the device-side assembly: the union grid of a batch, the specification on the device, pass 1 (per-design
+// reductions) and the rows of the stop block.
+struct ApPrep {
+    std::vector<double> w;               // union grid, sorted, unique
+    std::vector<unsigned char> is_base;
+    std::vector<int> srows;              // union rows that are a stop row of at least one design
+    int M1 = 0, ns = 0;
+    assemble::ApSpec sp;
+    double *dw = nullptr;
+    unsigned char *dbase = nullptr;
+    int *dsrows = nullptr;
+    assemble::ApRed *dred = nullptr;
+
+    int run(int n, int nband, const double *f, const double *a, const double *d, const double *obj, const double *peak, int B,
+            int oversamp)
+    {
+        using namespace mbrf::assemble;
+        if (n < 2 || nband < 1 || nband > MAX_BANDS || B < 1 || !f || !a || !d || !obj || !peak || oversamp < 1) {
+            set_error("fir_ap: bad arguments (n=%d nband=%d B=%d)", n, nband, B);
+            return MBRF_EINVAL;
+        }
+        // ---- union grid: w = sort([linspace(-pi, pi, 2 n oversamp), f*pi]) of every design (fir_ap_cvx.m:44-48), unique ----
+        const int m = 2 * n * oversamp, ne = 2 * nband;
+        std::vector<double> fw((size_t)B * ne);
+        for (size_t k = 0; k < fw.size(); ++k) fw[k] = f[k] * M_PI;              // :44
+        std::vector<std::pair<double, unsigned char>> grid;
+        grid.reserve((size_t)m + fw.size());
+        {
+            const double start = -M_PI, stop = M_PI;
+            volatile double step = (stop - start) / (double)(m - 1);             // numpy / MATLAB linspace: i*step + start, last = stop
+            for (int i = 0; i < m; ++i) {
+                volatile double t = (double)i * step;
+                t = t + start;
+                grid.push_back({i == m - 1 ? stop : (double)t, (unsigned char)1});
+            }
+        }
+        for (double v : fw) grid.push_back({v, (unsigned char)0});
+        std::sort(grid.begin(), grid.end(),
+                  [](const auto &x, const auto &y) { return x.first < y.first || (x.first == y.first && x.second > y.second); });
+        for (const auto &g : grid) {
+            if (!w.empty() && w.back() == g.first) continue;                     // base samples sort first among equals
+            w.push_back(g.first);
+            is_base.push_back(g.second);
+        }
+        M1 = (int)w.size();
+
+        // ---- pass 1 on the device: per-design reductions and the rows of the stop block ----
+        static thread_local DeviceScratch pre;
+        auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+        const size_t b_spec = al((size_t)B * ne * 8), b_d = al((size_t)B * nband * 8), b_B = al((size_t)B * 8);
+        const size_t pre_bytes = al((size_t)M1 * 8) + 2 * al((size_t)M1) + 2 * b_spec + b_d + 2 * b_B + al((size_t)B * sizeof(ApRed)) +
+                                 al((size_t)M1 * 4);
+        if (int rc = pre.reserve(pre_bytes)) return rc;
+        char *q = (char *)pre.ptr;
+        auto take = [&](size_t bytes) { char *r = q; q += al(bytes); return r; };
+        dw = (double *)take((size_t)M1 * 8);
+        dbase = (unsigned char *)take((size_t)M1);
+        unsigned char *dany = (unsigned char *)take((size_t)M1);
+        double *df = (double *)take((size_t)B * ne * 8), *da = (double *)take((size_t)B * ne * 8), *dd_ = (double *)take((size_t)B * nband * 8);
+        double *dobj = (double *)take((size_t)B * 8), *dpeak = (double *)take((size_t)B * 8);
+        dred = (ApRed *)take((size_t)B * sizeof(ApRed));
+        dsrows = (int *)take((size_t)M1 * 4);
+        cudaStream_t s0 = 0;
+        MBRF_CUDA(cudaMemcpyAsync(dw, w.data(), (size_t)M1 * 8, cudaMemcpyHostToDevice, s0));
+        MBRF_CUDA(cudaMemcpyAsync(dbase, is_base.data(), (size_t)M1, cudaMemcpyHostToDevice, s0));
+        MBRF_CUDA(cudaMemcpyAsync(df, fw.data(), (size_t)B * ne * 8, cudaMemcpyHostToDevice, s0));
+        MBRF_CUDA(cudaMemcpyAsync(da, a, (size_t)B * ne * 8, cudaMemcpyHostToDevice, s0));
+        MBRF_CUDA(cudaMemcpyAsync(dd_, d, (size_t)B * nband * 8, cudaMemcpyHostToDevice, s0));
+        MBRF_CUDA(cudaMemcpyAsync(dobj, obj, (size_t)B * 8, cudaMemcpyHostToDevice, s0));
+        MBRF_CUDA(cudaMemcpyAsync(dpeak, peak, (size_t)B * 8, cudaMemcpyHostToDevice, s0));
+        sp.f = df; sp.a = da; sp.d = dd_; sp.obj = dobj; sp.peak = dpeak; sp.nband = nband; sp.n = n; sp.B = B;
+        ap_reduce_kernel<<<B, 256, 0, s0>>>(sp, dw, dbase, M1, dred);
+        MBRF_LAUNCH_CHECK();
+        ap_stop_any_kernel<<<(M1 + 7) / 8, 256, 0, s0>>>(sp, dw, dbase, M1, dred, dany);
+        MBRF_LAUNCH_CHECK();
+        std::vector<unsigned char> any((size_t)M1);
+        MBRF_CUDA(cudaMemcpyAsync(any.data(), dany, (size_t)M1, cudaMemcpyDeviceToHost, s0));
+        MBRF_CUDA(cudaStreamSynchronize(s0));
+        for (int i = 0; i < M1; ++i) if (any[i]) srows.push_back(i);
+        ns = (int)srows.size();
+        if (ns) MBRF_CUDA(cudaMemcpyAsync(dsrows, srows.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, s0));
+        MBRF_CUDA(cudaStreamSynchronize(s0));
+        return MBRF_OK;
+    }
+};
+
+}  // namespace ipm
+}  // namespace mbrf
+
+extern "C" {
+
+int mbrf_fir_ipm_solve(const double *w_row, int M, const int *col_type, const double *col_kappa, const double *col_amp, int N,
+                       const int *pair_i, const int *pair_j, int npairs, const double *c, const double *lo, const double *hi,
+                       const double *bl, const double *bu, const double *rho, int B, int simplex_row0, int simplex_rows,
+                       const double *simplex_w, int max_iter, double feastol, double reltol, double abstol, double *z_out,
+                       double *info_out)
+{
+    return ipm_solve_impl(w_row, M, col_type, col_kappa, col_amp, N, pair_i, pair_j, npairs, c, lo, hi, bl, bu, rho, B, simplex_row0,
+                          simplex_rows, simplex_w, max_iter, feastol, reltol, abstol, z_out, info_out, nullptr);
+}
+
+/*
+ * fir_ap_cvx (fir_ap_cvx.m:1-245) for a batch of designs of one order n, specification in, taps out: the union grid is built
+ * here on the host (a few thousand doubles), everything per design -- band masks, bounds, stop rows, radii (:51-142) -- is
+ * assembled on the device (fir_assemble.cuh), the batch is solved by the interior-point method, and the minimum-phase factor
+ * h = fmp2(r) (:185-202) of every solved design is taken on the device from the solutions before anything is copied back.
+ */
+int mbrf_fir_ap_solve(int n, int nband, const double *f, const double *a, const double *d, const double *obj, const double *peak,
+                      int B, int oversamp, int max_iter, double feastol, double reltol, double abstol, double *x_out, double *h_re,
+                      double *h_im, double *info_out, int *rows_out)
+{
+    using namespace mbrf::assemble;
+    if (int rc = require_device()) return rc;
+    if (!info_out) { set_error("fir_ap_solve: info_out is required"); return MBRF_EINVAL; }
+    if ((h_re || h_im) && (!h_re || !h_im || n > mbrf_fmp2_max_taps())) {
+        set_error("fir_ap_solve: taps need both planes and n <= %d", mbrf_fmp2_max_taps());
+        return MBRF_EINVAL;
+    }
+    ApPrep pr;
+    if (int rc = pr.run(n, nband, f, a, d, obj, peak, B, oversamp)) return rc;
+    const int M1 = pr.M1, ns = pr.ns, M = M1 + ns;
+    const std::vector<double> &w = pr.w;
+    const std::vector<int> &srows = pr.srows;
+    const ApSpec sp = pr.sp;
+    double *dw = pr.dw;
+    unsigned char *dbase = pr.dbase;
+    int *dsrows = pr.dsrows;
+    ApRed *dred = pr.dred;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    if (rows_out) { rows_out[0] = M1; rows_out[1] = ns; }
+
+    // ---- matrix description: A = [1, 2cos(w k), 2sin(w k)], k = 1..n-1 (:100); pairs (x_i, x_{n+i-1}), i = 2..n (:133-139) ----
+    const int N = 2 * n - 1, np = n - 1;
+    std::vector<double> w_row((size_t)M), kappa((size_t)N), amp((size_t)N);
+    std::vector<int> type((size_t)N), pi((size_t)np), pj((size_t)np);
+    for (int i = 0; i < M1; ++i) w_row[i] = w[i];
+    for (int k = 0; k < ns; ++k) w_row[M1 + k] = w[srows[k]];
+    type[0] = 0; kappa[0] = 0.0; amp[0] = 1.0;
+    for (int k = 1; k < n; ++k) {
+        type[k] = 1; type[n - 1 + k] = 2;
+        kappa[k] = kappa[n - 1 + k] = (double)k;
+        amp[k] = amp[n - 1 + k] = 2.0;
+        pi[k - 1] = k; pj[k - 1] = n - 1 + k;
+    }
+    const int len = 2 * n - 1;
+    Hooks hk;
+    const size_t b_r = al((size_t)B * len * 8), b_h = al((size_t)B * n * 8), b_tw = al((size_t)mbrf_fmp2_workspace_bytes(n));
+    hk.extra_bytes = 3 * b_r + 2 * b_h + b_tw;
+    hk.fill = [&](const P &p, void *, cudaStream_t st) -> int {
+        ap_fill_rows_kernel<<<dim3((p.Bp + 127) / 128, p.Mp), 128, 0, st>>>(sp, dw, dbase, M1, dsrows, ns, dred, p.Mp, p.Bp,
+                                                                             (double *)p.lo, (double *)p.hi);
+        MBRF_LAUNCH_CHECK();
+        const int rows = p.Np > p.npairs ? p.Np : p.npairs;
+        ap_fill_cols_kernel<<<dim3((p.Bp + 127) / 128, rows), 128, 0, st>>>(sp, p.Np, p.Bp, p.npairs, (double *)p.c, (double *)p.bl,
+                                                                             (double *)p.bu, (double *)p.rho, (double *)p.ct);
+        MBRF_LAUNCH_CHECK();
+        return MBRF_OK;
+    };
+    hk.after = [&](const P &p, const double *x, const double *, void *extra, cudaStream_t st) -> int {
+        char *e = (char *)extra;
+        double *rr = (double *)e, *ri = (double *)(e + b_r), *xr = (double *)(e + 2 * b_r);
+        double *hr = (double *)(e + 3 * b_r), *hi_ = (double *)(e + 3 * b_r + b_h);
+        void *tw = e + 3 * b_r + 2 * b_h;
+        ap_x_to_r_kernel<<<dim3((len + 127) / 128, B), 128, 0, st>>>(x, n, B, p.Bp, rr, ri, xr);
+        MBRF_LAUNCH_CHECK();
+        if (x_out) MBRF_CUDA(cudaMemcpyAsync(x_out, xr, (size_t)B * len * 8, cudaMemcpyDeviceToHost, st));
+        if (h_re) {
+            if (int rc = mbrf_fmp2_batch_device(rr, ri, n, B, hr, hi_, tw, (void *)st)) return rc;
+            MBRF_CUDA(cudaMemcpyAsync(h_re, hr, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));
+            MBRF_CUDA(cudaMemcpyAsync(h_im, hi_, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));
+        }
+        return MBRF_OK;
+    };
+    return ipm_solve_impl(w_row.data(), M, type.data(), kappa.data(), amp.data(), N, pi.data(), pj.data(), np, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, B, M1, ns, nullptr, max_iter, feastol, reltol, abstol, nullptr, info_out, &hk);
+}
+
+/* Assembly alone (the arrays mbrf_fir_ap_solve hands to the solver), for callers that pose the problem to another solver and
+ * for the parity tests.  Call once with lo_out == NULL to learn rows_out = {grid rows M1, stop-block rows ns}. */
+int mbrf_fir_ap_assemble(int n, int nband, const double *f, const double *a, const double *d, const double *obj, const double *peak,
+                         int B, int oversamp, int *rows_out, double *w_row_out, double *lo_out, double *hi_out, double *c_out,
+                         double *bl_out, double *bu_out, double *rho_out, double *ct_out)
+{
+    using namespace mbrf::assemble;
+    if (int rc = require_device()) return rc;
+    if (!rows_out) { set_error("fir_ap_assemble: rows_out is required"); return MBRF_EINVAL; }
+    ApPrep pr;
+    if (int rc = pr.run(n, nband, f, a, d, obj, peak, B, oversamp)) return rc;
+    rows_out[0] = pr.M1; rows_out[1] = pr.ns;
+    if (!lo_out) return MBRF_OK;
+    if (!w_row_out || !hi_out || !c_out || !bl_out || !bu_out || !rho_out || !ct_out) { set_error("fir_ap_assemble: output arrays missing"); return MBRF_EINVAL; }
+    const int M = pr.M1 + pr.ns, N = 2 * n - 1, np = n - 1;
+    static thread_local DeviceScratch out;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t rb = al((size_t)M * B * 8), cb = al((size_t)N * B * 8), pb = al((size_t)np * B * 8), bb = al((size_t)B * 8);
+    if (int rc = out.reserve(2 * rb + 3 * cb + pb + bb)) return rc;
+    char *q = (char *)out.ptr;
+    double *lo = (double *)q, *hi = (double *)(q + rb), *c = (double *)(q + 2 * rb), *bl = (double *)(q + 2 * rb + cb),
+           *bu = (double *)(q + 2 * rb + 2 * cb), *rho = (double *)(q + 2 * rb + 3 * cb), *ct = (double *)(q + 2 * rb + 3 * cb + pb);
+    ap_fill_rows_kernel<<<dim3((B + 127) / 128, M), 128>>>(pr.sp, pr.dw, pr.dbase, pr.M1, pr.dsrows, pr.ns, pr.dred, M, B, lo, hi);
+    MBRF_LAUNCH_CHECK();
+    ap_fill_cols_kernel<<<dim3((B + 127) / 128, N > np ? N : np), 128>>>(pr.sp, N, B, np, c, bl, bu, rho, ct);
+    MBRF_LAUNCH_CHECK();
+    MBRF_CUDA(cudaMemcpyAsync(lo_out, lo, (size_t)M * B * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaMemcpyAsync(hi_out, hi, (size_t)M * B * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaMemcpyAsync(c_out, c, (size_t)N * B * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaMemcpyAsync(bl_out, bl, (size_t)N * B * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaMemcpyAsync(bu_out, bu, (size_t)N * B * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaMemcpyAsync(rho_out, rho, (size_t)np * B * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaMemcpyAsync(ct_out, ct, (size_t)B * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaStreamSynchronize(0));
+    for (int i = 0; i < pr.M1; ++i) w_row_out[i] = pr.w[i];
+    for (int k = 0; k < pr.ns; ++k) w_row_out[pr.M1 + k] = pr.w[pr.srows[k]];
     return MBRF_OK;
 }
 

@@ -40,6 +40,9 @@ IPM_MAX_ITER = 100
 # obj = 1e4 / 1e5) or "pdhg" (first order); MBRF_FIR_METHOD overrides
 import os as _os
 DEFAULT_METHOD = _os.environ.get("MBRF_FIR_METHOD", "ipm")
+# where fir_ap_cvx problems are assembled for the interior-point solver: "device" (mbrf_fir_ap_solve: specification in, taps
+# out) or "host" (numpy below + mbrf_fir_ipm_solve); the first-order solver always takes the host path
+DEFAULT_ASSEMBLE = _os.environ.get("MBRF_FIR_ASSEMBLE", "device")
 
 
 _OPTION_INDEX = {"eta_factor": 0, "beta_sufficient": 1, "beta_necessary": 2, "beta_artificial": 3, "omega_smoothing": 4,
@@ -137,19 +140,11 @@ def assemble_fir_ap(n, f, a, d, obj, peak, oversamp=15):
     return dict(n=n, w=w, lo=L_b, hi=U_b, stop=stop, obj=float(obj), radius=radius)
 
 
-def _solve_batch_ap(n, designs, max_iter=None, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR,
-                    eps_gap=EPS_GAP, warm=None, want_dual=False, method=None, ipm_max_iter=None):
-    """Solve designs (assemble_fir_ap dicts with one n) as ONE batch sharing one matrix.
-
-    Rows of the shared matrix = union over the batch of the designs' grid points (the base grid is common,
-    band-edge samples differ), followed by one duplicate of every row that is a stop-band row of at least
-    one design (the `A_U(idx_stop,:)*x <= ripple_stop` block, fir_ap_cvx.m:165).  A row a design does not
-    own gets the bounds (-inf, +inf) for that design.
-    warm = (x0 [B, 2n-1], y0 [B, M], omega0 [B]) starts the iteration from a neighbouring design's solution (entries may
-    be None); want_dual=True appends (y [B, M], omega [B]) to the result, in the row order of THIS batch's matrix (valid as a
-    warm start for batches with the same grids and stop rows, e.g. the other designs of an obj x Peak sweep).
-    Returns x [B, 2n-1], ripple_stop [B], info [B, 8].
-    """
+def _assemble_batch_ap(n, designs):
+    """Host assembly of a batch (assemble_fir_ap dicts of one n) into the arrays of the C ABI: one matrix shared through the
+    union of the designs' grids, [dim x B] per-design arrays.  Returns a dict (w_row, M, M1, srows, N, c, lo, hi, bl, bu, rho,
+    upper, sw, col_type, col_kappa, col_amp, pair_i, pair_j).  `mbrf_fir_ap_assemble` / `mbrf_fir_ap_solve` do the same on
+    the device (bit-identical, tests/test_fir_assemble_gpu.py); this version feeds the first-order solver."""
     B = len(designs)
     # designs of a sweep mostly share their grid (only band-edge samples differ): deduplicate before the union
     keys = [id(p["w"]) for p in designs]           # assemble_fir_ap hands out cached (shared) arrays per band specification
@@ -220,11 +215,33 @@ def _solve_batch_ap(n, designs, max_iter=None, check_every=CHECK_EVERY, eps_pr=E
     col_amp = np.concatenate([[1.0], np.full(2 * n - 2, 2.0)])            # A = [1, 2cos, 2sin], :100
     pair_i = np.arange(1, n, dtype=np.int32)                              # (x_i, x_{n+i-1}), :133-139
     pair_j = np.arange(n, 2 * n - 1, dtype=np.int32)
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho, upper, sw)]
+    w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho, upper, sw = arrs
+    return dict(w_row=w_row, M=M, M1=M1, srows=srows, N=N, c=c, lo=lo, hi=hi, bl=bl, bu=bu, rho=rho, upper=upper, sw=sw,
+                col_type=col_type, col_kappa=col_kappa, col_amp=col_amp, pair_i=pair_i, pair_j=pair_j)
+
+
+def _solve_batch_ap(n, designs, max_iter=None, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR,
+                    eps_gap=EPS_GAP, warm=None, want_dual=False, method=None, ipm_max_iter=None):
+    """Solve designs (assemble_fir_ap dicts with one n) as ONE batch sharing one matrix.
+
+    Rows of the shared matrix = union over the batch of the designs' grid points (the base grid is common,
+    band-edge samples differ), followed by one duplicate of every row that is a stop-band row of at least
+    one design (the `A_U(idx_stop,:)*x <= ripple_stop` block, fir_ap_cvx.m:165).  A row a design does not
+    own gets the bounds (-inf, +inf) for that design.
+    warm = (x0 [B, 2n-1], y0 [B, M], omega0 [B]) starts the iteration from a neighbouring design's solution (entries may
+    be None); want_dual=True appends (y [B, M], omega [B]) to the result, in the row order of THIS batch's matrix (valid as a
+    warm start for batches with the same grids and stop rows, e.g. the other designs of an obj x Peak sweep).
+    Returns x [B, 2n-1], ripple_stop [B], info [B, 8].
+    """
+    B = len(designs)
+    q = _assemble_batch_ap(n, designs)
+    M, M1, srows, N = q["M"], q["M1"], q["srows"], q["N"]
+    w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho, upper, sw = (q[k] for k in ("w_row", "col_kappa", "col_amp", "c", "lo", "hi",
+                                                                                      "bl", "bu", "rho", "upper", "sw"))
+    col_type, pair_i, pair_j = q["col_type"], q["pair_i"], q["pair_j"]
     z = np.zeros((N, B))
     info = np.zeros((B, 8))
-    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho,
-                                                                  upper, sw)]
-    w_row, col_kappa, col_amp, c, lo, hi, bl, bu, rho, upper, sw = arrs
     method = method or DEFAULT_METHOD
     if method == "ipm":
         if warm is not None or want_dual:
@@ -259,6 +276,51 @@ def _solve_batch_ap(n, designs, max_iter=None, check_every=CHECK_EVERY, eps_pr=E
     if want_dual:
         return z.T.copy(), info[:, 7].copy(), info, keep[3].T.copy(), keep[4].copy()
     return z.T.copy(), info[:, 7].copy(), info
+
+
+def _solve_batch_ap_device(n, f_list, a_list, d_list, obj_list, peak_list, ipm_max_iter=None, want_h=True, oversamp=15):
+    """fir_ap_cvx for B designs of one order through ONE C call (`mbrf_fir_ap_solve`): per-design assembly on the device,
+    interior-point solve, spectral factors on the device.  Returns x [B, 2n-1], h [B, n] complex (or None), info [B, 8],
+    (grid rows, stop rows)."""
+    B = len(f_list)
+    f = np.ascontiguousarray(np.stack([np.asarray(v, float).ravel() for v in f_list]))
+    a = np.ascontiguousarray(np.stack([np.asarray(v, float).ravel() for v in a_list]))
+    d = np.ascontiguousarray(np.stack([np.asarray(v, float).ravel() for v in d_list]))
+    nband = d.shape[1]
+    if f.shape != (B, 2 * nband) or a.shape != (B, 2 * nband):
+        raise ValueError("f and a need two entries per band, d one")
+    obj = np.ascontiguousarray(obj_list, dtype=float)
+    peak = np.ascontiguousarray(peak_list, dtype=float)
+    x = np.empty((B, 2 * n - 1))
+    info = np.zeros((B, 8))
+    hr = np.empty((B, n)) if want_h else None
+    hi = np.empty((B, n)) if want_h else None
+    rows = (C.c_int * 2)()
+    check(lib().mbrf_fir_ap_solve(int(n), nband, _dp(f), _dp(a), _dp(d), _dp(obj), _dp(peak), B, int(oversamp),
+                                  int(ipm_max_iter or IPM_MAX_ITER), IPM_FEASTOL, IPM_RELTOL, IPM_ABSTOL, _dp(x),
+                                  _dp(hr) if want_h else None, _dp(hi) if want_h else None, _dp(info), rows))
+    return x, (hr + 1j * hi) if want_h else None, info, (rows[0], rows[1])
+
+
+def assemble_fir_ap_device(n, f_list, a_list, d_list, obj_list, peak_list, oversamp=15):
+    """The arrays `mbrf_fir_ap_solve` hands to its solver, assembled on the device (`mbrf_fir_ap_assemble`), in the layout of
+    _assemble_batch_ap: dict(w_row, M, M1, ns, lo, hi, c, bl, bu, rho, sw)."""
+    B = len(f_list)
+    f = np.ascontiguousarray(np.stack([np.asarray(v, float).ravel() for v in f_list]))
+    a = np.ascontiguousarray(np.stack([np.asarray(v, float).ravel() for v in a_list]))
+    d = np.ascontiguousarray(np.stack([np.asarray(v, float).ravel() for v in d_list]))
+    nband = d.shape[1]
+    obj = np.ascontiguousarray(obj_list, dtype=float)
+    peak = np.ascontiguousarray(peak_list, dtype=float)
+    rows = (C.c_int * 2)()
+    args = (int(n), nband, _dp(f), _dp(a), _dp(d), _dp(obj), _dp(peak), B, int(oversamp), rows)
+    check(lib().mbrf_fir_ap_assemble(*args, None, None, None, None, None, None, None, None))
+    M1, ns = rows[0], rows[1]
+    M, N = M1 + ns, 2 * n - 1
+    out = dict(w_row=np.empty(M), lo=np.empty((M, B)), hi=np.empty((M, B)), c=np.empty((N, B)), bl=np.empty((N, B)),
+               bu=np.empty((N, B)), rho=np.empty((n - 1, B)), sw=np.empty(B))
+    check(lib().mbrf_fir_ap_assemble(*args, *[_dp(out[k]) for k in ("w_row", "lo", "hi", "c", "bl", "bu", "rho", "sw")]))
+    return dict(out, M=M, M1=M1, ns=ns)
 
 
 # --------------------------------------------------------------------------------------------
@@ -371,10 +433,27 @@ def fir_ap_cvx_decided(n, f_list, a, d, obj_list, peak_list, **solver_kw):
 def fir_ap_cvx_batch(n, f_list, a, d, obj_list, peak_list, return_info=False, **solver_kw):
     """Batched fir_ap_cvx: designs i = 0..B-1 with band edges f_list[i], trade-off obj_list[i], Peak peak_list[i]
     (a, d shared or per-design lists).  Returns (h_list, status_list[, info]); h is None where 'Failed'.
-    info["info"][:, 0] keeps what the string cannot: 1 solved, 2 infeasible (certificate), 3 iteration limit (undecided)."""
+    info["info"][:, 0] keeps what the string cannot: 1 solved, 2 infeasible (certificate), 3 iteration limit (undecided).
+    With the interior-point solver the whole batch is ONE C call (assemble="device", the default: specification in, taps out);
+    assemble="host" builds the problem in numpy and hands the arrays over."""
     B = len(f_list)
     a_list = a if isinstance(a, (list, tuple)) and np.ndim(a[0]) else [a] * B
     d_list = d if isinstance(d, (list, tuple)) and np.ndim(d[0]) else [d] * B
+    assemble = solver_kw.pop("assemble", None) or DEFAULT_ASSEMBLE
+    if (solver_kw.get("method") or DEFAULT_METHOD) == "ipm" and assemble == "device":
+        extra = set(solver_kw) - {"method", "ipm_max_iter"}
+        if extra:
+            raise TypeError(f"options {sorted(extra)} belong to the first-order solver")
+        x, hmp, info, _ = _solve_batch_ap_device(int(n), f_list, a_list, d_list, obj_list, peak_list,
+                                                 ipm_max_iter=solver_kw.get("ipm_max_iter"))
+        ok = info[:, 0] == 1.0
+        status = ["Solved" if o else "Failed" for o in ok]               # fir_ap_cvx.m:176-182
+        hs = [hmp[b] if ok[b] else None for b in range(B)]
+        if return_info:
+            return hs, status, dict(x=x, ripple_stop=info[:, 7].copy(), info=info)
+        return hs, status
+    if assemble not in ("device", "host"):
+        raise ValueError(f"unknown assemble {assemble!r}: 'device' or 'host'")
     designs = [assemble_fir_ap(n, f_list[i], a_list[i], d_list[i], obj_list[i], peak_list[i]) for i in range(B)]
     x, t, info = _solve_batch_ap(n, designs, **solver_kw)
     ok = info[:, 0] == 1.0                # 1 solved; 2 infeasible certificate; 3 iteration limit -> 'Failed'
@@ -541,7 +620,14 @@ def fir_ap_cvx_sweep(n, f, a, d, objs, peaks, f_adds, rank=0, world=1, batch=512
     mine = np.arange(rank, len(fl), world)
     concurrent = int(solver_kw.pop("concurrent_batches", 0) or 0)
 
+    assemble = solver_kw.pop("assemble", None) or DEFAULT_ASSEMBLE
+    on_device = (solver_kw.get("method") or DEFAULT_METHOD) == "ipm" and assemble == "device"
+
     def solve_batch(ids):
+        if on_device:                                   # specification in, solutions out: no host assembly, no [M x B] upload
+            x, _, info, _ = _solve_batch_ap_device(n, [fl[i] for i in ids], [a] * len(ids), [d] * len(ids), [ol[i] for i in ids],
+                                                   [pl[i] for i in ids], ipm_max_iter=solver_kw.get("ipm_max_iter"), want_h=False)
+            return x, info[:, 7].copy(), info
         designs = [assemble_fir_ap(n, fl[i], a, d, ol[i], pl[i]) for i in ids]
         stride = seed_stride
         if stride == "auto":                            # seeds about 0.1 decades of the weight apart; coarser sweeps run cold

@@ -11,6 +11,20 @@ function [hs, sts, info, xs] = fir_ap_cvx_batch(n, fcell, a, d, objs, Peaks)
 B = numel(fcell);
 if isscalar(objs),  objs = repmat(objs, 1, B);   end
 if isscalar(Peaks), Peaks = repmat(Peaks, 1, B); end
+if ~strcmpi(getenv('MBRF_FIR_METHOD'), 'pdhg')
+    % interior point (default): ONE call, specification in -> taps out.  Grid, band masks, bounds, stop rows and radii
+    % (fir_ap_cvx.m:44-142) are assembled on the GPU, the batch is solved there and h = fmp2(r) (:185-202) is taken there too.
+    F = zeros(numel(fcell{1}), B);
+    for b = 1:B, F(:, b) = reshape(fcell{b}, [], 1); end
+    [H, info, xs] = fir_ap_mex(n, F, reshape(a, [], 1), reshape(d, [], 1), objs, Peaks);
+    hs = cell(1, B);   sts = cell(1, B);
+    for b = 1:B
+        if info(1, b) == 1, sts{b} = 'Solved';  hs{b} = H(:, b);          % 2: infeasible, 3: iteration limit -> 'Failed', :176-182
+        else,               sts{b} = 'Failed';  hs{b} = [];  end
+    end
+    return
+end
+% first-order solver: the problem is assembled here and handed over as arrays
 amps = reshape(a, 1, []);   ripple = reshape(d, 1, []);
 W = cell(1, B);  LO = cell(1, B);  HI = cell(1, B);  STOP = cell(1, B);
 for b = 1:B
@@ -70,13 +84,8 @@ upper_obj = zeros(1, B);
 for b = 1:B, upper_obj(b) = n*Peaks(b) + objs(b) * max(HI{b}(STOP{b})); end
 blocks = [M1+1, ns, 0, 0, 0, 0, 0, 0, 0];
 block_w = [reshape(objs, 1, []); zeros(3, B)];
-if strcmpi(getenv('MBRF_FIR_METHOD'), 'pdhg')
-    [z, info] = fir_solve_mex(0, w_row, [], [], col_type, col_kappa, col_amp, [], 2:n, n+1:2*n-1, c, lo, hi, bl, bu, rho, ...
-                              upper_obj, [200000, 64, 8e-7, 1e-4, 5e-5], blocks, block_w);
-else
-    [z, info] = fir_solve_mex(1, w_row, [], [], col_type, col_kappa, col_amp, [], 2:n, n+1:2*n-1, c, lo, hi, bl, bu, rho, ...
-                              [], [100, 1e-7, 2e-6, 1e-12], blocks, block_w);
-end
+[z, info] = fir_solve_mex(0, w_row, [], [], col_type, col_kappa, col_amp, [], 2:n, n+1:2*n-1, c, lo, hi, bl, bu, rho, ...
+                          upper_obj, [200000, 64, 8e-7, 1e-4, 5e-5], blocks, block_w);
 xs = z;
 hs = cell(1, B);   sts = cell(1, B);
 ok = find(info(1, :) == 1);                           % 2: infeasible, 3: iteration limit -> 'Failed', :176-182

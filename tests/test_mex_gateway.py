@@ -16,7 +16,7 @@ MEX = os.path.join(ROOT, "multiband_rf_pulse_design_b200", "matlab")
 @pytest.fixture(scope="module")
 def gateways(mbrf):
     subprocess.check_call(["make", "-s", "-C", MEX, "check"])
-    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "fir_solve", "b2a", "ab2rf", "fmp2", "flip_zero")}
+    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "fir_solve", "b2a", "ab2rf", "fmp2", "flip_zero", "fir_ap")}
 
 
 def test_gateways_link_and_report_errors_like_the_reference(gateways, oracle, mbrf):
@@ -303,3 +303,33 @@ def test_fir_solve_gateway_like_fir_qprog_phs_m(gateways, oracle):
     r = O.solve_fir_qprog_phs_reference(o)
     assert r.success and (o["A"] @ z[:, 0] - o["B"]).max() < 1e-6
     assert abs(np.linalg.norm(z[:, 0]) - np.linalg.norm(r.x)) < 1e-4 * np.linalg.norm(r.x)
+
+
+def test_fir_ap_gateway_usage_errors(gateways, oracle):
+    out, err = oracle.mex_call(gateways["fir_ap"], 1, 24.0, np.zeros((6, 2)))
+    assert out is None and err.startswith("Usage: [H, info, X, rows] = fir_ap_mex")
+    out, err = oracle.mex_call(gateways["fir_ap"], 1, 24.0, np.zeros((5, 2)), np.zeros((5, 1)), np.zeros((2, 1)), 1.0, 1e-3)
+    assert out is None and err == "fir_ap_mex: F must be 2*nband-by-B"
+    out, err = oracle.mex_call(gateways["fir_ap"], 1, 24.0, np.zeros((6, 2)), np.zeros((4, 1)), np.zeros((3, 1)), 1.0, 1e-3)
+    assert out is None and err == "fir_ap_mex: A must be 2*nband-by-B or one column"
+
+
+@pytest.mark.gpu
+def test_fir_ap_gateway_like_fir_ap_cvx_batch_m(gateways, oracle):
+    """fir_ap_mex with the arguments matlab/fir_ap_cvx_batch.m builds (F one design per column, shared a / d columns, obj and
+    Peak vectors): the known answer of tests/golden/fir_ap_known.json and an infeasible neighbour in the same batch."""
+    import json
+    from multiband_rf_pulse_design_b200 import fir
+    k = json.load(open(os.path.join(ROOT, "tests", "golden", "fir_ap_known.json")))["lowpass_n24"]
+    n = k["n"]
+    f = np.asarray(k["f"], float)
+    F = np.column_stack([f, f])
+    outs, err = oracle.mex_call(gateways["fir_ap"], 4, float(n), F, np.asarray(k["a"], float).reshape(-1, 1),
+                                np.asarray(k["d"], float).reshape(-1, 1), np.array([k["obj"], k["obj"]]), np.array([k["peak"], 1e-7]))
+    assert err is None, err
+    H, info, X, rows = outs
+    assert H.shape == (n, 2) and info.shape == (8, 2) and X.shape == (2 * n - 1, 2)
+    assert info[0, 0] == 1.0 and info[0, 1] == 2.0                         # Peak = 1e-7 cannot carry the pass band: certificate
+    hs, st, ex = fir.fir_ap_cvx_batch(n, [f], k["a"], k["d"], [k["obj"]], [k["peak"]], return_info=True)
+    assert abs(info[2, 0] - ex["info"][0, 2]) <= 1e-7 * abs(ex["info"][0, 2])
+    assert np.abs(H[:, 0] - hs[0]).max() < 1e-6
