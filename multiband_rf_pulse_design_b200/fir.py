@@ -441,9 +441,7 @@ def fir_ap_cvx_batch(n, f_list, a, d, obj_list, peak_list, return_info=False, **
     d_list = d if isinstance(d, (list, tuple)) and np.ndim(d[0]) else [d] * B
     assemble = solver_kw.pop("assemble", None) or DEFAULT_ASSEMBLE
     if (solver_kw.get("method") or DEFAULT_METHOD) == "ipm" and assemble == "device":
-        extra = set(solver_kw) - {"method", "ipm_max_iter"}
-        if extra:
-            raise TypeError(f"options {sorted(extra)} belong to the first-order solver")
+        # (options of the first-order solver -- max_iter, eps_* -- are accepted and unused here, as on the host path)
         x, hmp, info, _ = _solve_batch_ap_device(int(n), f_list, a_list, d_list, obj_list, peak_list,
                                                  ipm_max_iter=solver_kw.get("ipm_max_iter"))
         ok = info[:, 0] == 1.0
