@@ -250,7 +250,8 @@ def leg_cfg4(args, m, lib, rank, world, dev, max_over_ranks, barrier):
     x 16 band-edge expansions f_add in linspace(0, 0.9 df_min/2) (fir_ap.m:70-83) = 4096 fir_ap_cvx designs at N = 256, the SAME
     grid at every GPU count (strong scaling): instance i goes to rank i mod world, every rank solves its share in batches of 512
     on the interior-point solver, the results (x, ripple_stop, status) are gathered on rank 0.  One timed pass through the
-    public API (host assembly + H2D + solve + D2H + gather inside the timed region)."""
+    public API: every batch is ONE C call (mbrf_fir_ap_solve: specification in, per-design assembly by kernels, solve, D2H of
+    the solutions) plus the gather, all inside the timed region."""
     from multiband_rf_pulse_design_b200 import fir
     from multiband_rf_pulse_design_b200.shard import gather_sweep
     n = 256
@@ -289,8 +290,9 @@ def leg_cfg4(args, m, lib, rank, world, dev, max_over_ranks, barrier):
            "seconds": sec, "seconds_solve_only": sec_solve, "scaling": "strong",
            "workload": "cfg4: fir_ap_cvx, dual-band H-1 sat spec, N=256, 7686-row grid, %d obj in logspace(-2,4) x %d Peak in "
                        "logspace(-4,-2) x %d f_add in linspace(0, 0.9 df_min/2); same grid at every GPU count" % (no, npk, nfa),
-           "method": "interior point (mbrf_fir_ipm_solve): structured normal matrix from Toeplitz/Hankel moments, batched "
-                     "double-double Cholesky", "batch": batch, "concurrent_batches": 2,
+           "method": "interior point (mbrf_fir_ap_solve): problem assembly on the device (band masks, bounds, stop rows, radii by "
+                     "kernels; only the union grid is built on the host), structured normal matrix from Toeplitz/Hankel moments, "
+                     "batched double-double Cholesky", "assembly": fir.DEFAULT_ASSEMBLE, "batch": batch, "concurrent_batches": 2,
            "status_counts": {"solved": int(ok.sum()), "infeasible_certificate": int((st == 2).sum()),
                              "iteration_limit": int((st == 3).sum())},
            "iterations_mean": float(info[:, 1].mean()), "iterations_max": float(info[:, 1].max()),
@@ -407,6 +409,48 @@ def leg_cfg5(m, lib, rank, world, allgather_obj, barrier):
         out["linear_phase"] = {"call": "fir_min_order_linprog(512, f, a, d)", "status": st, "taps": int(len(h)), "seconds": time.perf_counter() - t1,
                                "duration_ms": float(len(h) * dt)}
     barrier()
+    return out
+
+
+def leg_post(lib):
+    """The steps around the solve, one GPU: fir_flip_zero at the reference's cap of 2^12 flip patterns
+    on a 256-tap filter (fir_flip_zero.m:45-99: one poly() per pattern in a MATLAB loop; here one CTA per pattern), with the
+    numpy restatement of that loop timed on one host core for a sample of the patterns; and one fir_qprog_phs design."""
+    from multiband_rf_pulse_design_b200 import fir_post as P
+    from oracle import fir_post as O
+    rng = np.random.default_rng(0)
+    nsb, npb = 243, 12
+    zs = np.exp(1j * np.linspace(0.25 * np.pi, 1.75 * np.pi, nsb))
+    zp = rng.uniform(0.6, 0.9, npb) * np.exp(1j * rng.uniform(-0.2, 0.2, npb) * np.pi)
+    Z = np.concatenate([zs, zp])[rng.permutation(nsb + npb)]
+    idx = np.nonzero(np.abs(np.abs(Z) - 1) > 1e-2)[0]
+    mask = P.flip_patterns(idx.size)
+    P.flip_zero_candidates(Z, idx, mask, 1.0)
+    l0 = lib.mbrf_launch_count()
+    t = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        r = P.flip_zero_candidates(Z, idx, mask, 1.0)
+    gpu = (time.perf_counter() - t) / reps
+    launches = (lib.mbrf_launch_count() - l0) // reps
+    t = time.perf_counter()
+    sample = 64
+    for i in range(sample):
+        Ze = Z.copy()
+        Ze[idx] = np.where(mask[i].astype(bool), 1 / np.abs(Z[idx]) * np.exp(1j * np.angle(Z[idx])), Z[idx])
+        O.poly_reference(Ze)
+    cpu = (time.perf_counter() - t) / sample * mask.shape[0]
+    out = {"flip_zero": {"taps": int(Z.size + 1), "patterns": int(mask.shape[0]), "seconds_call": gpu, "patterns_per_s": mask.shape[0] / gpu,
+                         "gpu_launches_per_call": int(launches), "best": int(r["best"]),
+                         "cpu_baseline": {"seconds": cpu, "cores": 1, "kind": "port",
+                                          "sample": "%d of the %d patterns through oracle/fir_post.py:poly_reference (numpy), extrapolated" % (sample, mask.shape[0])}}}
+    spec = dict(f=[-0.6, -0.35, -0.15, 0.15, 0.35, 0.6], a=[0, 0, 1, 1, 0, 0], d=[0.02, 0.05 * np.exp(0.2j), 0.02])
+    P.fir_qprog_phs(15, spec["f"], spec["a"], spec["d"])
+    t = time.perf_counter()
+    h, st, ex = P.fir_qprog_phs(63, spec["f"], spec["a"], spec["d"], return_info=True)
+    out["fir_qprog_phs"] = {"n": 63, "status": st, "seconds": time.perf_counter() - t, "iterations": float(ex["info"][1]),
+                            "rows": int(ex["problem"]["w"].size), "energy": float(np.linalg.norm(ex["x"])),
+                            "max_violation": float(ex["info"][4])}
     return out
 
 
@@ -722,6 +766,7 @@ def run_ours(args):
         solver["roofline"] = solver_roofline(lib, tf.value)
         solver["single_design"] = leg_cfg3(m, lib, hbm_peak) if not args.skip_single_design else None
         solver["order_search"] = cfg5
+        solver["post"] = leg_post(lib)
         if world == 1 and not args.no_cpu_baseline:
             solver["cpu_baseline"] = solver_cpu_baseline()
 

@@ -706,9 +706,11 @@ def _solve_seeded(n, designs, fkeys, peaks, objs, stride, **solver_kw):
 # --------------------------------------------------------------------------------------------
 # ss/fir_linprog.m — linear-phase (real or complex-Hermitian) FIR by LP
 # --------------------------------------------------------------------------------------------
-def assemble_fir_linprog(n, f, a, d):
+def assemble_fir_linprog(n, f, a, d, a_min=None):
     """ss/fir_linprog.m:46-240 -> rows w, bounds, column description, objective.  Returns None for the
-    'n even and amplitude 1 at fs/2' case the reference rejects up front (:63-75)."""
+    'n even and amplitude 1 at fs/2' case the reference rejects up front (:63-75).
+    a_min (ss/fir_min_order.m:14, ss/fir_pm.m:42-43,102): lower bound of the response in the transition regions; its default
+    min(0, min(a - d)) is what fir_linprog.m:165-170 uses."""
     f = np.asarray(f, float).ravel() * np.pi                              # :46
     a = np.asarray(a, float).ravel()
     d = np.asarray(d, float).ravel()
@@ -728,7 +730,7 @@ def assemble_fir_linprog(n, f, a, d):
     idx_band, idx_tran, U, L = _bands(w, f, a, d)
     if idx_tran.size:                                                     # :163-171
         U_tran = np.full(idx_tran.size, U.max())
-        L_tran = np.full(idx_tran.size, min(0.0, L.min()))
+        L_tran = np.full(idx_tran.size, min(0.0, L.min()) if a_min is None or np.size(a_min) == 0 else float(a_min))
     else:
         U_tran = L_tran = np.zeros(0)
     w = np.concatenate([w[idx_band], w[idx_tran]])                        # :175-180
@@ -778,17 +780,45 @@ def _fill_h(x, p):
     return np.concatenate([np.conj(h[::-1]), h])
 
 
+def _fill_opt_param(h0, p):
+    """fill_opt_param, ss/fir_linprog.m:298-373, for a previous filter h0 of the same parity: the taps that fit are copied
+    into the optimisation vector, the rest stays zero.  Returns None where the reference falls back to its FFT initialisation
+    (no h0, or the other parity, :322-349) -- the solver then starts from its own point."""
+    if h0 is None or len(h0) == 0:
+        return None
+    h0 = np.asarray(h0).ravel()
+    nh = h0.size
+    if bool(nh & 1) != bool(p["odd"]):                                    # :332-336
+        return None
+    nh_half = int(np.ceil(nh / 2))
+    nx = p["col_type"].size
+    nx_half = nx if p["real"] else ((nx + 1) // 2 if p["odd"] else nx // 2)   # :305-313
+    k = min(nx_half, nh_half)
+    x0 = np.zeros(nx)
+    if p["odd"]:                                                          # :353-361 (1-based h0(nh_half : nh_half+k-1))
+        x0[:k] = h0[nh_half - 1:nh_half - 1 + k].real
+        if not p["real"]:
+            x0[nx_half:nx_half + k - 1] = h0[nh_half:nh_half + k - 1].imag
+    else:                                                                 # :362-371 (h0(nh_half+1 : nh_half+k))
+        x0[:k] = h0[nh_half:nh_half + k].real
+        if not p["real"]:
+            x0[nx_half:nx_half + k] = h0[nh_half:nh_half + k].imag
+    return x0
+
+
 def fir_linprog(n, f, a, d, h0=None, dbg=0, return_info=False, **solver_kw):
     """[h, status] = fir_linprog(n, f, a, d, h0, dbg) — ss/fir_linprog.m:2-272.
 
     The LP `min fmin*x s.t. [A;-A]x <= [U,-L]` (:246-252) is solved on the GPU, by default with the interior-point
     solver (method="ipm"; infeasible specifications end with a Farkas certificate -> 'Failed').  h0 is the reference's
     starting point for linprog's medium-scale algorithm (:157); an interior-point method starts from its own centred point
-    (MATLAB's linprog ignores x0 for its interior-point algorithm too), so h0 does not change the result and is not used.
+    (MATLAB's linprog ignores x0 for its interior-point algorithm too), so with method="ipm" h0 does not change the result and
+    is not used.  With method="pdhg" a previous filter of the same parity is the starting iterate, mapped as fill_opt_param
+    does (:298-373) -- what the reference's order searches do with `hbest`.
     method="pdhg" (first order) adds the redundant box |x_j| <= 2*max|bounds| so that its dual bound certifies
     infeasibility (|H| <= max U on a 15x oversampled grid bounds every Fourier coefficient by it)."""
     n = int(n)
-    p = assemble_fir_linprog(n, f, a, d)
+    p = assemble_fir_linprog(n, f, a, d, a_min=solver_kw.pop("a_min", None))
     if p is None:
         return (np.zeros(0), "Failed", dict(info=None)) if return_info else (np.zeros(0), "Failed")   # :68-72
     M, N = p["w"].size, p["col_type"].size
@@ -810,6 +840,10 @@ def fir_linprog(n, f, a, d, h0=None, dbg=0, return_info=False, **solver_kw):
         upper = arr([p["ntran"] * p["hi"].max() + 1e-9])                  # fmin*x = sum_tran H <= ntran*max U
         kw = dict(max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR, eps_gap=EPS_GAP)
         kw.update(solver_kw)
+        x0 = _fill_opt_param(h0, p)
+        if x0 is not None:                                                # x0 of fir_linprog.m:157 -> starting iterate
+            z0 = arr(x0.reshape(N, 1))
+            check(lib().mbrf_fir_pdhg_warm_start(_dp(z0), None, None, None, None))
         check(lib().mbrf_fir_pdhg_solve(_dp(w_row), None, M, _ip(p["col_type"]), _dp(kap), _dp(amp), N, -1, None, None, 0,
                                         _dp(cc), _dp(lo), _dp(hi), _dp(bl), _dp(bu), None, 1, _dp(upper), 0, 0, None,
                                         int(kw["max_iter"] or MAX_ITER), int(kw["check_every"]), float(kw["eps_pr"]),
@@ -902,9 +936,13 @@ def fir_min_order(n, f, a, d, even_odd=0, a_min=None, dbg=0, **solver_kw):
 
     The reference probes with fir_pm -> cfirpm (closed-source Parks-McClellan, ss/fir_pm.m:175), which cannot
     be reproduced; per BASELINE.json's north star the search is re-expressed as LP feasibility: the same
-    bisection (and the same 'longer of odd/even' selection, :222-226) with fir_linprog probes.  a_min is
-    fir_pm's minimum-amplitude option and has no LP counterpart; it is accepted and ignored."""
-    return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: _fir_linprog_decided(nt, f, a, d, hw, dbg, **solver_kw),
+    bisection (and the same 'longer of odd/even' selection, :222-226) with fir_linprog probes.  a_min is fir_pm's lower
+    bound of the response in the transition regions (ss/fir_pm.m:42-43,102: default min(0, min(a - d)), which is also the
+    LP's default, fir_linprog.m:165-170); a given value replaces that bound in every probe."""
+    kw = dict(solver_kw)
+    if a_min is not None and np.size(a_min):
+        kw["a_min"] = float(a_min)
+    return _min_order_search(int(n), f, a, d, even_odd, lambda nt, hw: _fir_linprog_decided(nt, f, a, d, hw, dbg, **kw),
                              pick_longer=True)
 
 

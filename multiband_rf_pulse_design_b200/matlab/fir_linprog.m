@@ -1,9 +1,11 @@
-function [h, status, info] = fir_linprog(n, f, a, d, h0, dbg) %#ok<INUSD>
+function [h, status, info] = fir_linprog(n, f, a, d, h0, dbg, a_min) %#ok<INUSL>
 %FIR_LINPROG  Drop-in for the toolbox's ss/fir_linprog.m (same signature, status strings and tap layout): the LP
 %     min fmin*x  s.t.  [A; -A] x <= [U, -L]                                   (ss/fir_linprog.m:221-252)
 %  goes to libmbrf's interior-point solver on the GPU (fir_solve_mex) instead of MATLAB's linprog.  h0 is the reference's
 %  starting point for linprog's medium-scale algorithm (:157); an interior-point method starts from its own centred point,
 %  so h0 does not change the result and is not used.  info (third output) is the solver's 8-vector (status code first).
+%  a_min (optional 7th argument, used by fir_min_order.m): lower bound of the response in the transition regions
+%  (ss/fir_pm.m:42-43,102); default min(0, min(L)) as in ss/fir_linprog.m:165-170.
 f = reshape(f, 1, []) * pi;   a = reshape(a, 1, []);   d = reshape(d, 1, []);      % :46
 real_filter = ~(min(f) < 0);                                                       % :48-52
 odd = mod(n, 2) == 1;                                                              % :56-60
@@ -25,7 +27,8 @@ end
 tranidx = find(~inband);                                                           % :163-171
 w = [w(bandidx), w(tranidx)];                                                      % :175-180
 hi = [U, repmat(max(U), 1, numel(tranidx))].';                                     % :221-226 (amplitude, not power)
-lo = [L, repmat(min(0, min(L)), 1, numel(tranidx))].';
+if nargin < 7 || isempty(a_min), a_min = min(0, min(L)); end
+lo = [L, repmat(a_min, 1, numel(tranidx))].';
 if odd                                                                             % :195-217
     kc = 1:nhalf-1;
     ctype = [0, ones(1, nhalf-1)];   kappa = [0, kc];   amp = [1, 2*ones(1, nhalf-1)];

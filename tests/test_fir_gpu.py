@@ -131,6 +131,33 @@ def test_fir_linprog_vs_highs(mbrf, case):
     assert np.abs(h - np.conj(h[::-1])).max() < 1e-12
 
 
+def test_fir_linprog_h0_is_a_warm_start_for_the_first_order_solver(mbrf):
+    """h0 (ss/fir_linprog.m:157, fill_opt_param :298-373): with method="pdhg" the previous filter is the starting iterate --
+    same optimum, fewer iterations; with the interior-point solver it is accepted and unused."""
+    k = LPK["lp_cplx_even_n40"]
+    h, st, ex = mbrf.fir_linprog(k["n"], k["f"], k["a"], k["d"], return_info=True, method="pdhg")
+    assert st == "Solved"
+    h2, st2, ex2 = mbrf.fir_linprog(k["n"], k["f"], k["a"], k["d"], h, return_info=True, method="pdhg")
+    assert st2 == "Solved" and abs(ex2["info"][2] - ex["info"][2]) <= 2 * TOL_OBJ * abs(ex["info"][2])
+    assert ex2["info"][1] < ex["info"][1]
+    h3, st3, ex3 = mbrf.fir_linprog(k["n"], k["f"], k["a"], k["d"], h, return_info=True, method="ipm")
+    assert st3 == "Solved" and abs(ex3["info"][2] - k["obj"]) <= TOL_OBJ * abs(k["obj"])
+
+
+def test_fir_min_order_a_min_bounds_the_transition_response(mbrf):
+    """a_min of ss/fir_min_order.m:14 (ss/fir_pm.m:42-43,102): the response in the transition regions stays above it.  Default
+    is min(0, min(a - d)) = -0.01 here; a_min = 0 is honoured by the returned filter and cannot make it shorter."""
+    k = LPK["minorder_real_n40"]
+    h0, st0 = mbrf.fir_min_order(k["n"], k["f"], k["a"], k["d"], 1, None, 0)
+    h1, st1 = mbrf.fir_min_order(k["n"], k["f"], k["a"], k["d"], 1, 0.0, 0)
+    assert st0 == st1 == "Solved" and h1.size >= h0.size == k["linprog_len"]
+    wt = np.linspace(k["f"][1], k["f"][2], 400)[1:-1] * np.pi
+    resp = lambda h: np.real(np.exp(-1j * np.outer(wt, np.arange(h.size) - (h.size - 1) / 2)) @ h)   # noqa: E731
+    assert resp(h1).min() >= -1e-4
+    h2, st2 = mbrf.fir_linprog(h0.size, k["f"], k["a"], k["d"], a_min=0.5)      # the transition cannot stay above 0.5 down to the stop band
+    assert st2 == "Failed"
+
+
 def test_fir_linprog_failures(mbrf):
     k = LPK["lp_real_odd_n11_infeasible"]
     h, st = mbrf.fir_linprog(k["n"], k["f"], k["a"], k["d"], max_iter=40000)

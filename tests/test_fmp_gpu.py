@@ -69,3 +69,16 @@ def test_fir_ap_cvx_returns_the_reference_taps(mbrf):
     for b in range(2):
         ref = x_to_h_reference(ex["x"][b], 40)
         assert np.abs(hs[b] - ref).max() <= 1e-10
+
+
+@pytest.mark.gpu
+def test_fmp2_kernel_recovers_known_minimum_phase_filters(mbrf):
+    """Known answer (not a comparison with the restatement): the spectral factor of the autocorrelation of a filter with all
+    zeros well inside the unit circle is the filter itself (tests/test_oracle_fir.py pins the restatement the same way)."""
+    from test_oracle_fir import MINPHASE_CASES, _minimum_phase_case
+    from multiband_rf_pulse_design_b200 import fir
+    for n, rad, tol in MINPHASE_CASES:
+        cases = [_minimum_phase_case(n, rad, seed=n + 100 * k) for k in range(4)]
+        H = fir.fmp2_batch(np.stack([r for _, r in cases]))
+        for (h0, _), h in zip(cases, H):
+            assert np.abs(h - h0).max() < tol

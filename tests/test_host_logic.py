@@ -115,3 +115,21 @@ def test_set_solver_options_names_and_ranges():
         fir.set_solver_options(min_restart_interval=0)
     with pytest.raises(ValueError):
         fir.set_solver_options(tc_digits=9)
+
+
+def test_fill_opt_param_inverts_fill_h():
+    """ss/fir_linprog.m: fill_opt_param (:298-373) maps a previous filter h0 to the optimisation vector, fill_h (:274-296) maps
+    the vector to the filter -- for a filter of the same length they are inverses, for a shorter one the taps that fit are copied."""
+    from multiband_rf_pulse_design_b200 import fir
+    rng = np.random.default_rng(0)
+    for n, f in ((21, [0, 0.3, 0.5, 1]), (20, [0, 0.3, 0.5, 0.9]), (21, [-0.8, -0.5, -0.2, 0.3, 0.5, 0.9]), (20, [-0.8, -0.5, -0.2, 0.3, 0.5, 0.9])):
+        nb = len(f) // 2
+        p = fir.assemble_fir_linprog(n, f, [1, 1, 0, 0, 0, 0][:2 * nb], [0.1] * nb)
+        x = rng.standard_normal(p["col_type"].size)
+        h = fir._fill_h(x, p)
+        assert h.size == n and np.array_equal(fir._fill_opt_param(h, p), x)
+        assert fir._fill_opt_param(h[:-1], p) is None and fir._fill_opt_param(None, p) is None      # other parity / no h0: FFT init
+        ps = fir.assemble_fir_linprog(n - 4, f, [1, 1, 0, 0, 0, 0][:2 * nb], [0.1] * nb)          # a shorter previous filter
+        xs = rng.standard_normal(ps["col_type"].size)
+        x0 = fir._fill_opt_param(fir._fill_h(xs, ps), p)
+        assert np.abs(fir._fill_h(x0, p)[2:-2] - fir._fill_h(xs, ps)).max() == 0 and np.all(fir._fill_h(x0, p)[[0, 1, -2, -1]] == 0)

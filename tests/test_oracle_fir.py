@@ -67,3 +67,38 @@ def test_numpy_qp_twin_matches_scipy_reference():
     assert iters < 100000
     assert abs(objective_fir_qp(p, x) - k["objective"]) <= 1e-4 * k["objective"]
     assert violation_fir_qp(p, x) <= 1e-6
+
+
+def _minimum_phase_case(n, rad, seed):
+    """A filter with all zeros inside |z| <= rad < 1 (angles spread around the circle, so the spectrum has no deep null and
+    the cepstrum does not alias on the 8x padded grid) and its autocorrelation: the spectral factor of r is h0 itself."""
+    from oracle.fir_post import poly_reference
+    rng = np.random.default_rng(seed)
+    ang = 2 * np.pi * (np.arange(n - 1) + rng.uniform(-0.3, 0.3, n - 1)) / (n - 1)
+    z = rng.uniform(0.2, rad, n - 1) * np.exp(1j * ang)
+    h0 = poly_reference(z[rng.permutation(n - 1)])
+    h0 = h0 / np.abs(h0).max()
+    return h0, np.correlate(h0, h0, mode="full")
+
+
+MINPHASE_CASES = ((16, 0.7, 1e-13), (33, 0.8, 1e-12), (64, 0.85, 1e-10), (128, 0.85, 1e-9), (256, 0.9, 1e-6))
+
+
+def test_fmp2_restatement_recovers_known_minimum_phase_filters():
+    """Known answer for fmp2 (fir_ap_cvx.m:262-283): the minimum-phase spectral factor is unique, so for a filter whose zeros
+    all lie inside the unit circle fmp2(autocorrelation) must return the filter itself -- to rounding where the log-spectrum is
+    smooth (measured 1e-16 ... 4e-12 up to n = 128, 4e-9 at n = 256 with zeros out to 0.9)."""
+    from oracle.fir_problems import fmp2_reference
+    for n, rad, tol in MINPHASE_CASES:
+        for k in range(4):
+            h0, r = _minimum_phase_case(n, rad, seed=n + 100 * k)
+            assert np.abs(fmp2_reference(r) - h0).max() < tol
+
+
+def test_mag2mp_of_fmp2_is_the_function_pinned_through_b2a():
+    """fir_ap_cvx.m:292-303 (local mag2mp) and rf_tools/mag2mp.m are the same text; the restatement used by b2a_m is pinned to
+    the reference's compiled b2rf (tests/test_oracle.py), and the one used by fmp2_reference is bit-identical to it."""
+    from oracle import ref
+    from oracle.fir_problems import mag2mp_reference
+    x = np.abs(np.random.default_rng(1).standard_normal(4096)) + 0.05
+    assert np.array_equal(mag2mp_reference(x), ref.mag2mp_m(x))
