@@ -639,6 +639,18 @@ def fir_ap_cvx_sweep(n, f, a, d, objs, peaks, f_adds, rank=0, world=1, batch=512
                                  [ol[i] for i in ids], int(stride), **solver_kw)
         return _solve_batch_ap(n, designs, **solver_kw)
 
+    # Batch composition.  A batch runs in lockstep until its slowest design is done, and the designs of this grid fall into
+    # groups with very different iteration counts (infeasible: certificate after ~17 iterations; solved: ~45; edge of
+    # feasibility: 70-100).  What decides the group is mostly Peak and the band edges, not the weight, so the local instances
+    # are ordered by (Peak, band edges, weight) before they are cut into batches: batches of hopeless Peak values end early
+    # instead of waiting for the stragglers of a mixed batch.  Results are returned in the order of `index` either way.
+    # The batches with the largest Peak (the ones with solvable designs and stragglers) go first, so that the short batches fill
+    # the end of the schedule when several batches are in flight.
+    order = solver_kw.pop("order", "grouped")
+    if order in ("grouped", "grouped_ascending") and mine.size > batch:
+        sign = -1.0 if order == "grouped" else 1.0
+        key = sorted(range(mine.size), key=lambda k: (sign * pl[mine[k]], tuple(fl[mine[k]]), ol[mine[k]]))
+        mine = mine[np.array(key, dtype=int)]
     chunks = [mine[b0:b0 + batch] for b0 in range(0, mine.size, batch)]
     if concurrent > 1 and len(chunks) > 1 and (solver_kw.get("method") or DEFAULT_METHOD) == "ipm":
         # interior point: the per-design kernels (Cholesky, triangular solves) of a batch leave SMs idle once most of its designs
@@ -659,8 +671,9 @@ def fir_ap_cvx_sweep(n, f, a, d, objs, peaks, f_adds, rank=0, world=1, batch=512
     for x, t, info in results:
         xs.append(x); ts.append(t); infos.append(info)
     cat = lambda v, w: np.concatenate(v) if v else np.zeros((0, w))   # noqa: E731
-    return dict(index=mine, x=cat(xs, 2 * n - 1), ripple_stop=np.concatenate(ts) if ts else np.zeros(0),
-                info=cat(infos, 8))
+    back = np.argsort(mine, kind="stable")                # results in ascending instance order, whatever the batch composition
+    return dict(index=mine[back], x=cat(xs, 2 * n - 1)[back], ripple_stop=(np.concatenate(ts) if ts else np.zeros(0))[back],
+                info=cat(infos, 8)[back])
 
 
 def _solve_seeded(n, designs, fkeys, peaks, objs, stride, **solver_kw):
