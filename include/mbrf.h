@@ -328,7 +328,8 @@ int mbrf_fir_ap_assemble(int n, int nband, const double *f, const double *a, con
 int mbrf_ipm_padded_sizes(int M, int N, int B, int *Mp, int *Np, int *Bp);
 /* 0: precision of the Newton systems (0 fp64, 1 double-double, 2 auto = double-double once mu < switch * mu0; default 2),
  * 1: that switch (default 1e-3), 2: refinement steps per solve in the double-double phase (default 1), 3: trace the first `value`
- * designs on stderr, 4: refinement steps per solve in the fp64 phase (default 0) */
+ * designs on stderr, 4: refinement steps per solve in the fp64 phase (default 0), 5: the factorisation is split over many CTAs
+ * per matrix when at most `value` designs of a batch are still running (default -1 = two thirds of the SMs, 0 = never) */
 int mbrf_ipm_set_option(int which, double value);
 /* Diagnostic: the batched Cholesky of the interior-point solver alone -- B matrices of order nv, double-double (use_dd) or
  * fp64, timed with CUDA events over `reps` launches (mean ms per launch): the kernel bench.py's solver roofline is quoted on. */

@@ -43,6 +43,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <type_traits>
 #include <vector>
 
 namespace mbrf {
@@ -800,6 +801,16 @@ __global__ void keep_best_kernel(P p)
     for (int j = blockIdx.y; j < p.N; j += gridDim.y) p.XB[(size_t)j * p.Bp + b] = p.x[(size_t)j * p.Bp + b];
 }
 
+// live[0 .. count) = the designs still running (any order); also commits the pivot failures the split factorisation of the
+// previous iteration flagged (the one-CTA kernel counts them itself)
+__global__ void live_list_kernel(P p, int *__restrict__ live, int *__restrict__ count, int *__restrict__ failflag)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    if (failflag[b]) { p.ctl[b].chol_fail += 1.0; failflag[b] = 0; }
+    if (p.ctl[b].status == 0.0) live[atomicAdd(count, 1)] = b;
+}
+
 __global__ void fill_kernel(double *a, long long n, double v)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -885,6 +896,7 @@ assemble_kernel(P p, const T *__restrict__ MC, const T *__restrict__ MS, const T
     const int b = blockIdx.x;
     T *H = Hall + (size_t)b * p.NVp * p.NVp;
     const bool live = b < p.B && p.ctl[b].status == 0.0;
+    if (!live) return;                                           // the factorisation and the solves skip finished designs too
     const int NV = p.NV, NVp = p.NVp, N = p.N, Bp = p.Bp;
     auto mom = [&](const T *m, int nlag, int lag) {
         T s = m[(size_t)lag * Bp + b];
@@ -945,6 +957,139 @@ assemble_kernel(P p, const T *__restrict__ MC, const T *__restrict__ MS, const T
 // batched Cholesky, one CTA of 256 threads per design: right-looking, 32-wide panels, 64 x 64 trailing tiles
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int CHOL_THREADS = 512;   // 16 warps: 4 per scheduler keep the FP64 pipe issuing through the long dd dependency chains
+
+// The three stages of one panel step k0 of the right-looking factorisation, shared by the one-CTA-per-design kernel and by the
+// split kernels (few designs left: one design's work spread over many CTAs).  NT = CHOL_THREADS threads.
+// (1) diagonal block: load, factor in shared memory (Ld stays valid for the caller), store
+template <typename T>
+__device__ __forceinline__ void chol_diag_block(T *__restrict__ H, int n, int k0, T *Ld, int *fail)
+{
+    constexpr int LDS_ = PANEL + 1, NT = CHOL_THREADS;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < PANEL * PANEL; e += NT) {
+        const int r = e / PANEL, c = e % PANEL;
+        Ld[r * LDS_ + c] = c <= r ? H[(size_t)(k0 + r) * n + k0 + c] : Num<T>::zero();
+    }
+    __syncthreads();
+    for (int j = 0; j < PANEL; ++j) {
+        if (tid == 0) {
+            T d = Ld[j * LDS_ + j];
+            if (!Num<T>::positive(d)) { *fail = 1; d = Num<T>::from(1e-300); }
+            Ld[j * LDS_ + j] = Num<T>::sqrt_(d);
+        }
+        __syncthreads();
+        if (tid > j && tid < PANEL) Ld[tid * LDS_ + j] = Num<T>::div(Ld[tid * LDS_ + j], Ld[j * LDS_ + j]);
+        __syncthreads();
+        // trailing part of the block: entries (r, c), j < c <= r < PANEL
+        for (int e = tid; e < PANEL * PANEL; e += NT) {
+            const int r = e / PANEL, c = e % PANEL;
+            if (c > j && c <= r) Ld[r * LDS_ + c] = Num<T>::fnma(Ld[r * LDS_ + j], Ld[c * LDS_ + j], Ld[r * LDS_ + c]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < PANEL * PANEL; e += NT) {
+        const int r = e / PANEL, c = e % PANEL;
+        if (c <= r) H[(size_t)(k0 + r) * n + k0 + c] = Ld[r * LDS_ + c];
+    }
+}
+
+// (2) panel rows [r0, r0 + nr) below the block, nr <= 256: X L11' = A21.  Two threads per row: the pair splits every inner sum
+// in halves.  Ld: the factored diagonal block in shared memory.
+template <typename T>
+__device__ __forceinline__ void chol_panel_rows(T *__restrict__ H, int n, int k0, int r0, int nr, const T *Ld, T *Xs)
+{
+    constexpr int LDS_ = PANEL + 1, NT = CHOL_THREADS;
+    const int tid = threadIdx.x;
+    __syncthreads();
+    for (int e = tid; e < nr * PANEL; e += NT) {
+        const int r = e / PANEL, c = e % PANEL;
+        Xs[r * LDS_ + c] = H[(size_t)(k0 + PANEL + r0 + r) * n + k0 + c];
+    }
+    __syncthreads();
+    {
+        const int row = tid >> 1, half = tid & 1;
+        T *xr = Xs + (row < nr ? row : 0) * LDS_;
+        for (int j = 0; j < PANEL; ++j) {
+            // partial sums over l = half, half + 2, ... < j, combined through a shuffle of the pair
+            T s = Num<T>::zero();
+            if (row < nr)
+                for (int l = half; l < j; l += 2) s = Num<T>::fnma_acc(xr[l], Ld[j * LDS_ + l], s);
+            s = Num<T>::renorm(s);
+            T o;
+            if constexpr (sizeof(T) == sizeof(dd)) {
+                o.hi = __shfl_xor_sync(0xffffffffu, s.hi, 1);
+                o.lo = __shfl_xor_sync(0xffffffffu, s.lo, 1);
+            } else {
+                o = __shfl_xor_sync(0xffffffffu, s, 1);
+            }
+            if (row < nr && half == 0) xr[j] = Num<T>::div(Num<T>::add(xr[j], Num<T>::add(s, o)), Ld[j * LDS_ + j]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nr * PANEL; e += NT) {
+        const int r = e / PANEL, c = e % PANEL;
+        H[(size_t)(k0 + PANEL + r0 + r) * n + k0 + c] = Xs[r * LDS_ + c];
+    }
+}
+
+// (3) one 64 x 64 tile (ti, tj), tj <= ti, of the trailing update A22[I][J] -= P[I] P[J]'; thread = 4 x 2 outputs
+template <typename T>
+__device__ __forceinline__ void chol_update_tile(T *__restrict__ H, int n, int k0, int ti, int tj, T *Xs)
+{
+    constexpr int NT = CHOL_THREADS;
+    const int tid = threadIdx.x;
+    T *Pi = Xs, *Pj = Xs + PANEL * TILE;                 // k-major: [PANEL][TILE]
+    const int base = k0 + PANEL;
+    const int ty = tid >> 5, tx = tid & 31;              // a warp shares its 4 rows (broadcast), lane tx owns columns tx and tx + 32 (conflict-free 16-byte loads)
+    __syncthreads();
+    for (int e = tid; e < TILE * PANEL; e += NT) {
+        const int r = e / PANEL, c = e % PANEL;
+        const int gi = base + ti * TILE + r, gj = base + tj * TILE + r;
+        Pi[c * TILE + r] = gi < n ? H[(size_t)gi * n + k0 + c] : Num<T>::zero();
+        Pj[c * TILE + r] = gj < n ? H[(size_t)gj * n + k0 + c] : Num<T>::zero();
+    }
+    __syncthreads();
+    T acc[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gi = base + ti * TILE + ty * 4 + i, gj = base + tj * TILE + tx + 32 * j;
+            acc[i][j] = (gi < n && gj <= gi) ? H[(size_t)gi * n + gj] : Num<T>::zero();
+        }
+    // on a diagonal tile the warps whose rows lie in its upper half own no entry of the columns tx + 32 (above the diagonal)
+    const bool upper_half_of_diag = ti == tj && ty < 8;
+    if (upper_half_of_diag) {
+#pragma unroll 8
+        for (int k = 0; k < PANEL; ++k) {
+            const T b0 = Pj[k * TILE + tx];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][0] = Num<T>::fnma_acc(Pi[k * TILE + ty * 4 + i], b0, acc[i][0]);
+        }
+    } else {
+#pragma unroll 8
+        for (int k = 0; k < PANEL; ++k) {
+            T a[4], bb[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Pi[k * TILE + ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bb[j] = Pj[k * TILE + tx + 32 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) acc[i][j] = Num<T>::fnma_acc(a[i], bb[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gi = base + ti * TILE + ty * 4 + i, gj = base + tj * TILE + tx + 32 * j;
+            if (gi < n && gj <= gi) H[(size_t)gi * n + gj] = Num<T>::renorm(acc[i][j]);
+        }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
 cholesky_kernel(P p, T *__restrict__ Hall)
@@ -954,134 +1099,66 @@ cholesky_kernel(P p, T *__restrict__ Hall)
     if (b >= p.B || p.ctl[b].status != 0.0) return;
     T *H = Hall + (size_t)b * p.NVp * p.NVp;
     const int n = p.NVp, tid = threadIdx.x;
-    constexpr int LDS_ = PANEL + 1, NT = CHOL_THREADS;
+    constexpr int LDS_ = PANEL + 1;
     T *Ld = reinterpret_cast<T *>(smem_raw);                 // [PANEL][PANEL+1] diagonal block
     T *Xs = Ld + PANEL * LDS_;                               // [256][PANEL+1] panel rows / [2][PANEL][TILE] update tiles
     __shared__ int fail;
     if (tid == 0) fail = 0;
     for (int k0 = 0; k0 < n; k0 += PANEL) {
-        // ---- diagonal block ----
-        for (int e = tid; e < PANEL * PANEL; e += NT) {
-            const int r = e / PANEL, c = e % PANEL;
-            Ld[r * LDS_ + c] = c <= r ? H[(size_t)(k0 + r) * n + k0 + c] : Num<T>::zero();
-        }
-        __syncthreads();
-        for (int j = 0; j < PANEL; ++j) {
-            if (tid == 0) {
-                T d = Ld[j * LDS_ + j];
-                if (!Num<T>::positive(d)) { fail = 1; d = Num<T>::from(1e-300); }
-                Ld[j * LDS_ + j] = Num<T>::sqrt_(d);
-            }
-            __syncthreads();
-            if (tid > j && tid < PANEL) Ld[tid * LDS_ + j] = Num<T>::div(Ld[tid * LDS_ + j], Ld[j * LDS_ + j]);
-            __syncthreads();
-            // trailing part of the block: entries (r, c), j < c <= r < PANEL
-            for (int e = tid; e < PANEL * PANEL; e += NT) {
-                const int r = e / PANEL, c = e % PANEL;
-                if (c > j && c <= r) Ld[r * LDS_ + c] = Num<T>::fnma(Ld[r * LDS_ + j], Ld[c * LDS_ + j], Ld[r * LDS_ + c]);
-            }
-            __syncthreads();
-        }
-        for (int e = tid; e < PANEL * PANEL; e += NT) {
-            const int r = e / PANEL, c = e % PANEL;
-            if (c <= r) H[(size_t)(k0 + r) * n + k0 + c] = Ld[r * LDS_ + c];
-        }
+        chol_diag_block<T>(H, n, k0, Ld, &fail);
         const int rows = n - k0 - PANEL;
         if (rows <= 0) break;
-        // ---- panel: X L11' = A21.  Two threads per row (256 rows per pass): the pair splits every inner sum in halves ----
-        for (int r0 = 0; r0 < rows; r0 += 256) {
-            const int nr = min(256, rows - r0);
-            __syncthreads();
-            for (int e = tid; e < nr * PANEL; e += NT) {
-                const int r = e / PANEL, c = e % PANEL;
-                Xs[r * LDS_ + c] = H[(size_t)(k0 + PANEL + r0 + r) * n + k0 + c];
-            }
-            __syncthreads();
-            {
-                const int row = tid >> 1, half = tid & 1;
-                T *xr = Xs + (row < nr ? row : 0) * LDS_;
-                for (int j = 0; j < PANEL; ++j) {
-                    // partial sums over l = half, half + 2, ... < j, combined through a shuffle of the pair
-                    T s = Num<T>::zero();
-                    if (row < nr)
-                        for (int l = half; l < j; l += 2) s = Num<T>::fnma_acc(xr[l], Ld[j * LDS_ + l], s);
-                    s = Num<T>::renorm(s);
-                    T o;
-                    if constexpr (sizeof(T) == sizeof(dd)) {
-                        o.hi = __shfl_xor_sync(0xffffffffu, s.hi, 1);
-                        o.lo = __shfl_xor_sync(0xffffffffu, s.lo, 1);
-                    } else {
-                        o = __shfl_xor_sync(0xffffffffu, s, 1);
-                    }
-                    if (row < nr && half == 0) xr[j] = Num<T>::div(Num<T>::add(xr[j], Num<T>::add(s, o)), Ld[j * LDS_ + j]);
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-            for (int e = tid; e < nr * PANEL; e += NT) {
-                const int r = e / PANEL, c = e % PANEL;
-                H[(size_t)(k0 + PANEL + r0 + r) * n + k0 + c] = Xs[r * LDS_ + c];
-            }
-        }
+        for (int r0 = 0; r0 < rows; r0 += 256) chol_panel_rows<T>(H, n, k0, r0, min(256, rows - r0), Ld, Xs);
         __syncthreads();
-        // ---- trailing update: A22[I][J] -= P[I] P[J]', tiles of 64 x 64, thread = 4 x 2 outputs ----
-        T *Pi = Xs, *Pj = Xs + PANEL * TILE;                 // k-major: [PANEL][TILE]
-        const int base = k0 + PANEL;
         const int nt = (rows + TILE - 1) / TILE;
-        const int ty = tid >> 5, tx = tid & 31;              // a warp shares its 4 rows (broadcast), lane tx owns columns tx and tx + 32 (conflict-free 16-byte loads)
         for (int ti = 0; ti < nt; ++ti)
-            for (int tj = 0; tj <= ti; ++tj) {
-                __syncthreads();
-                for (int e = tid; e < TILE * PANEL; e += NT) {
-                    const int r = e / PANEL, c = e % PANEL;
-                    const int gi = base + ti * TILE + r, gj = base + tj * TILE + r;
-                    Pi[c * TILE + r] = gi < n ? H[(size_t)gi * n + k0 + c] : Num<T>::zero();
-                    Pj[c * TILE + r] = gj < n ? H[(size_t)gj * n + k0 + c] : Num<T>::zero();
-                }
-                __syncthreads();
-                T acc[4][2];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int gi = base + ti * TILE + ty * 4 + i, gj = base + tj * TILE + tx + 32 * j;
-                        acc[i][j] = (gi < n && gj <= gi) ? H[(size_t)gi * n + gj] : Num<T>::zero();
-                    }
-                // on a diagonal tile the warps whose rows lie in its upper half own no entry of the columns tx + 32 (above the diagonal)
-                const bool upper_half_of_diag = ti == tj && ty < 8;
-                if (upper_half_of_diag) {
-#pragma unroll 8
-                    for (int k = 0; k < PANEL; ++k) {
-                        const T b0 = Pj[k * TILE + tx];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[i][0] = Num<T>::fnma_acc(Pi[k * TILE + ty * 4 + i], b0, acc[i][0]);
-                    }
-                } else {
-#pragma unroll 8
-                    for (int k = 0; k < PANEL; ++k) {
-                        T a[4], bb[2];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) a[i] = Pi[k * TILE + ty * 4 + i];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) bb[j] = Pj[k * TILE + tx + 32 * j];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) acc[i][j] = Num<T>::fnma_acc(a[i], bb[j], acc[i][j]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int gi = base + ti * TILE + ty * 4 + i, gj = base + tj * TILE + tx + 32 * j;
-                        if (gi < n && gj <= gi) H[(size_t)gi * n + gj] = Num<T>::renorm(acc[i][j]);
-                    }
-            }
+            for (int tj = 0; tj <= ti; ++tj) chol_update_tile<T>(H, n, k0, ti, tj, Xs);
         __syncthreads();
     }
     __syncthreads();
     if (tid == 0 && fail) p.ctl[b].chol_fail += 1.0;
+}
+
+// Split factorisation for the late iterations of a batch and for single designs: with fewer live designs than SMs the
+// one-CTA-per-design kernel leaves the GPU idle while every matrix takes its full single-SM latency (5.5 ms at order 512 in
+// double-double).  Here one panel step is three launches whose grids spread ONE design's work over many CTAs:
+// stage 0 the diagonal block (one CTA per design), stage 1 the panel rows in chunks of 256 (grid.y chunks), stage 2 the
+// trailing tiles (grid.y = tile pairs).  `live` lists the designs still running.
+template <typename T>
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
+cholesky_split_kernel(P p, T *__restrict__ Hall, const int *__restrict__ live, int k0, int stage, int *__restrict__ failflag)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = live[blockIdx.x];
+    T *H = Hall + (size_t)b * p.NVp * p.NVp;
+    const int n = p.NVp, tid = threadIdx.x;
+    constexpr int LDS_ = PANEL + 1;
+    T *Ld = reinterpret_cast<T *>(smem_raw);
+    T *Xs = Ld + PANEL * LDS_;
+    const int rows = n - k0 - PANEL;
+    if (stage == 0) {
+        __shared__ int fail;
+        if (tid == 0) fail = 0;
+        __syncthreads();
+        chol_diag_block<T>(H, n, k0, Ld, &fail);
+        __syncthreads();
+        if (tid == 0 && fail) failflag[b] = 1;                    // committed once per factorisation by live_list_kernel
+    } else if (stage == 1) {
+        const int r0 = blockIdx.y * 256;
+        if (r0 >= rows) return;
+        for (int e = tid; e < PANEL * PANEL; e += CHOL_THREADS) {
+            const int r = e / PANEL, c = e % PANEL;
+            Ld[r * LDS_ + c] = c <= r ? H[(size_t)(k0 + r) * n + k0 + c] : Num<T>::zero();
+        }
+        chol_panel_rows<T>(H, n, k0, r0, min(256, rows - r0), Ld, Xs);
+    } else {
+        // tile pair index -> (ti, tj), tj <= ti
+        int t = blockIdx.y, ti = 0;
+        while (t > ti) { t -= ti + 1; ++ti; }
+        const int nt = (rows + TILE - 1) / TILE;
+        if (ti >= nt) return;
+        chol_update_tile<T>(H, n, k0, ti, t, Xs);
+    }
 }
 
 // solve L L' u = rhs for system r of every live design: rhs = (RHS[r] | DXV , RHST[r]) -> (UX[r] | DXV, UT[r] | RHST)
@@ -1187,6 +1264,7 @@ static int g_precision = 2;          // 0 fp64, 1 double-double, 2 auto (double-
 static double g_dd_switch = 1e-3;    // auto: double-double when min over live designs of mu / mu0 falls below this
 static int g_refine = 1, g_refine_fp64 = 0;
 static int g_verbose = 0;
+static int g_split_max = -1;         // split factorisation when at most this many designs are running (-1: 2/3 of the SMs, 0: never)
 
 // Device-side input / output of a solve (mbrf_fir_ap_solve): `fill` writes c, bl, bu, lo, hi, rho, ct of the padded problem
 // with kernels instead of an upload; `after` sees the solutions x [Np x Bp] (caller's units) and info [Bp x 8] on the device
@@ -1213,6 +1291,7 @@ int mbrf_ipm_set_option(int which, double value)
     case 2: if (value < 0 || value > 4) return MBRF_EINVAL; g_refine = (int)value; break;
     case 3: g_verbose = (int)value; break;
     case 4: if (value < 0 || value > 4) return MBRF_EINVAL; g_refine_fp64 = (int)value; break;
+    case 5: if (value < -1 || value > 1e6) return MBRF_EINVAL; g_split_max = (int)value; break;
     default: return MBRF_EINVAL;
     }
     return MBRF_OK;
@@ -1354,6 +1433,7 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
     need(16 * (size_t)Np * Bp * 8);                              // split-K slabs of K' y
     need(colsz + (size_t)Bp * 64);                               // z_out, info
     need(hooks ? hooks->extra_bytes : 0);
+    need(2 * (size_t)Bp * 4 + 256);                              // live list, pivot-failure flags, counter
     if (int rc = scratch.reserve(total + (1 << 20))) return rc;
     char *dptr = (char *)scratch.ptr;
     auto take = [&](size_t b) { char *q = dptr; dptr += al(b); return q; };
@@ -1400,6 +1480,8 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
     double *dslab = (double *)take(16 * (size_t)Np * Bp * 8);
     double *dzout = (double *)take(colsz), *dinfo = (double *)take((size_t)Bp * 64);
     void *dextra = hooks && hooks->extra_bytes ? take(hooks->extra_bytes) : nullptr;
+    int *dlive = (int *)take(2 * (size_t)Bp * 4 + 256), *dfailflag = dlive + Bp, *dlivecount = dfailflag + Bp;
+    MBRF_CUDA(cudaMemsetAsync(dlive, 0, 2 * (size_t)Bp * 4 + 256, st));
 
     // ---- upload ----
     std::vector<double> h;
@@ -1513,6 +1595,8 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
     const size_t sm_trs_dd = (size_t)(NVp + PANEL * (PANEL + 1)) * sizeof(dd), sm_trs_d = (size_t)(NVp + PANEL * (PANEL + 1)) * sizeof(double);
     MBRF_CUDA(cudaFuncSetAttribute(cholesky_kernel<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_dd));
     MBRF_CUDA(cudaFuncSetAttribute(cholesky_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_d));
+    MBRF_CUDA(cudaFuncSetAttribute(cholesky_split_kernel<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_dd));
+    MBRF_CUDA(cudaFuncSetAttribute(cholesky_split_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_d));
     // a constant limit: concurrent host threads (order searches) solve different sizes, and the attribute is per function
     constexpr int SM_TRS_MAX = 200 * 1024;
     if (sm_trs_dd > (size_t)SM_TRS_MAX) { set_error("fir_ipm_solve: %d variables exceed the triangular-solve kernel", N); return MBRF_EINVAL; }
@@ -1520,7 +1604,35 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
     MBRF_CUDA(cudaFuncSetAttribute(trsolve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TRS_MAX));
 
     bool use_dd = g_precision == 1;
+    // Split factorisation (cholesky_split_kernel) once fewer designs are running than about 2/3 of the SMs: three launches per
+    // panel step spread each matrix over many CTAs instead of leaving it to the latency of one SM.
+    const int split_max = g_split_max >= 0 ? g_split_max : (2 * nsm) / 3;
+    auto chol_split = [&](auto *Hptr, size_t smem) -> int {
+        using T = std::remove_pointer_t<decltype(Hptr)>;
+        const int L = hactive;
+        for (int k0 = 0; k0 < NVp; k0 += PANEL) {
+            cholesky_split_kernel<T><<<dim3(L, 1), CHOL_THREADS, smem, st>>>(p, Hptr, dlive, k0, 0, dfailflag);
+            MBRF_LAUNCH_CHECK();
+            const int rows = NVp - k0 - PANEL;
+            if (rows <= 0) break;
+            cholesky_split_kernel<T><<<dim3(L, (rows + 255) / 256), CHOL_THREADS, smem, st>>>(p, Hptr, dlive, k0, 1, dfailflag);
+            MBRF_LAUNCH_CHECK();
+            const int nt = (rows + TILE - 1) / TILE;
+            cholesky_split_kernel<T><<<dim3(L, nt * (nt + 1) / 2), CHOL_THREADS, smem, st>>>(p, Hptr, dlive, k0, 2, dfailflag);
+            MBRF_LAUNCH_CHECK();
+        }
+        return MBRF_OK;
+    };
+    auto chol_split_dd = [&]() -> int { return chol_split((dd *)dH, sm_chol_dd); };
+    auto chol_split_d = [&]() -> int { return chol_split((double *)dH, sm_chol_d); };
+    bool split = false;
     auto factor = [&]() -> int {
+        split = hactive > 0 && hactive <= split_max;
+        if (split || g_split_max != 0) {                         // the live list also commits pivot failures flagged by the split kernels
+            MBRF_CUDA(cudaMemsetAsync(dlivecount, 0, 4, st));
+            live_list_kernel<<<(B + 255) / 256, 256, 0, st>>>(p, dlive, dlivecount, dfailflag);
+            MBRF_LAUNCH_CHECK();
+        }
         const dim3 gm((Bp + 31) / 32, (nlagM + 7) / 8, nsplit_hint), gb((Bp + 31) / 32, (nlagB + 7) / 8, 1);
         int ay = (int)(((long long)NVp * NVp + 255) / 256);
         if (ay > 64) ay = 64;
@@ -1530,16 +1642,16 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
             if (p.ns) { moments_kernel<dd><<<gb, 256, 0, st>>>(p, p.DS, p.srow0, p.srow0 + p.ns, nlagB, (dd *)dBC, (dd *)dBS); MBRF_LAUNCH_CHECK(); }
             assemble_kernel<dd><<<dim3(B, ay), 256, 0, st>>>(p, (dd *)dMC, (dd *)dMS, (dd *)dBC, (dd *)dBS, nsplit_hint, nlagM, nlagB, (dd *)dH);
             MBRF_LAUNCH_CHECK();
-            cholesky_kernel<dd><<<B, CHOL_THREADS, sm_chol_dd, st>>>(p, (dd *)dH);
-            MBRF_LAUNCH_CHECK();
+            if (split) { if (int rc = chol_split_dd()) return rc; }
+            else { cholesky_kernel<dd><<<B, CHOL_THREADS, sm_chol_dd, st>>>(p, (dd *)dH); MBRF_LAUNCH_CHECK(); }
         } else {
             moments_kernel<double><<<gm, 256, 0, st>>>(p, p.D, 0, M, nlagM, (double *)dMC, (double *)dMS);
             MBRF_LAUNCH_CHECK();
             if (p.ns) { moments_kernel<double><<<gb, 256, 0, st>>>(p, p.DS, p.srow0, p.srow0 + p.ns, nlagB, (double *)dBC, (double *)dBS); MBRF_LAUNCH_CHECK(); }
             assemble_kernel<double><<<dim3(B, ay), 256, 0, st>>>(p, (double *)dMC, (double *)dMS, (double *)dBC, (double *)dBS, nsplit_hint, nlagM, nlagB, (double *)dH);
             MBRF_LAUNCH_CHECK();
-            cholesky_kernel<double><<<B, CHOL_THREADS, sm_chol_d, st>>>(p, (double *)dH);
-            MBRF_LAUNCH_CHECK();
+            if (split) { if (int rc = chol_split_d()) return rc; }
+            else { cholesky_kernel<double><<<B, CHOL_THREADS, sm_chol_d, st>>>(p, (double *)dH); MBRF_LAUNCH_CHECK(); }
         }
         return MBRF_OK;
     };
