@@ -687,8 +687,15 @@ __global__ void scalars_kernel(P p, int phase, int r, int iter)
         if (iter == 0 || prog < 0.5 * ct.merit_ref) { ct.merit_ref = prog; ct.iter_ref = iter; }
         const bool stalled = iter - ct.iter_ref > 30.0;       // no halving of the merit in 30 iterations: a design at the edge of
                                                               // feasibility that neither converges nor yields a certificate
+        // Farkas certificate h'z < 0, ||G'z|| / (-h'z) <= feastol.  Once the embedding has collapsed (tau / kap -> 0: the
+        // signature of infeasibility; tau then falls 100x per iteration) the iterate no longer improves and the quotient sits
+        // at the accuracy of the fp64 products -- 1e-7 give or take a rounding, so a fixed 1e-7 is met in one run and missed in
+        // the next (C-13 spec, n = 50: status 2 at iteration 39, at 47, or never).  There the test takes 100 x feastol, as the
+        // dual residual does above; without the collapse the strict tolerance stands.
+        const double cert = hz < 0.0 ? sqrt(acc[A_GTZ2 * Bp + b] + gtzt * gtzt) / (-hz) : INFINITY;
+        const bool collapsed = tau <= 1e-8 * kap;
         if (merit <= 1.0) st = 1;
-        else if (hz < 0.0 && sqrt(acc[A_GTZ2 * Bp + b] + gtzt * gtzt) / (-hz) <= p.feastol) st = 2;
+        else if (cert <= p.feastol || (collapsed && cert <= 100.0 * p.feastol)) st = 2;
         else if (cx < 0.0 && sqrt(acc[A_GXS2 * Bp + b]) / (-cx) <= p.feastol) st = 4;
         else if (iter >= p.max_iter || stalled || ct.chol_fail > 2.0 || merit == INFINITY || (ct.merit_best <= 10.0 && merit > 1e3 * ct.merit_best)) {
             st = 3;
@@ -962,13 +969,16 @@ constexpr int CHOL_THREADS = 512;   // 16 warps: 4 per scheduler keep the FP64 p
 // split kernels (few designs left: one design's work spread over many CTAs).  NT = CHOL_THREADS threads.
 // (1) diagonal block: load, factor in shared memory (Ld stays valid for the caller), store
 template <typename T>
-__device__ __forceinline__ void chol_diag_block(T *__restrict__ H, int n, int k0, T *Ld, int *fail)
+__device__ __forceinline__ void chol_diag_block(T *__restrict__ H, int n, int k0, T *Ld, int *fail, T *Xi, T *__restrict__ Xout)
 {
+    // Xi [PANEL][PANEL+1] (shared): inv(L11), built by the same elimination steps applied to the identity -- row j of the
+    // inverse is final once column j of L11 is; the triangular solves then multiply by it instead of substituting serially.
     constexpr int LDS_ = PANEL + 1, NT = CHOL_THREADS;
     const int tid = threadIdx.x;
     for (int e = tid; e < PANEL * PANEL; e += NT) {
         const int r = e / PANEL, c = e % PANEL;
         Ld[r * LDS_ + c] = c <= r ? H[(size_t)(k0 + r) * n + k0 + c] : Num<T>::zero();
+        Xi[r * LDS_ + c] = Num<T>::from(r == c ? 1.0 : 0.0);
     }
     __syncthreads();
     for (int j = 0; j < PANEL; ++j) {
@@ -979,17 +989,20 @@ __device__ __forceinline__ void chol_diag_block(T *__restrict__ H, int n, int k0
         }
         __syncthreads();
         if (tid > j && tid < PANEL) Ld[tid * LDS_ + j] = Num<T>::div(Ld[tid * LDS_ + j], Ld[j * LDS_ + j]);
+        else if (tid >= PANEL && tid - PANEL <= j) Xi[j * LDS_ + tid - PANEL] = Num<T>::div(Xi[j * LDS_ + tid - PANEL], Ld[j * LDS_ + j]);
         __syncthreads();
-        // trailing part of the block: entries (r, c), j < c <= r < PANEL
+        // trailing part of the block: entries (r, c), j < c <= r < PANEL; inverse: rows r > j, columns c <= j
         for (int e = tid; e < PANEL * PANEL; e += NT) {
             const int r = e / PANEL, c = e % PANEL;
             if (c > j && c <= r) Ld[r * LDS_ + c] = Num<T>::fnma(Ld[r * LDS_ + j], Ld[c * LDS_ + j], Ld[r * LDS_ + c]);
+            else if (r > j && c <= j) Xi[r * LDS_ + c] = Num<T>::fnma(Ld[r * LDS_ + j], Xi[j * LDS_ + c], Xi[r * LDS_ + c]);
         }
         __syncthreads();
     }
     for (int e = tid; e < PANEL * PANEL; e += NT) {
         const int r = e / PANEL, c = e % PANEL;
         if (c <= r) H[(size_t)(k0 + r) * n + k0 + c] = Ld[r * LDS_ + c];
+        if (Xout) Xout[e] = Xi[r * LDS_ + c];
     }
 }
 
@@ -1092,12 +1105,13 @@ __device__ __forceinline__ void chol_update_tile(T *__restrict__ H, int n, int k
 
 template <typename T>
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
-cholesky_kernel(P p, T *__restrict__ Hall)
+cholesky_kernel(P p, T *__restrict__ Hall, T *__restrict__ Xall)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     if (b >= p.B || p.ctl[b].status != 0.0) return;
     T *H = Hall + (size_t)b * p.NVp * p.NVp;
+    T *Xinv = Xall + (size_t)b * p.NVp * PANEL;                // [NVp / PANEL][PANEL][PANEL]: inverses of the diagonal blocks
     const int n = p.NVp, tid = threadIdx.x;
     constexpr int LDS_ = PANEL + 1;
     T *Ld = reinterpret_cast<T *>(smem_raw);                 // [PANEL][PANEL+1] diagonal block
@@ -1105,7 +1119,7 @@ cholesky_kernel(P p, T *__restrict__ Hall)
     __shared__ int fail;
     if (tid == 0) fail = 0;
     for (int k0 = 0; k0 < n; k0 += PANEL) {
-        chol_diag_block<T>(H, n, k0, Ld, &fail);
+        chol_diag_block<T>(H, n, k0, Ld, &fail, Xs, Xinv + (size_t)k0 * PANEL);
         const int rows = n - k0 - PANEL;
         if (rows <= 0) break;
         for (int r0 = 0; r0 < rows; r0 += 256) chol_panel_rows<T>(H, n, k0, r0, min(256, rows - r0), Ld, Xs);
@@ -1126,7 +1140,8 @@ cholesky_kernel(P p, T *__restrict__ Hall)
 // trailing tiles (grid.y = tile pairs).  `live` lists the designs still running.
 template <typename T>
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
-cholesky_split_kernel(P p, T *__restrict__ Hall, const int *__restrict__ live, int k0, int stage, int *__restrict__ failflag)
+cholesky_split_kernel(P p, T *__restrict__ Hall, T *__restrict__ Xall, const int *__restrict__ live, int k0, int stage,
+                      int *__restrict__ failflag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = live[blockIdx.x];
@@ -1140,7 +1155,7 @@ cholesky_split_kernel(P p, T *__restrict__ Hall, const int *__restrict__ live, i
         __shared__ int fail;
         if (tid == 0) fail = 0;
         __syncthreads();
-        chol_diag_block<T>(H, n, k0, Ld, &fail);
+        chol_diag_block<T>(H, n, k0, Ld, &fail, Xs, Xall + ((size_t)b * p.NVp + k0) * PANEL);
         __syncthreads();
         if (tid == 0 && fail) failflag[b] = 1;                    // committed once per factorisation by live_list_kernel
     } else if (stage == 1) {
@@ -1162,41 +1177,60 @@ cholesky_split_kernel(P p, T *__restrict__ Hall, const int *__restrict__ live, i
 }
 
 // solve L L' u = rhs for system r of every live design: rhs = (RHS[r] | DXV , RHST[r]) -> (UX[r] | DXV, UT[r] | RHST)
-// One CTA per design; 32-wide blocks: the diagonal block is solved by warp 0 out of shared memory, the rest of the
-// right-hand side is updated by all threads.
+// One CTA per design; 32-wide blocks.  The diagonal blocks are applied through their inverses (built by the factorisation):
+// a 32 x 32 triangular matrix-vector product, 8 threads per output, instead of 32 serial substitution steps with a divide
+// each -- the serial version was 60 % of a single design's solve time (profiles/r2_ipm_single_launches_summary.txt).
+template <typename T>
+__device__ __forceinline__ T shfl_xor_num(T v, int m)
+{
+    if constexpr (sizeof(T) == sizeof(dd)) {
+        dd o;
+        o.hi = __shfl_xor_sync(0xffffffffu, v.hi, m);
+        o.lo = __shfl_xor_sync(0xffffffffu, v.lo, m);
+        return o;
+    } else {
+        return __shfl_xor_sync(0xffffffffu, v, m);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-trsolve_kernel(P p, const T *__restrict__ Hall, const double *rhs, const double *rhst, double *out, double *outt, int accumulate_t)
+trsolve_kernel(P p, const T *__restrict__ Hall, const T *__restrict__ Xall, const double *rhs, const double *rhst, double *out,
+               double *outt, int accumulate_t)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     if (b >= p.B || p.ctl[b].status != 0.0) return;
     const T *H = Hall + (size_t)b * p.NVp * p.NVp;
+    const T *Xinv = Xall + (size_t)b * p.NVp * PANEL;
     const int n = p.NVp, tid = threadIdx.x, N = p.N, Bp = p.Bp;
     constexpr int LDS_ = PANEL + 1;
     T *v = reinterpret_cast<T *>(smem_raw);                  // [n]
-    T *Ld = v + n;                                           // [PANEL][PANEL+1]
+    T *Ld = v + n;                                           // [PANEL][PANEL+1]: inverse of the current diagonal block
+    T *yb = Ld + PANEL * LDS_;                               // [PANEL]
     for (int i = tid; i < n; i += 256)
         v[i] = Num<T>::from(i < N ? rhs[(size_t)i * Bp + b] : i == N ? rhst[b] : 0.0);
     __syncthreads();
+    const int orow = tid >> 3, part = tid & 7;               // 8 threads per output of the block product
     // forward: L y = v
     for (int k0 = 0; k0 < n; k0 += PANEL) {
-        for (int e = tid; e < PANEL * PANEL; e += 256) {
-            const int r = e / PANEL, c = e % PANEL;
-            Ld[r * LDS_ + c] = c <= r ? H[(size_t)(k0 + r) * n + k0 + c] : Num<T>::zero();
+        for (int e = tid; e < PANEL * PANEL; e += 256) Ld[(e / PANEL) * LDS_ + e % PANEL] = Xinv[(size_t)k0 * PANEL + e];
+        __syncthreads();
+        {
+            T s = Num<T>::zero();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = part * 4 + q;
+                if (c <= orow) s = Num<T>::fnma_acc(Ld[orow * LDS_ + c], Num<T>::neg(v[k0 + c]), s);
+            }
+            s = Num<T>::renorm(s);
+            s = Num<T>::add(s, shfl_xor_num<T>(s, 1));
+            s = Num<T>::add(s, shfl_xor_num<T>(s, 2));
+            s = Num<T>::add(s, shfl_xor_num<T>(s, 4));
+            if (part == 0) yb[orow] = s;
         }
         __syncthreads();
-        if (tid < PANEL) {
-            T mine = v[k0 + tid];
-            for (int j = 0; j < PANEL; ++j) {
-                T yj;
-                if (tid == j) { mine = Num<T>::div(mine, Ld[j * LDS_ + j]); v[k0 + j] = mine; }
-                __syncwarp();
-                yj = v[k0 + j];
-                if (tid > j) mine = Num<T>::fnma(Ld[tid * LDS_ + j], yj, mine);
-                __syncwarp();
-            }
-        }
+        if (tid < PANEL) v[k0 + tid] = yb[tid];
         __syncthreads();
         for (int i = k0 + PANEL + tid; i < n; i += 256) {
             T s = v[i];
@@ -1209,22 +1243,23 @@ trsolve_kernel(P p, const T *__restrict__ Hall, const double *rhs, const double 
     }
     // backward: L' u = y
     for (int k0 = n - PANEL; k0 >= 0; k0 -= PANEL) {
-        for (int e = tid; e < PANEL * PANEL; e += 256) {
-            const int r = e / PANEL, c = e % PANEL;
-            Ld[r * LDS_ + c] = c <= r ? H[(size_t)(k0 + r) * n + k0 + c] : Num<T>::zero();
+        for (int e = tid; e < PANEL * PANEL; e += 256) Ld[(e / PANEL) * LDS_ + e % PANEL] = Xinv[(size_t)k0 * PANEL + e];
+        __syncthreads();
+        {
+            T s = Num<T>::zero();                            // u_c = sum_{r >= c} Xinv[r][c] v_r
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = part * 4 + q;
+                if (r >= orow) s = Num<T>::fnma_acc(Ld[r * LDS_ + orow], Num<T>::neg(v[k0 + r]), s);
+            }
+            s = Num<T>::renorm(s);
+            s = Num<T>::add(s, shfl_xor_num<T>(s, 1));
+            s = Num<T>::add(s, shfl_xor_num<T>(s, 2));
+            s = Num<T>::add(s, shfl_xor_num<T>(s, 4));
+            if (part == 0) yb[orow] = s;
         }
         __syncthreads();
-        if (tid < PANEL) {
-            T mine = v[k0 + tid];
-            for (int j = PANEL - 1; j >= 0; --j) {
-                T uj;
-                if (tid == j) { mine = Num<T>::div(mine, Ld[j * LDS_ + j]); v[k0 + j] = mine; }
-                __syncwarp();
-                uj = v[k0 + j];
-                if (tid < j) mine = Num<T>::fnma(Ld[j * LDS_ + tid], uj, mine);
-                __syncwarp();
-            }
-        }
+        if (tid < PANEL) v[k0 + tid] = yb[tid];
         __syncthreads();
         for (int c = tid; c < k0; c += 256) {
             T s = v[c];
@@ -1308,8 +1343,9 @@ int mbrf_ipm_cholesky_bench(int nv, int B, int use_dd, int reps, float *ms)
     p.NV = nv; p.NVp = up(nv, PANEL); p.B = B; p.Bp = B;
     const size_t tsz = use_dd ? sizeof(dd) : sizeof(double), hb = (size_t)B * p.NVp * p.NVp * tsz;
     char *buf = nullptr;
-    MBRF_CUDA(cudaMalloc(&buf, 2 * hb + (size_t)B * sizeof(Ctl)));
-    p.ctl = (Ctl *)(buf + 2 * hb);
+    const size_t xb = (size_t)B * p.NVp * PANEL * tsz;           // inverses of the diagonal blocks (built by the same kernel)
+    MBRF_CUDA(cudaMalloc(&buf, 2 * hb + xb + (size_t)B * sizeof(Ctl)));
+    p.ctl = (Ctl *)(buf + 2 * hb + xb);
     MBRF_CUDA(cudaMemset(p.ctl, 0, (size_t)B * sizeof(Ctl)));
     const long long ne = (long long)B * p.NVp * p.NVp;
     if (use_dd) spd_fill_kernel<dd><<<(unsigned)((ne + 255) / 256), 256>>>((dd *)buf, p.NVp, B);
@@ -1325,8 +1361,8 @@ int mbrf_ipm_cholesky_bench(int nv, int B, int use_dd, int reps, float *ms)
     for (int r = 0; r <= reps; ++r) {                            // first pass: warm-up
         MBRF_CUDA(cudaMemcpyAsync(buf + hb, buf, hb, cudaMemcpyDeviceToDevice, 0));
         MBRF_CUDA(cudaEventRecord(e0, 0));
-        if (use_dd) cholesky_kernel<dd><<<B, CHOL_THREADS, sm>>>(p, (dd *)(buf + hb));
-        else cholesky_kernel<double><<<B, CHOL_THREADS, sm>>>(p, (double *)(buf + hb));
+        if (use_dd) cholesky_kernel<dd><<<B, CHOL_THREADS, sm>>>(p, (dd *)(buf + hb), (dd *)(buf + 2 * hb));
+        else cholesky_kernel<double><<<B, CHOL_THREADS, sm>>>(p, (double *)(buf + hb), (double *)(buf + 2 * hb));
         MBRF_LAUNCH_CHECK();
         MBRF_CUDA(cudaEventRecord(e1, 0));
         MBRF_CUDA(cudaEventSynchronize(e1));
@@ -1430,6 +1466,7 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
     need((size_t)NACC * Bp * 8 + (size_t)Bp * sizeof(Ctl) + 256);
     need(2 * (size_t)nsplit_hint * nlagM * Bp * tsz + 2 * (size_t)nsplit_hint * nlagB * Bp * tsz);   // moments
     need((size_t)B * NVp * NVp * tsz);                           // normal matrices
+    need((size_t)B * NVp * PANEL * tsz);                         // inverses of the diagonal blocks of the factors
     need(16 * (size_t)Np * Bp * 8);                              // split-K slabs of K' y
     need(colsz + (size_t)Bp * 64);                               // z_out, info
     need(hooks ? hooks->extra_bytes : 0);
@@ -1477,6 +1514,7 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
     void *dMC = take((size_t)nsplit_hint * nlagM * Bp * tsz), *dMS = take((size_t)nsplit_hint * nlagM * Bp * tsz);
     void *dBC = take((size_t)nsplit_hint * nlagB * Bp * tsz), *dBS = take((size_t)nsplit_hint * nlagB * Bp * tsz);
     void *dH = take((size_t)B * NVp * NVp * tsz);
+    void *dXinv = take((size_t)B * NVp * PANEL * tsz);
     double *dslab = (double *)take(16 * (size_t)Np * Bp * 8);
     double *dzout = (double *)take(colsz), *dinfo = (double *)take((size_t)Bp * 64);
     void *dextra = hooks && hooks->extra_bytes ? take(hooks->extra_bytes) : nullptr;
@@ -1592,7 +1630,7 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
     // shared memory of the factorisation kernels
     const size_t sm_chol_dd = (size_t)(PANEL * (PANEL + 1) + 256 * (PANEL + 1)) * sizeof(dd);
     const size_t sm_chol_d = (size_t)(PANEL * (PANEL + 1) + 256 * (PANEL + 1)) * sizeof(double);
-    const size_t sm_trs_dd = (size_t)(NVp + PANEL * (PANEL + 1)) * sizeof(dd), sm_trs_d = (size_t)(NVp + PANEL * (PANEL + 1)) * sizeof(double);
+    const size_t sm_trs_dd = (size_t)(NVp + PANEL * (PANEL + 1) + PANEL) * sizeof(dd), sm_trs_d = (size_t)(NVp + PANEL * (PANEL + 1) + PANEL) * sizeof(double);
     MBRF_CUDA(cudaFuncSetAttribute(cholesky_kernel<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_dd));
     MBRF_CUDA(cudaFuncSetAttribute(cholesky_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_d));
     MBRF_CUDA(cudaFuncSetAttribute(cholesky_split_kernel<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol_dd));
@@ -1611,14 +1649,14 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
         using T = std::remove_pointer_t<decltype(Hptr)>;
         const int L = hactive;
         for (int k0 = 0; k0 < NVp; k0 += PANEL) {
-            cholesky_split_kernel<T><<<dim3(L, 1), CHOL_THREADS, smem, st>>>(p, Hptr, dlive, k0, 0, dfailflag);
+            cholesky_split_kernel<T><<<dim3(L, 1), CHOL_THREADS, smem, st>>>(p, Hptr, (T *)dXinv, dlive, k0, 0, dfailflag);
             MBRF_LAUNCH_CHECK();
             const int rows = NVp - k0 - PANEL;
             if (rows <= 0) break;
-            cholesky_split_kernel<T><<<dim3(L, (rows + 255) / 256), CHOL_THREADS, smem, st>>>(p, Hptr, dlive, k0, 1, dfailflag);
+            cholesky_split_kernel<T><<<dim3(L, (rows + 255) / 256), CHOL_THREADS, smem, st>>>(p, Hptr, (T *)dXinv, dlive, k0, 1, dfailflag);
             MBRF_LAUNCH_CHECK();
             const int nt = (rows + TILE - 1) / TILE;
-            cholesky_split_kernel<T><<<dim3(L, nt * (nt + 1) / 2), CHOL_THREADS, smem, st>>>(p, Hptr, dlive, k0, 2, dfailflag);
+            cholesky_split_kernel<T><<<dim3(L, nt * (nt + 1) / 2), CHOL_THREADS, smem, st>>>(p, Hptr, (T *)dXinv, dlive, k0, 2, dfailflag);
             MBRF_LAUNCH_CHECK();
         }
         return MBRF_OK;
@@ -1643,7 +1681,7 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
             assemble_kernel<dd><<<dim3(B, ay), 256, 0, st>>>(p, (dd *)dMC, (dd *)dMS, (dd *)dBC, (dd *)dBS, nsplit_hint, nlagM, nlagB, (dd *)dH);
             MBRF_LAUNCH_CHECK();
             if (split) { if (int rc = chol_split_dd()) return rc; }
-            else { cholesky_kernel<dd><<<B, CHOL_THREADS, sm_chol_dd, st>>>(p, (dd *)dH); MBRF_LAUNCH_CHECK(); }
+            else { cholesky_kernel<dd><<<B, CHOL_THREADS, sm_chol_dd, st>>>(p, (dd *)dH, (dd *)dXinv); MBRF_LAUNCH_CHECK(); }
         } else {
             moments_kernel<double><<<gm, 256, 0, st>>>(p, p.D, 0, M, nlagM, (double *)dMC, (double *)dMS);
             MBRF_LAUNCH_CHECK();
@@ -1651,13 +1689,13 @@ static int ipm_solve_impl(const double *w_row, int M, const int *col_type, const
             assemble_kernel<double><<<dim3(B, ay), 256, 0, st>>>(p, (double *)dMC, (double *)dMS, (double *)dBC, (double *)dBS, nsplit_hint, nlagM, nlagB, (double *)dH);
             MBRF_LAUNCH_CHECK();
             if (split) { if (int rc = chol_split_d()) return rc; }
-            else { cholesky_kernel<double><<<B, CHOL_THREADS, sm_chol_d, st>>>(p, (double *)dH); MBRF_LAUNCH_CHECK(); }
+            else { cholesky_kernel<double><<<B, CHOL_THREADS, sm_chol_d, st>>>(p, (double *)dH, (double *)dXinv); MBRF_LAUNCH_CHECK(); }
         }
         return MBRF_OK;
     };
     auto trsolve = [&](const double *rhs, const double *rhst, double *out, double *outt, int acc_t) -> int {
-        if (use_dd) trsolve_kernel<dd><<<B, 256, sm_trs_dd, st>>>(p, (const dd *)dH, rhs, rhst, out, outt, acc_t);
-        else trsolve_kernel<double><<<B, 256, sm_trs_d, st>>>(p, (const double *)dH, rhs, rhst, out, outt, acc_t);
+        if (use_dd) trsolve_kernel<dd><<<B, 256, sm_trs_dd, st>>>(p, (const dd *)dH, (const dd *)dXinv, rhs, rhst, out, outt, acc_t);
+        else trsolve_kernel<double><<<B, 256, sm_trs_d, st>>>(p, (const double *)dH, (const double *)dXinv, rhs, rhst, out, outt, acc_t);
         MBRF_LAUNCH_CHECK();
         return MBRF_OK;
     };
