@@ -658,10 +658,11 @@ def fir_ap_cvx_sweep(n, f, a, d, objs, peaks, f_adds, rank=0, world=1, batch=512
         from concurrent.futures import ThreadPoolExecutor
         import ctypes as _C
         dev = _C.c_int(0)
-        check(lib().mbrf_get_device(_C.byref(dev)))
+        have_dev = lib().mbrf_get_device(_C.byref(dev)) == 0   # no device: the solves themselves fail loudly
 
         def run(ids):
-            check(lib().mbrf_set_device(dev.value))
+            if have_dev:                                   # worker threads start on device 0: hand them the caller's device
+                check(lib().mbrf_set_device(dev.value))
             return solve_batch(ids)
         with ThreadPoolExecutor(max_workers=concurrent) as ex:
             results = list(ex.map(run, chunks))

@@ -133,3 +133,37 @@ def test_fill_opt_param_inverts_fill_h():
         xs = rng.standard_normal(ps["col_type"].size)
         x0 = fir._fill_opt_param(fir._fill_h(xs, ps), p)
         assert np.abs(fir._fill_h(x0, p)[2:-2] - fir._fill_h(xs, ps)).max() == 0 and np.all(fir._fill_h(x0, p)[[0, 1, -2, -1]] == 0)
+
+
+def test_sweep_batch_composition_keeps_the_instance_order(monkeypatch):
+    """fir_ap_cvx_sweep composes its batches of designs with similar Peak / band edges (long batches first) and runs several
+    batches from host threads; whatever the composition, results come back in ascending instance order, every instance once,
+    each row belonging to its own design (the solve is stubbed out: host logic only)."""
+    from multiband_rf_pulse_design_b200 import fir
+    seen = []
+
+    def fake(n, f_list, a_list, d_list, obj_list, peak_list, ipm_max_iter=None, want_h=True, oversamp=15):
+        B = len(f_list)
+        seen.append(sorted(set(peak_list)))
+        x = np.zeros((B, 2 * n - 1))
+        x[:, 0], x[:, 1], x[:, 2] = obj_list, peak_list, [f[0] for f in f_list]
+        info = np.ones((B, 8))
+        info[:, 7] = np.asarray(obj_list) * 2
+        return x, None, info, (10, 2)
+    monkeypatch.setattr(fir, "_solve_batch_ap_device", fake)
+    f = np.array([-0.5, -0.2, 0.1, 0.4])
+    objs, peaks, fadds = np.logspace(-2, 2, 5), np.logspace(-4, -2, 4), np.linspace(0, 0.02, 3)
+    fl, ol, pl = fir.sweep_grid(f, objs, peaks, fadds)
+    for world, order, conc in ((1, "grouped", 3), (1, "natural", 0), (2, "grouped", 2), (3, "grouped_ascending", 0)):
+        parts = []
+        for rank in range(world):
+            seen.clear()
+            r = fir.fir_ap_cvx_sweep(8, f, [1, 1, 0, 0], [0.1, 0.1], objs, peaks, fadds, rank=rank, world=world, batch=16,
+                                     order=order, concurrent_batches=conc)
+            assert np.array_equal(r["index"], np.arange(rank, len(fl), world))
+            for k, i in enumerate(r["index"]):
+                assert r["x"][k, 0] == ol[i] and r["x"][k, 1] == pl[i] and r["x"][k, 2] == fl[i][0] and r["ripple_stop"][k] == 2 * ol[i]
+            if order == "grouped" and world == 1:
+                assert all(len(p) <= 2 for p in seen)            # a batch of 16 spans at most two of the four Peak values
+            parts.append(r["index"])
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(len(fl)))
