@@ -1059,11 +1059,15 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, oversamp=10, 
     blocks.group_row0, blocks.group_pairs, blocks.group_w = 2 * m, n, _dp(gw)
     blocks.norm_coords, blocks.norm_w = N, _dp(lam)
     kw = dict(max_iter=MAX_ITER, check_every=CHECK_EVERY, eps_pr=EPS_PR, eps_dr=EPS_DR, eps_gap=EPS_GAP)
-    kw.update(solver_kw)
+    kw.update({k: v for k, v in solver_kw.items() if k != "want_dual"})
     z, info = np.zeros((N, 1)), np.zeros((1, 8))
     arr = lambda v: np.ascontiguousarray(v, dtype=np.float64)            # noqa: E731
     w_row, row_phase, row_scale, col_kappa, col_amp, tv, lo, hi = map(arr, (w_row, row_phase, row_scale, col_kappa,
                                                                              col_amp, tv, lo, hi))
+    y_out = om_out = None
+    if solver_kw.get("want_dual"):                                       # final multipliers [M] (rows as above), for certificates
+        y_out, om_out = np.zeros((M, 1)), np.ones(1)
+        check(lib().mbrf_fir_pdhg_warm_start(None, None, None, _dp(y_out), _dp(om_out)))
     check(lib().mbrf_fir_pdhg_solve2(_dp(w_row), _dp(row_phase), _dp(row_scale), M, _ip(col_type), _dp(col_kappa),
                                      _dp(col_amp), N, 2 * n, _ip(ti), _ip(tj), _dp(tv), None, None, 0, _dp(c), _dp(lo),
                                      _dp(hi), _dp(bl), _dp(bu), None, 1, None, C.byref(blocks), int(kw["max_iter"]),
@@ -1079,5 +1083,8 @@ def fir_qp_cvx(n, f, a, d, k=100, obj=0, dbg=0, return_info=False, oversamp=10, 
     st = "Solved" if ok else "Failed"                                     # :200-206
     if return_info:
         p = dict(p, radius=radius)
-        return h, st, dict(x=x.copy(), info=info[0].copy(), problem=p)
+        ex = dict(x=x.copy(), info=info[0].copy(), problem=p)
+        if y_out is not None:
+            ex["y"] = y_out[:, 0].copy()                                  # rows 2i, 2i+1: the disk of grid point i; then the identity rows
+        return h, st, ex
     return h, st

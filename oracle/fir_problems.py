@@ -343,3 +343,25 @@ def x_to_h_reference(x, n):
     r = np.concatenate([[x[0]], x[1:n] + 1j * x[n:2 * n - 1]])            # :185
     r = np.concatenate([np.conj(r[:0:-1]), r])                            # :186
     return fmp2_reference(r)
+
+
+def peak_lower_bound_fir_qp(p, y_disk):
+    """A RIGOROUS lower bound on Peak = max_i ||(x_i, x_{n+i})|| over the feasible set of the scalar-obj fir_qp_cvx problem
+    (fir_qp_cvx.m:145-166), from ANY multipliers y_i in R^2 of the disk constraints ||A_i x - Hd_i|| <= D_i (build_fir_qp
+    rows), evaluated here on the CPU -- it does not matter where y came from, only how good it is:
+        feasible x:  <y_i, A_i x - Hd_i> >= -D_i ||y_i||   =>   <r, x> >= sum_i (<y_i, Hd_i> - D_i ||y_i||),   r = sum_i A_i' y_i
+        <r, x> <= (sum_pairs ||r_pair||) * max_pairs ||x_pair||                                  (Cauchy-Schwarz per pair)
+        =>  Peak >= sum_i (<y_i, Hd_i> - D_i ||y_i||) / sum_pairs ||(r_k, r_{n+k})||.
+    Since E_total >= 0, obj * (this bound) is a lower bound on the optimal value E_total + obj * Peak.  Both signs of y are
+    tried (the bound is valid for either)."""
+    n, w = p["n"], p["w"]
+    y = np.asarray(y_disk, float).reshape(-1, 2)
+    k = np.arange(n)
+    wk = np.outer(w, k)
+    C, S = np.cos(wk), np.sin(wk)
+    # A_i = [cos sin; -sin cos] (fir_qp_cvx.m:96-109): A_i' y_i = [cos*y0 - sin*y1 ; sin*y0 + cos*y1]
+    r = np.concatenate([C.T @ y[:, 0] - S.T @ y[:, 1], S.T @ y[:, 0] + C.T @ y[:, 1]])
+    den = np.hypot(r[:n], r[n:]).sum()
+    num = (y[:, 0] * p["center"].real + y[:, 1] * p["center"].imag).sum()
+    pen = (p["radius"] * np.hypot(y[:, 0], y[:, 1])).sum()
+    return max(num - pen, -num - pen) / den

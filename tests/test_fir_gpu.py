@@ -197,6 +197,28 @@ def test_fir_qp_cvx_vs_scipy_reference(mbrf, case):
     assert violation_fir_qp(p, x) <= TOL_VIOL
 
 
+def test_fir_qp_cvx_reference_call_is_certified_on_the_cpu(mbrf, solver_method):
+    """BASELINE config 3 on the reference grid: fir_qp_cvx(256, f, a, d, 120, 1e6) (dzrf_mb.m:211-213).  No CPU solver finishes
+    this SOCP in test time, so the answer is bracketed instead of compared: the returned x gives an upper bound on the optimum
+    (objective and every disk recomputed on the CPU), and the returned multipliers of the disk rows give a RIGOROUS lower bound
+    by weak duality, also evaluated on the CPU (oracle.fir_problems.peak_lower_bound_fir_qp: valid for any multipliers, so
+    nothing of the solver's own bookkeeping is trusted).  The optimum lies in between; the bracket is the test."""
+    if solver_method != "pdhg":
+        pytest.skip("fir_qp_cvx runs on the first-order solver only")
+    from oracle.fir_problems import H1_DUALBAND as S, build_fir_qp, objective_fir_qp, peak_lower_bound_fir_qp, violation_fir_qp
+    n, k, obj = 256, 120.0, 1e6
+    h, st, ex = mbrf.fir_qp_cvx(n, S["f"], S["a"], S["d"], k, obj, return_info=True, max_iter=1500000, want_dual=True)
+    assert st == "Solved"
+    p = build_fir_qp(n, S["f"], S["a"], S["d"], k, obj)
+    x = ex["x"]
+    assert violation_fir_qp(p, x) <= TOL_VIOL
+    upper = objective_fir_qp(p, x)
+    lower = obj * peak_lower_bound_fir_qp(p, ex["y"][:2 * p["w"].size])
+    print(f"cfg3 bracket: {lower:.6f} <= optimum <= {upper:.6f}  (relative width {(upper - lower) / upper:.2e})")
+    assert lower <= upper * (1 + 1e-9)
+    assert upper - lower <= TOL_OBJ * upper                               # measured: 8.7e-6 (14864.5427 <= optimum <= 14864.6724)
+
+
 def test_fir_qp_cvx_config3(mbrf):
     """BASELINE config 3: min-energy multiband FIR, N=256, dual-band H-1 spec, k=120 (dzrf_mb.m:211-213)."""
     from oracle.fir_problems import H1_DUALBAND, build_fir_qp, objective_fir_qp, violation_fir_qp

@@ -102,3 +102,29 @@ def test_mag2mp_of_fmp2_is_the_function_pinned_through_b2a():
     from oracle.fir_problems import mag2mp_reference
     x = np.abs(np.random.default_rng(1).standard_normal(4096)) + 0.05
     assert np.array_equal(mag2mp_reference(x), ref.mag2mp_m(x))
+
+
+def test_peak_lower_bound_is_valid_for_any_multipliers():
+    """oracle.fir_problems.peak_lower_bound_fir_qp is a weak-duality bound: whatever the multipliers, it cannot exceed the Peak
+    of a feasible point.  Feasibility by construction: the radii are set so that an arbitrary x0 satisfies every disk."""
+    from oracle.fir_problems import H1_DUALBAND as S, build_fir_qp, peak_lower_bound_fir_qp, response_fir_qp, violation_fir_qp
+    rng = np.random.default_rng(3)
+    n = 24
+    p = build_fir_qp(n, np.array(S["f"]) * 8, S["a"], S["d"], 20.0, 1.0)
+    x0 = rng.standard_normal(2 * n) * 0.05
+    p = dict(p, radius=np.abs(response_fir_qp(p["w"], n, x0) - p["center"]) + rng.uniform(0.0, 0.05, p["w"].size))
+    assert violation_fir_qp(p, x0) == 0.0
+    peak0 = np.hypot(x0[:n], x0[n:]).max()
+    best = -np.inf
+    for trial in range(200):
+        y = rng.standard_normal(2 * p["w"].size) * rng.uniform(0, 1, 2 * p["w"].size) ** 8
+        lb = peak_lower_bound_fir_qp(p, y)
+        assert lb <= peak0 + 1e-12
+        best = max(best, lb)
+    # multipliers pointing from the disk centres towards the response of x0 on the tightest disks give a positive bound
+    H = response_fir_qp(p["w"], n, x0)
+    tight = np.argsort(p["radius"] - np.abs(H - p["center"]))[:5]
+    y = np.zeros((p["w"].size, 2))
+    d = (p["center"] - H)[tight]
+    y[tight, 0], y[tight, 1] = d.real, d.imag
+    assert peak_lower_bound_fir_qp(p, y.ravel()) <= peak0 + 1e-12
