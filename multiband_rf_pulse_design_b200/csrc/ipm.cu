@@ -1953,6 +1953,7 @@ int mbrf_fir_ap_solve(int n, int nband, const double *f, const double *a, const 
     const size_t b_r = al((size_t)B * len * 8), b_h = al((size_t)B * n * 8), b_tw = al((size_t)mbrf_fmp2_workspace_bytes(n));
     hk.extra_bytes = 3 * b_r + 2 * b_h + b_tw;
     hk.fill = [&](const P &p, void *, cudaStream_t st) -> int {
+        if (p.Mp > 65535) { set_error("fir_ap_solve: %d grid rows exceed the assembly kernel's grid (n too large)", p.Mp); return MBRF_EINVAL; }
         ap_fill_rows_kernel<<<dim3((p.Bp + 127) / 128, p.Mp), 128, 0, st>>>(sp, dw, dbase, M1, dsrows, ns, dred, p.Mp, p.Bp,
                                                                              (double *)p.lo, (double *)p.hi);
         MBRF_LAUNCH_CHECK();
@@ -1996,6 +1997,7 @@ int mbrf_fir_ap_assemble(int n, int nband, const double *f, const double *a, con
     if (!lo_out) return MBRF_OK;
     if (!w_row_out || !hi_out || !c_out || !bl_out || !bu_out || !rho_out || !ct_out) { set_error("fir_ap_assemble: output arrays missing"); return MBRF_EINVAL; }
     const int M = pr.M1 + pr.ns, N = 2 * n - 1, np = n - 1;
+    if (M > 65535) { set_error("fir_ap_assemble: %d grid rows exceed the assembly kernel's grid (n too large)", M); return MBRF_EINVAL; }
     static thread_local DeviceScratch out;
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t rb = al((size_t)M * B * 8), cb = al((size_t)N * B * 8), pb = al((size_t)np * B * 8), bb = al((size_t)B * 8);
