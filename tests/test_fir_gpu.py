@@ -215,8 +215,10 @@ def test_fir_qp_cvx_reference_call_is_certified_on_the_cpu(mbrf, solver_method):
     upper = objective_fir_qp(p, x)
     lower = obj * peak_lower_bound_fir_qp(p, ex["y"][:2 * p["w"].size])
     print(f"cfg3 bracket: {lower:.6f} <= optimum <= {upper:.6f}  (relative width {(upper - lower) / upper:.2e})")
-    assert lower <= upper * (1 + 1e-9)
-    assert upper - lower <= TOL_OBJ * upper                               # measured: 8.7e-6 (14864.5427 <= optimum <= 14864.6724)
+    # x satisfies the disks to 1e-6 absolute (7e-5 of the smallest radius), so its objective may undercut the optimum by about
+    # that much: the two bounds may cross by the tolerance, not more
+    assert lower <= upper * (1 + TOL_OBJ)
+    assert abs(upper - lower) <= TOL_OBJ * upper                               # measured: 8.7e-6 (14864.5427 <= optimum <= 14864.6724)
 
 
 def test_fir_qp_cvx_config3(mbrf):
