@@ -211,38 +211,16 @@ H1_DUALBAND = dict(f=[-0.047006, -0.027115, -0.016335, 0.013779, 0.029671, 0.047
 
 
 def c13_bssfp_spec(B0=14.0, n=200, T=4.0, FA=60.0, d1=0.01, d2=0.005):
-    """The band specification of BASELINE config 5, restated from the reference's input script (benchmark input generation,
-    SURVEY.md 2.3 M6): bSSFP_pulse_lp_ap.m:8-64 (urea selected, 5 bands of 0.1 kHz), spectrum_C13.m:27-41 (chemical shifts at B0),
-    rf_bandedge.m:133-161 (edges = centre -+ range/2, normalised by fs/2), rf_ripple_GFA.m:180-260 ('ex': flip-angle range by
-    asin, |B| = sin(theta/2)), dzrf_mb.m:100-110 (a = mid, d = half-range).  Returns f (normalised to [-1,1]), a, d, dt (ms)."""
-    gam = 10.705e6                                                         # spectrum_C13.m:27
-    cs = np.array([170.60, 182.98, 176.32, 178.91, 160.9, 163.13])         # pyr, lac, ala, pyr-H2O, bicarb, urea (:28-33)
-    f0 = gam * B0 * (1 + cs * 1e-6)
-    fhz = f0 - f0[0]                                                       # :38-40
-    pick = np.array([6, 1, 3, 4, 2]) - 1                                   # bSSFP_pulse_lp_ap.m:29: urea pyr ala pyr-H2O lac
+    """The band specification of BASELINE config 5 from the reference's input script bSSFP_pulse_lp_ap.m:8-64 (urea selected, 5 bands
+    of 0.1 kHz, 'ex'), built with the package's mirrors of the specification builders (spec.py: spectrum_C13.m, rf_bandedge.m,
+    rf_ripple_GFA.m, dzrf_mb.m:92-121).  Returns f (normalised to [-1,1]), a, d, dt (ms)."""
+    from multiband_rf_pulse_design_b200 import spec
+    fhz, _ = spec.spectrum_C13(B0)                                         # bSSFP_pulse_lp_ap.m:25
+    pick = np.array([6, 1, 3, 4, 2]) - 1                                   # :29: urea pyr ala pyr-H2O lac
     cf = fhz[pick]
-    mb_fa = np.array([FA, 0, 0, 0, 0])                                     # :52-55 ('urea')
-    mb_rip = np.array([d1, d2, d2, d2, d2])
     cf = (cf - cf[0]) * 1e-3                                               # kHz, selected compound on resonance (:55, :64)
-    dt = T / n                                                             # :68-74 (0.02 ms is a multiple of 4 us)
-    fs = 1.0 / dt
-    rng = 0.1                                                              # mb_range, kHz (:30)
-    f = np.empty(10)
-    f[0::2], f[1::2] = cf - rng / 2, cf + rng / 2                          # rf_bandedge.m:133-141
-    assert np.all(np.diff(f) > 0) and f[0] >= -fs / 2 and f[-1] <= fs / 2  # :146-161
-    a, d = np.zeros(10), np.zeros(5)
-    for i in range(5):                                                     # rf_ripple_asin 'ex' + rf_ripple_FA2Beta
-        fa = np.deg2rad(mb_fa[i])
-        if np.sin(fa) + mb_rip[i] >= 1:
-            r = np.arcsin(np.sin(fa) - mb_rip[i]); lo_, hi_ = r, np.pi - r
-        elif fa <= np.pi / 2:
-            lo_, hi_ = np.arcsin(np.sin(fa) - mb_rip[i]), np.arcsin(np.sin(fa) + mb_rip[i])
-        else:
-            hi_, lo_ = np.pi - np.arcsin(np.sin(fa) - mb_rip[i]), np.pi - np.arcsin(np.sin(fa) + mb_rip[i])
-        bmin, bmax = np.sin(lo_ / 2), np.sin(hi_ / 2)
-        a[2 * i] = a[2 * i + 1] = (bmax + bmin) / 2                        # dzrf_mb.m:105-110
-        d[i] = (bmax - bmin) / 2
-    return f / (fs / 2), a, d, dt
+    out = spec.multiband_spec(n, T / n, list(cf), [0.1] * 5, [FA, 0, 0, 0, 0], [d1, d2, d2, d2, d2], "ex")   # :30, :52-55, :68-74
+    return out["f"], out["a"], out["d"], out["dt"]
 
 
 def leg_cfg4(args, m, lib, rank, world, dev, max_over_ranks, barrier):
