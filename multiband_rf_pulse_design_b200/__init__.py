@@ -21,12 +21,12 @@ and a CUDA device.
 from ._lib import lib, MbrfError, library_path  # noqa: F401
 from .bloch import bloch, blochC, blochH, blochsimfz, GAMMA_C13, GAMMA_H1  # noqa: F401
 from .slr import ab2rf, abr, abrm, abrx, b2a, b2rf  # noqa: F401
-from .fir import (fir_ap, fir_ap_cvx, fir_ap_cvx_batch, fir_linprog, fir_min_order,  # noqa: F401
+from .fir import (fir_ap, fir_ap_cvx, fir_ap_cvx_batch, fir_linprog, fir_min_order, fir_qp,  # noqa: F401
                   fir_min_order_linprog, fir_qp_cvx, fmp2)
 from .fir_post import fir_flip_zero, fir_min_order_qprog_phs, fir_qprog_phs  # noqa: F401
 from .design import dzrf_mb, rfscaleg  # noqa: F401
 from .spec import dinf, multiband_spec, rf_bandedge, rf_Mrange_desired, rf_ripple_GFA, spectrum_C13  # noqa: F401
 
 __all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "b2a", "ab2rf", "b2rf", "fir_ap", "fir_ap_cvx",
-           "fir_ap_cvx_batch", "fir_flip_zero", "fir_qprog_phs", "fir_min_order_qprog_phs", "fir_linprog", "fir_min_order", "fir_min_order_linprog", "fir_qp_cvx", "fmp2", "lib", "MbrfError",
+           "fir_ap_cvx_batch", "fir_qp", "fir_flip_zero", "fir_qprog_phs", "fir_min_order_qprog_phs", "fir_linprog", "fir_min_order", "fir_min_order_linprog", "fir_qp_cvx", "fmp2", "lib", "MbrfError",
            "library_path", "GAMMA_C13", "GAMMA_H1"]

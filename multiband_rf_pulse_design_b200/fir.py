@@ -585,6 +585,90 @@ def _fir_ap_search(n, f, a, d, Peak, min_order, min_tran, dbg, **solver_kw):
     return h, status, n_op, f_op
 
 
+def fir_qp(n, f, a, d, min_order=0, min_tran=0, min_peak=0, dbg=0, **solver_kw):
+    """[h, status] = fir_qp(n, f, a, d, min_order, min_tran, min_peak, dbg) — fir_qp.m:1-150.
+
+    The low-pass relative of fir_ap: every probe is fir_ap_cvx(n, f, a, d, 1e5) (stop-band weight lambda = 1e5, default Peak;
+    fir_qp.m:47,68,92,107,130 -- the function never calls fir_qp_cvx), the transition search moves the single transition of
+    f = [-fp, fp, fs, f4] symmetrically about its centre (:57-85, threshold 1e-3), the order search is the bisection of fir_ap
+    (:103-123).  As in fir_ap the next three levels of each bisection tree are solved as one batch / concurrently and the tree
+    is then walked with the reference's decisions; iteration-limit probes are retried before their 'Failed' is believed."""
+    f = np.asarray(f, float).ravel()
+    lam, df_thre = 1e5, 0.001                                             # fir_qp.m:36-37
+    peak = 1e-3                                                           # fir_ap_cvx's default (fir_ap_cvx.m:33)
+
+    def solve1(nn, ff):
+        hq, sq, _ = fir_ap_cvx_decided(int(nn), [ff], a, d, [lam], [peak], **solver_kw)
+        return (hq[0] if hq[0] is not None else np.zeros(0)), sq[0]
+
+    h, status = solve1(n, f)                                              # :47
+    if status == "Failed":
+        raise RuntimeError("original parameters are too tight")          # :48-50
+    if min_tran > 0:
+        if f.size != 4:
+            raise ValueError("fir_qp's transition search is written for f = [-fp, fp, fs, f4] (fir_qp.m:66-67)")
+        centre = (f[2] + f[1]) / 2                                        # :58
+        top, bot = (f[2] - f[1]) / 2, 0.0                                 # :59-60
+        edges = lambda dfv: np.array([-(centre - dfv), centre - dfv, centre + dfv, f[3]])   # noqa: E731  :64-67
+        while True:
+            # the next three bisection steps can only probe bot + (top - bot) j / 8, j = 1..7: one batch, then the reference's walk
+            span = top - bot
+            nodes = {j: bot + span * j / 8 for j in range(1, 8)}
+            hs, sts, _ = fir_ap_cvx_decided(n, [edges(nodes[j]) for j in range(1, 8)], a, d, [lam] * 7, [peak] * 7, **solver_kw)
+            lo_j, hi_j, done = 0, 8, False
+            for _ in range(3):
+                mid = (lo_j + hi_j) // 2                                  # df_mid = (df_top + df_bot) / 2, :63
+                if sts[mid - 1] == "Failed":
+                    lo_j = mid                                            # :69-71: a narrower transition cannot be designed
+                else:
+                    h, status, hi_j = hs[mid - 1], sts[mid - 1], mid      # :72-76
+                if span * (hi_j - lo_j) / 8 < df_thre:                    # :78-80
+                    done = True
+                    break
+            bot, top = bot + span * lo_j / 8, bot + span * hi_j / 8
+            if done:
+                break
+        if not (0 < min_tran <= 1):
+            raise ValueError("invalid input of min_tran")                 # :97-99
+        df_new = ((f[2] - f[1]) / 2) * (1 - min_tran) + top * min_tran    # :90
+        f = edges(df_new)                                                 # :91-96
+        h, status = solve1(n, f)
+    elif min_tran != 0:
+        raise ValueError("invalid input of min_tran")
+    if min_order > 0:
+        def step(st, solved):                                             # :104-122
+            b_, t_, mid = st
+            if solved:
+                t_ = mid
+            else:
+                b_ = mid
+            return (b_, t_, int(np.ceil((t_ + b_) / 2)) if t_ - b_ > 1 else None)
+
+        state = (2, int(n), int(np.ceil((int(n) + 2) / 2)) if int(n) - 2 > 1 else None)
+        cache = {}
+        while state[2] is not None:
+            need = [q for q in _speculate(state, step, 3) if q not in cache]
+            cache.update(dict(zip(need, _solve_concurrently([(lambda q=q: solve1(q, f)) for q in need]))))
+            for _ in range(3):
+                if state[2] is None:
+                    break
+                h0, st0 = cache[state[2]]
+                if st0 != "Failed":
+                    h, status = h0, st0
+                state = step(state, st0 != "Failed")
+        n_top = state[1]
+        if 0 < min_order < 1:                                             # :128-131
+            h, status = solve1(int(np.ceil(n * (1 - min_order) + n_top * min_order)), f)
+        elif min_order != 1:
+            raise ValueError("invalid input of min_order")                # :132-134
+    elif min_order != 0:
+        raise ValueError("invalid input of min_order")
+    if min_peak and len(h):                                               # :136-146
+        from .fir_post import fir_flip_zero
+        h = fir_flip_zero(h, dbg)
+    return h, status
+
+
 def sweep_grid(f, objs, peaks, f_adds):
     """The trade-off sweep of BASELINE config 4: every combination of the stop-band weight
     `obj`, the peak bound `Peak` and the band-edge expansion `f_add` (fir_ap.m:70-83 widens every band by

@@ -153,3 +153,53 @@ def test_c13_bssfp_order_search_finds_the_reference_order(mbrf):
         warnings.simplefilter("ignore", fir.UndecidedProbe)
         h, st, n_op, _ = mbrf.fir_ap(96, f, a, d, 1e-3, 1, 0, 0, 0, method="ipm")
     assert st == "Solved" and n_op in (57, 58) and h.size == n_op
+
+
+def test_fir_qp_searches_walk_the_reference_bisections(mbrf):
+    """fir_qp.m (every probe is fir_ap_cvx(n, f, a, d, 1e5), :47-130): the batched / speculative searches of the mirror make
+    exactly the decisions of the reference's serial loops (re-run here one probe at a time), and the returned filter meets the
+    specification of the band edges the search ended with."""
+    from multiband_rf_pulse_design_b200 import fir
+    n, f, a, d = 40, np.array([-0.12, 0.12, 0.4, 1.0]), [0.2, 0.2, 0, 0], [0.01, 0.005]
+    lam, peak = 1e5, 1e-3
+
+    def probe(nn, ff):
+        hs, st, _ = fir.fir_ap_cvx_decided(int(nn), [np.asarray(ff, float)], a, d, [lam], [peak])
+        return hs[0], st[0]
+
+    # serial transition search, fir_qp.m:57-96
+    centre, top, bot = (f[2] + f[1]) / 2, (f[2] - f[1]) / 2, 0.0
+    edges = lambda dfv: np.array([-(centre - dfv), centre - dfv, centre + dfv, f[3]])   # noqa: E731
+    assert probe(n, f)[1] == "Solved"
+    while True:
+        mid = (top + bot) / 2
+        if probe(n, edges(mid))[1] == "Failed":
+            bot = mid
+        else:
+            top = mid
+        if top - bot < 0.001:
+            break
+    f_want = edges(((f[2] - f[1]) / 2) * (1 - 0.9) + top * 0.9)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", fir.UndecidedProbe)
+        h, st = mbrf.fir_qp(n, f, a, d, 0, 0.9, 0, 0)
+    assert st == "Solved" and h.size == n
+    w = np.linspace(-np.pi, np.pi, 4001)
+    H = np.abs(np.exp(-1j * np.outer(w, np.arange(n))) @ h)
+    pb = (w >= f_want[0] * np.pi) & (w <= f_want[1] * np.pi)
+    sb = (w >= f_want[2] * np.pi) & (w <= f_want[3] * np.pi)
+    assert H[pb].max() <= 0.2 + 0.01 + 2e-3 and H[pb].min() >= 0.2 - 0.01 - 2e-3 and H[sb].max() <= 0.005 + 2e-3
+    # serial order search, fir_qp.m:103-123
+    n_top, n_bot = n, 2
+    while True:
+        n_mid = int(np.ceil((n_top + n_bot) / 2))
+        if probe(n_mid, f)[1] == "Failed":
+            n_bot = n_mid
+        else:
+            n_top = n_mid
+        if n_top - n_bot == 1:
+            break
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", fir.UndecidedProbe)
+        h2, st2 = mbrf.fir_qp(n, f, a, d, 1, 0, 0, 0)
+    assert st2 == "Solved" and h2.size == n_top
