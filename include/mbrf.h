@@ -154,6 +154,12 @@ int mbrf_bloch_scale_sweep_device(const double *b1real, const double *b1imag,
                                   double *mx, double *my, double *mz, double gamma,
                                   void *workspace, void *stream);
 
+/* host-pointer form of the sweep: constant time step tp (s), b1imag may be NULL, M0 = (0, 0, 1), mode 0;
+ * mx, my, mz: nfreq*nscale doubles, element [i_f + nfreq*i_s] */
+int mbrf_bloch_scale_sweep(const double *b1real, const double *b1imag, int ntime, double tp, double t1, double t2,
+                           const double *dfreq, int nfreq, const double *b1scale, int nscale,
+                           double *mx, double *my, double *mz, double gamma);
+
 /* tuning knobs of the Bloch kernel (0 = automatic): resident CTAs per SM, spins per thread (1|2) */
 int mbrf_bloch_set_tuning(int ctas_per_sm, int spins_per_thread);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
                                _ll, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _d, _vp, _vp]),
     "mbrf_bloch_scale_sweep_device": (_i, [_vp, _vp, _vp, _i, _d, _d, _vp, _i, _vp, _i, _ll, _ll,
                                            _vp, _vp, _vp, _d, _vp, _vp]),
+    "mbrf_bloch_scale_sweep": (_i, [_dp, _dp, _i, _d, _d, _d, _dp, _i, _dp, _i, _dp, _dp, _dp, _d]),
     "mbrf_bloch_set_tuning": (_i, [_i, _i]),
     "mbrf_abr": (_i, [_dp, _dp, _dp, _dp, _i, _dp, _i, _dp, _i, _i, _dp, _dp, _dp, _dp]),
     "mbrf_abr_device": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _ll, _ll,

@@ -176,3 +176,49 @@ int mbrf_bloch(const double *b1r, const double *b1i, int ntime, const double *gr
 }
 
 }  // extern "C"
+
+/*
+ * Host-pointer form of the sweep extension: one call simulates nfreq off-resonances x nscale B1 scalings of ONE pulse
+ * (sim_rf_scale.m:82-89 runs one blochC / blochH call per scale).  b1imag may be NULL; tp is the constant time step (s).
+ * mx, my, mz: nfreq*nscale doubles each, element [i_f + nfreq*i_s].  Magnetisation starts at (0, 0, 1), mode 0 (end point).
+ */
+extern "C" int mbrf_bloch_scale_sweep(const double *b1real, const double *b1imag, int ntime, double tp, double t1, double t2,
+                                      const double *dfreq, int nfreq, const double *b1scale, int nscale, double *mx, double *my,
+                                      double *mz, double gamma)
+{
+    using namespace mbrf;
+    if (int rc = require_device()) return rc;
+    if (ntime <= 0 || nfreq <= 0 || nscale <= 0 || !b1real || !dfreq || !b1scale || !mx || !my || !mz || !(tp > 0.0)) {
+        set_error("bloch sweep: bad arguments (ntime=%d nfreq=%d nscale=%d)", ntime, nfreq, nscale);
+        return MBRF_EINVAL;
+    }
+    static thread_local DeviceScratch scratch;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t nt = (size_t)ntime, ns = (size_t)nfreq * nscale;
+    const size_t wsb = al(mbrf_bloch_workspace_bytes(ntime));
+    if (int rc = scratch.reserve(wsb + 3 * al(nt * 8) + al((size_t)nfreq * 8) + al((size_t)nscale * 8) + 3 * al(ns * 8))) return rc;
+    char *d = (char *)scratch.ptr;
+    void *ws = d; d += wsb;
+    double *dbr = (double *)d; d += al(nt * 8);
+    double *dbi = (double *)d; d += al(nt * 8);
+    double *ddt = (double *)d; d += al(nt * 8);
+    double *ddf = (double *)d; d += al((size_t)nfreq * 8);
+    double *dsc = (double *)d; d += al((size_t)nscale * 8);
+    double *dmx = (double *)d; d += al(ns * 8);
+    double *dmy = (double *)d; d += al(ns * 8);
+    double *dmz = (double *)d;
+    std::vector<double> steps(nt, tp);
+    MBRF_CUDA(cudaMemcpyAsync(dbr, b1real, nt * 8, cudaMemcpyHostToDevice, 0));
+    if (b1imag) MBRF_CUDA(cudaMemcpyAsync(dbi, b1imag, nt * 8, cudaMemcpyHostToDevice, 0));
+    MBRF_CUDA(cudaMemcpyAsync(ddt, steps.data(), nt * 8, cudaMemcpyHostToDevice, 0));
+    MBRF_CUDA(cudaMemcpyAsync(ddf, dfreq, (size_t)nfreq * 8, cudaMemcpyHostToDevice, 0));
+    MBRF_CUDA(cudaMemcpyAsync(dsc, b1scale, (size_t)nscale * 8, cudaMemcpyHostToDevice, 0));
+    MBRF_CUDA(cudaStreamSynchronize(0));                        // `steps` is pageable and goes out of scope with this call
+    if (int rc = mbrf_bloch_scale_sweep_device(dbr, b1imag ? dbi : nullptr, ddt, ntime, t1, t2, ddf, nfreq, dsc, nscale, 0, (long long)ns,
+                                               dmx, dmy, dmz, gamma, ws, nullptr)) return rc;
+    MBRF_CUDA(cudaMemcpyAsync(mx, dmx, ns * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaMemcpyAsync(my, dmy, ns * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaMemcpyAsync(mz, dmz, ns * 8, cudaMemcpyDeviceToHost, 0));
+    MBRF_CUDA(cudaStreamSynchronize(0));
+    return MBRF_OK;
+}

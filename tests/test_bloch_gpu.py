@@ -170,3 +170,26 @@ def test_full_size_sample_vs_oracle(mbrf, oracle):
     for o, w in zip((mx, my, mz), want):
         sub = o[np.ix_(pi, fi)].ravel(order="F")
         assert np.abs(sub - w).max() < TOL_BLOCH
+
+
+@pytest.mark.gpu
+def test_scale_sweep_matches_one_call_per_scale(mbrf, oracle):
+    """The sweep extension (mbrf_bloch_scale_sweep; sim_rf_scale.m:82-89 runs one blochC / blochH call per B1 scaling): every
+    (off-resonance, scale) spin of the single launch equals the oracle (bit-identical to the reference C, tests/test_oracle.py) run once per scale."""
+    g = golden("pulses.npz")
+    b1 = g["b1_cfg1_gauss"]
+    dt = 4e-3 / b1.size
+    df = np.linspace(-3000.0, 3000.0, 301)
+    scales = np.array([0.5, 0.8, 1.0, 1.2, 1.5])
+    for gamma, name in ((mbrf.GAMMA_C13, "C-13"), (mbrf.GAMMA_H1, "H-1")):
+        mx, my, mz = mbrf.bloch_scale_sweep(b1, dt, 1e3, 1e3, df, scales, gamma)
+        assert mx.shape == (scales.size, df.size)
+        for k, sc in enumerate(scales):
+            want = oracle.blochsimfz_oracle(b1 * sc, np.zeros(b1.size), None, None, dt, 1e3, 1e3, df, np.zeros(1), mode=0, gamma=gamma)
+            assert max(np.abs(got[k] - w).max() for got, w in zip((mx, my, mz), want)) < TOL_BLOCH, (name, sc)
+    r = mbrf.sim_rf_scale(b1, dt * 1e3, "pulse", None, "C-13", "ex", 2.0)       # 7-argument form: passband bandwidth in kHz
+    assert r["df"].size == 2048 and r["df"][0] == -6000.0 and r["mz"].shape == (5, 2048) and np.all(r["scale"] == [0.8, 0.9, 1, 1.1, 1.2])
+    mx1, my1, mz1 = mbrf.blochC(b1 * 1.1, np.zeros(b1.size), dt, 1e3, 1e3, r["df"], 0.0, 0)
+    assert np.abs(r["mz"][3] - np.asarray(mz1).ravel()).max() < 1e-12 and np.abs(r["mxy"][3] - (np.asarray(mx1) + 1j * np.asarray(my1)).ravel()).max() < 1e-12
+    with pytest.raises(mbrf.MbrfError):
+        mbrf.bloch_scale_sweep(b1, 0.0, 1e3, 1e3, df, scales)
