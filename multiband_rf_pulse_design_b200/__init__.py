@@ -11,6 +11,7 @@ behaviour) over the C ABI in ``include/mbrf.h`` / ``libmbrf.so``:
     fir_ap_cvx, fir_ap               <- fir_ap_cvx.m, fir_ap.m (solve = batched interior point / restarted PDHG on the GPU)
     fir_flip_zero                    <- fir_flip_zero.m (all flip patterns expanded in one launch)
     fir_qprog_phs, fir_min_order_qprog_phs <- ss/fir_qprog_phs.m, ss/fir_min_order_qprog_phs.m
+    sim_rf_spectral                  <- sim_rf_spectral.m (the spectral profile of a designed pulse, without the figures)
     sim_rf_scale, bloch_scale_sweep  <- sim_rf_scale.m (all B1 scalings x off-resonances in ONE launch of the sweep kernel)
     dzrf_mb, rfscaleg                <- dzrf_mb.m (the design driver: orchestration of the stages above), rf_tools/rfscaleg.m
     rf_ripple_GFA, rf_Mrange_desired, rf_bandedge, dinf, spectrum_C13, multiband_spec <- the specification builders
@@ -26,7 +27,7 @@ from .fir import (fir_ap, fir_ap_cvx, fir_ap_cvx_batch, fir_linprog, fir_min_ord
                   fir_min_order_linprog, fir_qp_cvx, fmp2)
 from .fir_post import fir_flip_zero, fir_min_order_qprog_phs, fir_qprog_phs  # noqa: F401
 from .design import dzrf_mb, rfscaleg  # noqa: F401
-from .sim import bloch_scale_sweep, sim_rf_scale  # noqa: F401
+from .sim import bloch_scale_sweep, sim_rf_scale, sim_rf_spectral  # noqa: F401
 from .spec import dinf, multiband_spec, rf_bandedge, rf_Mrange_desired, rf_ripple_GFA, spectrum_C13  # noqa: F401
 
 __all__ = ["bloch", "blochC", "blochH", "blochsimfz", "abr", "abrm", "abrx", "b2a", "ab2rf", "b2rf", "fir_ap", "fir_ap_cvx",

@@ -60,3 +60,35 @@ def sim_rf_scale(rf, dt, rfname=None, scale=None, nucleus="C-13", ptype="ex", f=
     df = np.linspace(wrange[0], wrange[1], 256 * 8)                        # :76-77
     mx, my, mz = bloch_scale_sweep(np.asarray(rf).ravel(), dt * 1e-3, 1e3, 1e3, df, scale, gamma)   # :82-89
     return dict(df=df, scale=np.asarray(scale, float), mxy=mx + 1j * my, mz=mz)
+
+
+def sim_rf_spectral(rf, dt, rfname=None, nucleus="C-13", ptype="ex", f=None, a=None, d=None, name_cell=None):
+    """sim_rf_spectral(rf, dt, rfname, nucleus, ptype, f, a, d, name_cell) — sim_rf_spectral.m without the figures: the spectral
+    profile of one pulse (or of a list of pulses: the cell-array form of the reference) over 2048 off-resonances, G = 0,
+    T1 = T2 = 1e3 s, M0 = (0, 0, 1) (:62-78).  rf in Gauss, dt in ms.  f alone: passband bandwidth in kHz, range +-3 BW
+    (:33-36); f, a, d: the multiband specification in kHz, range f(1) - 500 Hz .. f(end) + 500 Hz (:37-41).
+    Returns dict(df [Hz], mxy, mz) -- arrays of 2048 points, or lists of them for a list of pulses."""
+    from .bloch import bloch
+    if f is None:
+        raise ValueError("Number of input should be either 4 or 6")       # :46-48
+    if a is None and d is None:
+        bw = float(np.ravel(f)[0]) * 1e3
+        wrange = (-3 * bw, 3 * bw)
+    else:
+        fh = np.asarray(f, float).ravel() * 1e3
+        wrange = (fh[0] - 500, fh[-1] + 500)
+    if nucleus not in ("H-1", "C-13"):
+        raise ValueError("No such option for nucleus. Options are H-1 and C-13")
+    gamma = GAMMA_H1 if nucleus == "H-1" else GAMMA_C13
+    df = np.linspace(wrange[0], wrange[1], 256 * 8)                        # :62-63
+    pulses = list(rf) if isinstance(rf, (list, tuple)) else [rf]
+    dts = list(dt) if isinstance(dt, (list, tuple)) else [dt] * len(pulses)
+    mxy, mzs = [], []
+    for p, t in zip(pulses, dts):
+        p = np.asarray(p).ravel()
+        mx, my, mz = bloch(p, np.zeros(p.size), t * 1e-3, 1e3, 1e3, df, 0.0, 0, gamma=gamma)      # :70-78
+        mxy.append((np.asarray(mx) + 1j * np.asarray(my)).ravel())
+        mzs.append(np.asarray(mz).ravel())
+    if isinstance(rf, (list, tuple)):
+        return dict(df=df, mxy=mxy, mz=mzs)
+    return dict(df=df, mxy=mxy[0], mz=mzs[0])

@@ -83,3 +83,10 @@ def test_dzrf_mb_runs_the_reference_example_script(mbrf, oracle):
         return worst
     # tolerance: |beta| is met to ~2e-3 by the design (Peak cones, SLR hard-pulse approximation), Mz = 1 - 2|beta|^2 moves by 4|beta| times that
     assert bands_met(fn) <= 1e-2, (bands_met(fn), "mirrored axis:", bands_met(-fn))
+    # the same through the mirror of the reference's verification script (sim_rf_spectral.m: 2048 points, f(1)-500 .. f(end)+500 Hz)
+    fk = b_spec["f"] * (fs / 2)                                             # kHz
+    r = mbrf.sim_rf_spectral(rf, dt, "db-specsat", "H-1", "sat", fk, rf_spec["a"], rf_spec["d"])
+    assert r["df"].size == 2048 and r["df"][0] == pytest.approx(fk[0] * 1e3 - 500) and r["mz"].shape == (2048,)
+    mz_i = np.interp(r["df"], df_hz, mz)
+    inside = (r["df"] >= df_hz[0]) & (r["df"] <= df_hz[-1])
+    assert np.abs(r["mz"][inside] - mz_i[inside]).max() < 5e-3             # same profile, other sampling of the axis
