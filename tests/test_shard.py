@@ -102,6 +102,57 @@ def _worker_sweep(rank, world, port, ndesigns, q):
     dist.destroy_process_group()
 
 
+def _worker_sweep_grouped(rank, world, port, q):
+    """fir_ap_cvx_sweep itself (solve stubbed out: no GPU here) with grouped batches and host threads, then the real gather"""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multiband_rf_pulse_design_b200 import fir
+    from multiband_rf_pulse_design_b200.shard import gather_sweep
+
+    def fake(n, f_list, a_list, d_list, obj_list, peak_list, ipm_max_iter=None, want_h=True, oversamp=15):
+        B = len(f_list)
+        x = np.zeros((B, 2 * n - 1))
+        x[:, 0], x[:, 1], x[:, 2] = obj_list, peak_list, [f[0] for f in f_list]
+        info = np.ones((B, 8))
+        info[:, 7] = np.asarray(obj_list) * 2
+        return x, None, info, (10, 2)
+    fir._solve_batch_ap_device = fake
+    n = 6
+    f = np.array([-0.5, -0.2, 0.1, 0.4])
+    objs, peaks, fadds = np.logspace(-2, 2, 5), np.logspace(-4, -2, 3), np.linspace(0, 0.02, 3)
+    fl, ol, pl = fir.sweep_grid(f, objs, peaks, fadds)
+    r = fir.fir_ap_cvx_sweep(n, f, [1, 1, 0, 0], [0.1, 0.1], objs, peaks, fadds, rank=rank, world=world, batch=8, concurrent_batches=3)
+    full = gather_sweep(r, n, len(fl))
+    if rank == 0:
+        ok = np.array_equal(full["index"], np.arange(len(fl)))
+        for i in range(len(fl)):
+            ok = ok and full["x"][i, 0] == ol[i] and full["x"][i, 1] == pl[i] and full["x"][i, 2] == fl[i][0] and full["ripple_stop"][i] == 2 * ol[i]
+        q.put(bool(ok))
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grouped_sweep_and_gather_world2_gloo():
+    """batch composition (designs grouped by Peak / band edges, several batches in flight) must not disturb the partition the
+    gather checks: every instance once, in instance order, each row with its own design's numbers"""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker_sweep_grouped, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
+
+
 @pytest.mark.parametrize("ndesigns", [7, 16])
 def test_sweep_gather_world2_gloo(ndesigns):
     """the final gather of a design sweep (x, ripple_stop, status rows of every instance to rank 0), ragged shares"""
