@@ -16,7 +16,7 @@ MEX = os.path.join(ROOT, "multiband_rf_pulse_design_b200", "matlab")
 @pytest.fixture(scope="module")
 def gateways(mbrf):
     subprocess.check_call(["make", "-s", "-C", MEX, "check"])
-    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "fir_solve", "b2a", "ab2rf", "fmp2", "flip_zero", "fir_ap")}
+    return {n: os.path.join(MEX, n + "_stub.so") for n in ("blochC", "blochH", "abrx", "fir_pdhg", "fir_solve", "b2a", "ab2rf", "fmp2", "flip_zero", "fir_ap", "bloch_sweep")}
 
 
 def test_gateways_link_and_report_errors_like_the_reference(gateways, oracle, mbrf):
@@ -333,3 +333,31 @@ def test_fir_ap_gateway_like_fir_ap_cvx_batch_m(gateways, oracle):
     hs, st, ex = fir.fir_ap_cvx_batch(n, [f], k["a"], k["d"], [k["obj"]], [k["peak"]], return_info=True)
     assert abs(info[2, 0] - ex["info"][0, 2]) <= 1e-7 * abs(ex["info"][0, 2])
     assert np.abs(H[:, 0] - hs[0]).max() < 1e-6
+
+
+def test_bloch_sweep_gateway_usage_errors(gateways, oracle, mbrf):
+    out, err = oracle.mex_call(gateways["bloch_sweep"], 3, np.ones(4), 1e-5)
+    assert out is None and err.startswith("Usage: [mx, my, mz] = bloch_sweep_mex")
+    out, err = oracle.mex_call(gateways["bloch_sweep"], 3, np.ones(4), 1e-5, 1.0, 1.0, np.zeros((0, 0)), np.ones(2), 6726.1)
+    assert out is None and err == "bloch_sweep_mex: b1, df and scale must be non-empty"
+    if mbrf.lib().mbrf_device_count() == 0:
+        out, err = oracle.mex_call(gateways["bloch_sweep"], 3, np.ones(4) * 0.01, 1e-5, 1.0, 1.0, np.zeros(3), np.ones(2), 6726.1)
+        assert out is None and "no CPU path" in err
+
+
+@pytest.mark.gpu
+def test_bloch_sweep_gateway_vs_one_call_per_scale(gateways, oracle, mbrf):
+    """bloch_sweep_mex (sim_rf_scale.m:82-89 as one call): column k equals the blochC gateway called with b1 * scale(k)."""
+    g = golden("pulses.npz")
+    b1 = g["b1_cfg1_gauss"]
+    dt = 4e-3 / b1.size
+    df = np.linspace(-2500.0, 2500.0, 101)
+    scale = np.array([0.8, 1.0, 1.2])
+    outs, err = oracle.mex_call(gateways["bloch_sweep"], 3, b1, dt, 1e3, 1e3, df, scale, 6726.1)
+    assert err is None, err
+    assert outs[0].shape == (df.size, scale.size)
+    for k, sc in enumerate(scale):
+        ref, err = oracle.mex_call(gateways["blochC"], 3, (b1 * sc).reshape(-1, 1), np.zeros((b1.size, 1)), dt, 1e3, 1e3, df, 0.0, 0)
+        assert err is None, err
+        for o, r in zip(outs, ref):
+            assert np.abs(o[:, k] - r.ravel()).max() < 1e-12
